@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py -- IPDG operator-apply throughput (DoF/s, FP64) on N B200s of one node.
+
+A "step" is one pass of the hot path, y = A x, over one synthetic vector on the BASELINE.json
+configs[1] workload: 3-D Poisson SIPG on a 64^3 structured mesh, uniform DG Q3 (16 777 216 DoF per GPU).
+N > 1 is weak scaling: every rank owns a 64^3 brick of a (px,py,pz) mesh and exchanges face traces with
+NCCL each step.  One JSON line on rank 0; see DESIGN.md section 6 for every field.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2|cfg5]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "dune-hpdg_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: (elements per direction per GPU, degree, description)
+    "cfg2": (64, 3, "3D Poisson SIPG, 64^3 YaspGrid-like mesh per GPU, uniform DG Q3, operator apply"),
+    "cfg5": (128, 4, "3D Poisson SIPG, 128^3 elements per GPU, uniform DG Q4, operator apply"),
+}
+PGRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+METRIC = "IPDG matvec DoF/s (3D Q3, FP64)"
+BYTES_PER_DOF = 16  # algorithmic: read x once + write y once
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(pk["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+def ncu_traffic(workload):
+    try:
+        s = json.load(open(os.path.join(ROOT, "profiles", "apply_uniform_ncu_summary.json")))
+        return s.get(workload, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def cpu_reference_rate(n, degree, budget_s, threads=None, min_reps=1):
+    """Time the CPU restatement of the reference's matrix-free apply (Operator::apply over IPDGOperator,
+    /root/reference/dune/hpdg/matrix-free/operator.hh:41, localoperators/ipdgoperator.hh:80) on an n^3 sample."""
+    from oracle import orc
+    threads = threads or orc.max_threads()
+    m = orc.Mesh((n, n, n), degree=degree, sigma=2.0, dirichlet=True)
+    x = orc.fill_random(m.ndof)
+    m.apply_mf(x, threads=threads)  # warm caches
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        m.apply_mf(x, threads=threads)
+        reps += 1
+        el = time.perf_counter() - t0
+        if reps >= min_reps and el >= budget_s:
+            break
+        if reps >= 50:
+            break
+    return m.ndof * reps / el, threads, m.ndof, reps, el
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (here: its plain-C restatement, the
+    reference being uncompilable in this image) on the host cores, all threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import orc
+    nelem_dir, degree, desc = WORKLOADS[args.workload]
+    threads = orc.max_threads()
+    rate, _, _, _, _ = cpu_reference_rate(8, degree, 0.5)
+    per_step = max(0.02, min(2.0, 150.0 / max(1, args.steps + args.warmup)))
+    n = int(round((rate * per_step / (degree + 1) ** 3) ** (1.0 / 3.0)))
+    n = max(4, min(32, n))
+    m = orc.Mesh((n, n, n), degree=degree, sigma=2.0, dirichlet=True)
+    x = orc.fill_random(m.ndof)
+    for _ in range(args.warmup):
+        m.apply_mf(x, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m.apply_mf(x, threads=threads)
+    el = time.perf_counter() - t0
+    val = m.ndof * args.steps / el
+    sample = f"{n}^3 elements Q{degree} ({m.ndof} DoF) per step, matrix-free quadrature-loop apply, {threads} OpenMP threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "DoF/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "DoF/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "DoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-pointer leg (default min(steps, 50))")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:  # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import hpdg_b200 as hp
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    nelem_dir, degree, desc = WORKLOADS[args.workload]
+    n = (nelem_dir,) * 3
+    if world not in PGRID:
+        raise SystemExit(f"unsupported GPU count {world}")
+    pgrid = PGRID[world]
+    # the global domain is [0,px]x[0,py]x[0,pz] so that every brick is a unit cube with h = 1/nelem_dir
+    L = [1.0, 1.0, 1.0]
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            import ctypes
+            buf = ctypes.create_string_buffer(128)
+            assert hp.lib().hpdg_nccl_unique_id(buf) == 0
+            idt = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        ctx = hp.Context(n, L=L, degree=degree, sigma=2.0, dirichlet=True, device=local_rank, pgrid=pgrid, rank=rank,
+                         nranks=world, nccl_id=bytes(idt.cpu().tolist()))
+    else:
+        ctx = hp.Context(n, L=L, degree=degree, sigma=2.0, dirichlet=True, device=local_rank)
+    ndof = ctx.dimension()
+    op = hp.Operator(ctx)
+    assert ctx.uses_uniform_kernel()
+
+    # synthetic input resident in HBM: NBUF (x, y) pairs rotated so no step re-reads what the previous one left in L2
+    NBUF = 3
+    rng = np.random.default_rng(1887 + rank)
+    hx, hx_ptr = ctx.host_alloc(ndof)
+    hy, hy_ptr = ctx.host_alloc(ndof)
+    hx[:] = rng.standard_normal(ndof)
+    dxs = [ctx.upload(hx) for _ in range(NBUF)]
+    dys = [ctx.vec_alloc() for _ in range(NBUF)]
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    for i in range(args.warmup):
+        op.apply_device(dxs[i % NBUF], dys[i % NBUF], sync=False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        op.apply_device(dxs[i % NBUF], dys[i % NBUF], sync=False)
+    e1.record(stream)
+    ctx.sync()
+    barrier()
+    launches = ctx.launch_count - l0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = ndof * world / (ms_per_step * 1e-3)
+
+    # dominant kernel alone (the tile kernel; at N=1 it is the whole step), timed on its launching stream
+    kernel_ms = ctx.time_apply_device(dxs[0], dys[0], max(10, min(args.steps, 100)))
+
+    # end-to-end leg: the drop-in call with HOST buffers, copies inside the timed region
+    e2e_steps = args.e2e_steps or min(args.steps, 50)
+    for _ in range(3):
+        op.apply(hx_ptr, hy_ptr)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        op.apply(hx_ptr, hy_ptr)
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e_val = ndof * world * e2e_steps / t_e2e
+    checksum = float(np.abs(hy[:1024]).sum())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = BYTES_PER_DOF * ndof / (kernel_ms * 1e-3) / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": "DoF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": desc, "elements_per_gpu": list(n), "degree": degree, "dof_per_gpu": ndof,
+                       "pgrid": list(pgrid), "sigma": 2.0, "dirichlet": True,
+                       "l2": f"{NBUF} rotating (x,y) pairs of {ndof * 8 / 1e6:.0f} MB each: inputs larger than the 126 MB L2",
+                       "halo": "NCCL send/recv of face traces overlapped with interior tiles" if world > 1 else "none"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "DoF/s", "h2d_bytes_per_step": ndof * 8, "d2h_bytes_per_step": ndof * 8,
+                    "steps": e2e_steps, "api": "hpdg_op_apply (host pointers, pinned)", "checksum": checksum},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                         "kernel": "k_apply_uniform", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": BYTES_PER_DOF * ndof},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, thr, sdof, reps, el = cpu_reference_rate(32, degree, 10.0)
+            out["cpu_baseline"] = {"value": rate, "unit": "DoF/s", "cores": thr, "kind": "port",
+                                   "sample": f"32^3 elements Q{degree} ({sdof} DoF) x {reps} applies in {el:.1f} s, matrix-free "
+                                             f"quadrature-loop apply (CPU restatement of ipdgoperator.hh), {thr} OpenMP threads"}
+        print(json.dumps(out), flush=True)
+    for d in dxs + dys:
+        ctx.vec_free(d)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

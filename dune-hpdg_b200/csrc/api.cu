@@ -1,0 +1,556 @@
+// C ABI (include/hpdg_b200.h) over the CUDA kernels: context, levels, staging, V-cycle driver, NCCL halo.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/hpdg_b200.h"
+#include "ctx.hpp"
+
+using namespace hpdg;
+
+struct hpdg_ctx : public Ctx {};
+
+static std::string g_create_err;
+
+// ---- NCCL through dlopen: the library keeps no link-time dependency on NCCL, and inside a torch
+// process it binds to the libnccl torch already loaded. -------------------------------------------
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+bool load_nccl(std::string& err) {
+  if (g_nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL); if (h) break; }
+  if (!h) for (const char* nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+  if (!h) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+#define SYM(field, name) *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { err = "missing NCCL symbol " name; return false; }
+  SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+  SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
+  SYM(AllReduce, "ncclAllReduce") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  g_nccl.lib = h;
+  return true;
+}
+#define HPDG_NCCL(call)                                                                       \
+  do {                                                                                        \
+    ncclResult_t r__ = (call);                                                                \
+    if (r__ != ncclSuccess) { ctx->err = std::string(#call) + ": " + g_nccl.GetErrorString(r__); return 1; } \
+  } while (0)
+
+int ipow_h(int b, int e) { int r = 1; while (e-- > 0) r *= b; return r; }
+
+int setup_level(Ctx* ctx, Level& L, int dim, const int* n, const double* h, const std::vector<int>& deg,
+                const std::vector<int>& pdeg) {
+  L.dim = dim;
+  L.nelem = 1;
+  for (int d = 0; d < 3; d++) { L.n[d] = d < dim ? n[d] : 1; L.h[d] = d < dim ? h[d] : 1.0; L.nelem *= L.n[d]; }
+  L.deg = deg; L.pdeg = pdeg;
+  L.off.assign(L.nelem + 1, 0);
+  L.maxp = 0;
+  bool uni = true;
+  for (long e = 0; e < L.nelem; e++) {
+    L.off[e + 1] = L.off[e] + ipow_h(deg[e] + 1, dim);
+    L.maxp = std::max(L.maxp, deg[e]);
+    if (deg[e] != deg[0] || pdeg[e] != pdeg[0]) uni = false;
+  }
+  L.ndof = L.off[L.nelem];
+  L.uniform = uni; L.p_uni = uni ? deg[0] : -1; L.pen_uni = uni ? pdeg[0] : -1;
+  // buckets by degree (stable counting sort)
+  std::vector<long> cnt(kMaxP + 2, 0);
+  for (long e = 0; e < L.nelem; e++) cnt[deg[e] + 1]++;
+  for (int p = 0; p <= kMaxP; p++) cnt[p + 1] += cnt[p];
+  std::vector<int> elist(L.nelem);
+  std::vector<long> pos(cnt.begin(), cnt.end() - 1);
+  for (long e = 0; e < L.nelem; e++) elist[pos[deg[e]]++] = (int)e;
+  L.bucket_p.clear(); L.bucket_begin.clear();
+  for (int p = 0; p <= kMaxP; p++)
+    if (cnt[p + 1] > cnt[p]) { L.bucket_p.push_back(p); L.bucket_begin.push_back(cnt[p]); }
+  L.bucket_begin.push_back(L.nelem);
+  HPDG_CUDA(cudaMalloc(&L.d_deg, sizeof(int) * L.nelem));
+  HPDG_CUDA(cudaMalloc(&L.d_pdeg, sizeof(int) * L.nelem));
+  HPDG_CUDA(cudaMalloc(&L.d_off, sizeof(long) * (L.nelem + 1)));
+  HPDG_CUDA(cudaMalloc(&L.d_elist, sizeof(int) * L.nelem));
+  HPDG_CUDA(cudaMemcpy(L.d_deg, deg.data(), sizeof(int) * L.nelem, cudaMemcpyHostToDevice));
+  HPDG_CUDA(cudaMemcpy(L.d_pdeg, pdeg.data(), sizeof(int) * L.nelem, cudaMemcpyHostToDevice));
+  HPDG_CUDA(cudaMemcpy(L.d_off, L.off.data(), sizeof(long) * (L.nelem + 1), cudaMemcpyHostToDevice));
+  HPDG_CUDA(cudaMemcpy(L.d_elist, elist.data(), sizeof(int) * L.nelem, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+void free_level(Level& L) {
+  cudaFree(L.d_deg); cudaFree(L.d_pdeg); cudaFree(L.d_off); cudaFree(L.d_elist);
+  cudaFree(L.jd.d_inv); cudaFree(L.jf.d_fac); cudaFree(L.jf.d_idx);
+  cudaFree(L.mg_x); cudaFree(L.mg_r); cudaFree(L.mg_t1); cudaFree(L.mg_t2);
+}
+
+int create_common(Ctx* ctx, int dim, const int* n, const double* Lx, const std::vector<int>& deg, double sigma,
+                  int dirichlet, int device) {
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    ctx->err = "no CUDA device available (this library has no CPU fallback)";
+    return 1;
+  }
+  ctx->device = device; ctx->dim = dim; ctx->sigma = sigma; ctx->dirichlet = dirichlet;
+  HPDG_CUDA(cudaSetDevice(device));
+  HPDG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  HPDG_CUDA(cudaStreamCreateWithFlags(&ctx->stream_comm, cudaStreamNonBlocking));
+  HPDG_CUDA(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
+  HPDG_CUDA(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
+  const HostTables& H = host_tables();
+  HPDG_CUDA(cudaMalloc(&ctx->d_tab, sizeof(DegTable) * H.deg.size()));
+  HPDG_CUDA(cudaMemcpy(ctx->d_tab, H.deg.data(), sizeof(DegTable) * H.deg.size(), cudaMemcpyHostToDevice));
+  HPDG_CUDA(cudaMalloc(&ctx->d_P, sizeof(double) * H.P.size()));
+  HPDG_CUDA(cudaMemcpy(ctx->d_P, H.P.data(), sizeof(double) * H.P.size(), cudaMemcpyHostToDevice));
+  HPDG_CUDA(cudaMalloc(&ctx->d_T, sizeof(double) * H.T.size()));
+  HPDG_CUDA(cudaMemcpy(ctx->d_T, H.T.data(), sizeof(double) * H.T.size(), cudaMemcpyHostToDevice));
+  double h[3] = {1, 1, 1};
+  for (int d = 0; d < dim; d++) h[d] = Lx[d] / n[d];
+  ctx->levels.resize(1);
+  return setup_level(ctx, ctx->levels[0], dim, n, h, deg, deg);
+}
+
+Level* get_level(Ctx* ctx, int level) {
+  int nl = (int)ctx->levels.size();
+  if (level == HPDG_FINEST) level = nl - 1;
+  if (level < 0 || level >= nl) { ctx->err = "level index out of range"; return nullptr; }
+  return &ctx->levels[level];
+}
+
+int ensure_stage(Ctx* ctx, size_t ndof) {
+  if (ctx->stage_cap >= ndof) return 0;
+  cudaFree(ctx->d_in); cudaFree(ctx->d_out);
+  ctx->d_in = ctx->d_out = nullptr; ctx->stage_cap = 0;
+  HPDG_CUDA(cudaMalloc(&ctx->d_in, ndof * sizeof(double)));
+  HPDG_CUDA(cudaMalloc(&ctx->d_out, ndof * sizeof(double)));
+  ctx->stage_cap = ndof;
+  return 0;
+}
+
+int halo_exchange(Ctx* ctx, Level& L, const double* d_x) {
+  // copyFromMaster analogue (parallel/communicationhpdg.hh:411-418) on face traces
+  if (launch_pack_traces(ctx, L, d_x)) return 1;
+  HPDG_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
+  HPDG_CUDA(cudaStreamWaitEvent(ctx->stream_comm, ctx->ev_a, 0));
+  ncclComm_t comm = (ncclComm_t)ctx->nccl;
+  HPDG_NCCL(g_nccl.GroupStart());
+  for (int f = 0; f < 6; f++) {
+    if (!ctx->ghost.active[f]) continue;
+    HPDG_NCCL(g_nccl.Send(ctx->ghost.d_send[f], ctx->ghost.count[f], ncclDouble, ctx->ghost.peer[f], comm, ctx->stream_comm));
+    HPDG_NCCL(g_nccl.Recv(ctx->ghost.d_recv[f], ctx->ghost.count[f], ncclDouble, ctx->ghost.peer[f], comm, ctx->stream_comm));
+  }
+  HPDG_NCCL(g_nccl.GroupEnd());
+  HPDG_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream_comm));
+  return 0;
+}
+
+int op_apply_async(Ctx* ctx, Level& L, const double* d_x, double* d_y, double factor) {
+  const bool finest = (&L == &ctx->levels.back());
+  if (ctx->nranks > 1) {
+    if (!finest || !uniform_supported(ctx, L)) { ctx->err = "distributed apply needs the uniform-degree 3-D kernel on the finest level"; return 1; }
+    if (halo_exchange(ctx, L, d_x)) return 1;
+    if (launch_apply_uniform(ctx, L, d_x, d_y, factor, 1)) return 1;   // tiles that need no ghost data: overlaps the exchange
+    HPDG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
+    return launch_apply_uniform(ctx, L, d_x, d_y, factor, 2);
+  }
+  if (uniform_supported(ctx, L)) return launch_apply_uniform(ctx, L, d_x, d_y, factor, 0);
+  return launch_apply_generic(ctx, L, d_x, d_y, factor);
+}
+
+int jacobi_async(Ctx* ctx, Level& L, int form, const double* r, double* c, double damping) {
+  if (form == HPDG_JACOBI_DENSE) return jacobi_apply_dense(ctx, L, r, c, damping);
+  if (form == HPDG_JACOBI_FD) return jacobi_apply_fd(ctx, L, r, c, damping);
+  ctx->err = "unknown block-Jacobi form"; return 1;
+}
+
+// ---- V-cycle (iterationsteps/mg/multigrid_impl.hh:16-117) -----------------------------------------
+struct VC { int form; double damping; int pre, post, coarse_its; };
+
+int mg_smooth(Ctx* ctx, int l, const VC& v, int steps, double* x, double* r) {
+  Level& L = ctx->levels[l];
+  for (int i = 0; i < steps; i++) {                                   // multigrid_impl.hh:76-81
+    if (jacobi_async(ctx, L, v.form, r, L.mg_t1, v.damping)) return 1;  // smoother(tmp1, r)
+    if (launch_axpy(ctx, L.ndof, 1.0, L.mg_t1, x)) return 1;            // x += tmp1
+    if (op_apply_async(ctx, L, L.mg_t1, L.mg_t2, 1.0)) return 1;        // tmp2 = A tmp1
+    if (launch_axpy(ctx, L.ndof, -1.0, L.mg_t2, r)) return 1;           // r -= tmp2
+  }
+  return 0;
+}
+
+int mg_level(Ctx* ctx, int l, const VC& v) {
+  Level& L = ctx->levels[l];
+  double* x = L.mg_x; double* r = L.mg_r;
+  if (l == 0) {  // coarse solver: coarse_its damped block-Jacobi iterations from x = 0 (cf. solversetup.hh:198-215)
+    for (int i = 0; i < v.coarse_its; i++) {
+      if (op_apply_async(ctx, L, x, L.mg_t1, 1.0)) return 1;
+      if (launch_xpay_sub(ctx, L.ndof, r, L.mg_t1, L.mg_t2)) return 1;
+      if (jacobi_async(ctx, L, v.form, L.mg_t2, L.mg_t1, v.damping)) return 1;
+      if (launch_axpy(ctx, L.ndof, 1.0, L.mg_t1, x)) return 1;
+    }
+    return 0;
+  }
+  if (mg_smooth(ctx, l, v, v.pre, x, r)) return 1;                      // :99
+  Level& C = ctx->levels[l - 1];
+  if (launch_restrict(ctx, L, C, r, C.mg_r)) return 1;                  // :103
+  HPDG_CUDA(cudaMemsetAsync(C.mg_x, 0, sizeof(double) * C.ndof, ctx->stream));
+  if (mg_level(ctx, l - 1, v)) return 1;                                // mu_ = 1
+  if (launch_prolong(ctx, L, C, C.mg_x, L.mg_t1)) return 1;             // :108
+  if (launch_axpy(ctx, L.ndof, 1.0, L.mg_t1, x)) return 1;
+  if (op_apply_async(ctx, L, L.mg_t1, L.mg_t2, 1.0)) return 1;
+  if (launch_axpy(ctx, L.ndof, -1.0, L.mg_t2, r)) return 1;
+  return mg_smooth(ctx, l, v, v.post, x, r);                            // :116
+}
+
+int vcycle_device(Ctx* ctx, const VC& v, double* d_x, double* d_b) {
+  if (ctx->nranks > 1) { ctx->err = "V-cycle is single-rank in this round"; return 1; }
+  const int nl = (int)ctx->levels.size();
+  for (int l = 0; l < nl; l++) {
+    Level& L = ctx->levels[l];
+    if (!L.mg_x) {
+      HPDG_CUDA(cudaMalloc(&L.mg_x, sizeof(double) * L.ndof));
+      HPDG_CUDA(cudaMalloc(&L.mg_r, sizeof(double) * L.ndof));
+      HPDG_CUDA(cudaMalloc(&L.mg_t1, sizeof(double) * L.ndof));
+      HPDG_CUDA(cudaMalloc(&L.mg_t2, sizeof(double) * L.ndof));
+    }
+    if (v.form == HPDG_JACOBI_DENSE ? !L.jd.ready : !L.jf.ready) {
+      if (v.form == HPDG_JACOBI_DENSE ? jacobi_setup_dense(ctx, L) : jacobi_setup_fd(ctx, L)) return 1;
+    }
+  }
+  Level& F = ctx->levels[nl - 1];
+  HPDG_CUDA(cudaMemsetAsync(F.mg_x, 0, sizeof(double) * F.ndof, ctx->stream));
+  if (op_apply_async(ctx, F, d_x, F.mg_t1, 1.0)) return 1;             // r = b - A x (:30-36)
+  if (launch_xpay_sub(ctx, F.ndof, d_b, F.mg_t1, F.mg_r)) return 1;
+  if (mg_level(ctx, nl - 1, v)) return 1;
+  if (launch_axpy(ctx, F.ndof, 1.0, F.mg_x, d_x)) return 1;            // x += state.x[fine] (:60)
+  HPDG_CUDA(cudaMemcpyAsync(d_b, F.mg_r, sizeof(double) * F.ndof, cudaMemcpyDeviceToDevice, ctx->stream));  // b = r (:61)
+  return 0;
+}
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int hpdg_create(hpdg_ctx** out, int dim, const int* n, const double* L, const int* degree, long ndegree,
+                double sigma, int dirichlet, int device) {
+  *out = nullptr;
+  if (dim != 2 && dim != 3) { g_create_err = "dim must be 2 or 3"; return 1; }
+  long nelem = 1;
+  for (int d = 0; d < dim; d++) { if (n[d] < 1) { g_create_err = "mesh extents must be positive"; return 1; } nelem *= n[d]; }
+  if (ndegree != 1 && ndegree != nelem) { g_create_err = "degree array must have 1 or nelem entries"; return 1; }
+  std::vector<int> deg(nelem);
+  for (long e = 0; e < nelem; e++) {
+    deg[e] = degree[ndegree == 1 ? 0 : e];
+    if (deg[e] < 0 || deg[e] > kMaxP) { g_create_err = "polynomial degree out of range 0..13"; return 1; }
+  }
+  hpdg_ctx* ctx = new hpdg_ctx();
+  if (create_common(ctx, dim, n, L, deg, sigma, dirichlet, device)) { g_create_err = ctx->err; delete ctx; return 1; }
+  *out = ctx;
+  return 0;
+}
+
+int hpdg_nccl_unique_id(void* out128) {
+  std::string err;
+  if (!load_nccl(err)) { g_create_err = err; return 1; }
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_err = "ncclGetUniqueId failed"; return 1; }
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(out128, &id, 128);
+  return 0;
+}
+
+int hpdg_create_distributed(hpdg_ctx** out, int dim, const int* n, const double* L, int degree, double sigma,
+                            int dirichlet, int device, const int* pgrid, int rank, int nranks, const void* nccl_id) {
+  *out = nullptr;
+  if (dim != 3) { g_create_err = "distributed bricks are 3-D"; return 1; }
+  if (pgrid[0] * pgrid[1] * pgrid[2] != nranks) { g_create_err = "pgrid does not match nranks"; return 1; }
+  long nelem = (long)n[0] * n[1] * n[2];
+  std::vector<int> deg(nelem, degree);
+  hpdg_ctx* ctx = new hpdg_ctx();
+  if (create_common(ctx, dim, n, L, deg, sigma, dirichlet, device)) { g_create_err = ctx->err; delete ctx; return 1; }
+  ctx->rank = rank; ctx->nranks = nranks;
+  for (int d = 0; d < 3; d++) ctx->pgrid[d] = pgrid[d];
+  ctx->pcoord[0] = rank % pgrid[0]; ctx->pcoord[1] = (rank / pgrid[0]) % pgrid[1]; ctx->pcoord[2] = rank / (pgrid[0] * pgrid[1]);
+  auto fail = [&](const std::string& e) { g_create_err = e; hpdg_destroy(ctx); return 1; };
+  if (nranks > 1) {
+    Level& Lv = ctx->levels.back();
+    if (!uniform_supported(ctx, Lv)) return fail("distributed path needs a degree with a specialised uniform kernel (1..5)");
+    std::string err;
+    if (!load_nccl(err)) return fail(err);
+    ncclUniqueId id; memcpy(&id, nccl_id, 128);
+    ncclComm_t comm;
+    if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice failed");
+    ncclResult_t r = g_nccl.CommInitRank(&comm, nranks, id, rank);
+    if (r != ncclSuccess) return fail(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+    ctx->nccl = comm;
+    const int N2 = (degree + 1) * (degree + 1);
+    const int pstride[3] = {1, pgrid[0], pgrid[0] * pgrid[1]};
+    for (int f = 0; f < 6; f++) {
+      const int d = f / 2, s = f % 2;
+      const int c = ctx->pcoord[d] + (s ? 1 : -1);
+      if (c < 0 || c >= pgrid[d]) continue;
+      ctx->bnd_is_rank[f] = true;
+      ctx->ghost.active[f] = true;
+      ctx->ghost.peer[f] = rank + (s ? pstride[d] : -pstride[d]);
+      size_t felems = (size_t)nelem / n[d];
+      ctx->ghost.count[f] = felems * N2 * 2;
+      if (cudaMalloc(&ctx->ghost.d_send[f], ctx->ghost.count[f] * sizeof(double)) != cudaSuccess ||
+          cudaMalloc(&ctx->ghost.d_recv[f], ctx->ghost.count[f] * sizeof(double)) != cudaSuccess)
+        return fail("cudaMalloc of halo buffers failed");
+    }
+  }
+  *out = ctx;
+  return 0;
+}
+
+void hpdg_destroy(hpdg_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream_comm) cudaStreamSynchronize(ctx->stream_comm);
+  if (ctx->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl);
+  for (auto& L : ctx->levels) free_level(L);
+  for (int f = 0; f < 6; f++) { cudaFree(ctx->ghost.d_send[f]); cudaFree(ctx->ghost.d_recv[f]); }
+  cudaFree(ctx->d_tab); cudaFree(ctx->d_P); cudaFree(ctx->d_T); cudaFree(ctx->d_in); cudaFree(ctx->d_out);
+  if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream_comm) cudaStreamDestroy(ctx->stream_comm);
+  delete ctx;
+}
+
+const char* hpdg_last_error(const hpdg_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int hpdg_set_option(hpdg_ctx* ctx, const char* name, long value) {
+  if (!strcmp(name, "force_generic")) { ctx->force_generic = (int)value; return 0; }
+  ctx->err = std::string("unknown option ") + name; return 1;
+}
+
+int hpdg_num_levels(const hpdg_ctx* ctx) { return (int)ctx->levels.size(); }
+long hpdg_num_elements(const hpdg_ctx* ctx) { return ctx->levels.back().nelem; }
+long hpdg_dimension(const hpdg_ctx* ctx, int level) {
+  Level* L = get_level(const_cast<hpdg_ctx*>(ctx), level);
+  return L ? L->ndof : -1;
+}
+int hpdg_block_offsets(const hpdg_ctx* ctx, int level, long* offsets) {
+  Level* L = get_level(const_cast<hpdg_ctx*>(ctx), level);
+  if (!L) return 1;
+  memcpy(offsets, L->off.data(), sizeof(long) * (L->nelem + 1));
+  return 0;
+}
+int hpdg_level_degrees(const hpdg_ctx* ctx, int level, int* degree) {
+  Level* L = get_level(const_cast<hpdg_ctx*>(ctx), level);
+  if (!L) return 1;
+  memcpy(degree, L->deg.data(), sizeof(int) * L->nelem);
+  return 0;
+}
+
+int hpdg_build_p_hierarchy(hpdg_ctx* ctx) {
+  if (ctx->levels.size() != 1) { ctx->err = "hierarchy already built"; return 1; }
+  Level fine = ctx->levels[0];
+  const int pmax = fine.maxp;
+  const int pLevels = pmax >= 1 ? (int)std::log2((double)pmax) : 0;   // solversetup.hh:77
+  std::vector<Level> lv(pLevels + 1);
+  lv[pLevels] = fine;
+  ctx->levels.clear();
+  for (int idx = pLevels - 1; idx >= 0; idx--) {
+    const int cap = pmax / ((pLevels - idx) * 2);                     // solversetup.hh:94
+    std::vector<int> deg(fine.nelem);
+    for (long e = 0; e < fine.nelem; e++) deg[e] = std::min(lv[idx + 1].deg[e], cap);  // ordertransfer.hh:62-67
+    Level L;
+    if (setup_level(ctx, L, fine.dim, fine.n, fine.h, deg, fine.pdeg)) return 1;
+    lv[idx] = L;
+  }
+  ctx->levels = lv;
+  return 0;
+}
+
+int hpdg_vec_alloc(hpdg_ctx* ctx, int level, double** d_vec) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  HPDG_CUDA(cudaMalloc(d_vec, sizeof(double) * std::max<long>(L->ndof, 1)));
+  HPDG_CUDA(cudaMemsetAsync(*d_vec, 0, sizeof(double) * L->ndof, ctx->stream));
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int hpdg_vec_free(hpdg_ctx* ctx, double* d_vec) { HPDG_CUDA(cudaFree(d_vec)); return 0; }
+int hpdg_vec_upload(hpdg_ctx* ctx, int level, const double* h_src, double* d_dst) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(d_dst, h_src, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int hpdg_vec_download(hpdg_ctx* ctx, int level, const double* d_src, double* h_dst) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(h_dst, d_src, sizeof(double) * L->ndof, cudaMemcpyDeviceToHost, ctx->stream));
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int hpdg_host_alloc(hpdg_ctx* ctx, size_t bytes, void** h_ptr) { HPDG_CUDA(cudaMallocHost(h_ptr, bytes)); return 0; }
+int hpdg_host_free(hpdg_ctx* ctx, void* h_ptr) { HPDG_CUDA(cudaFreeHost(h_ptr)); return 0; }
+int hpdg_sync(hpdg_ctx* ctx) {
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream_comm));
+  return 0;
+}
+void* hpdg_stream(hpdg_ctx* ctx) { return (void*)ctx->stream; }
+
+int hpdg_op_apply_async(hpdg_ctx* ctx, int level, const double* d_x, double* d_y, double factor) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  return op_apply_async(ctx, *L, d_x, d_y, factor);
+}
+int hpdg_op_apply_device(hpdg_ctx* ctx, int level, const double* d_x, double* d_y, double factor) {
+  if (hpdg_op_apply_async(ctx, level, d_x, d_y, factor)) return 1;
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int hpdg_op_apply(hpdg_ctx* ctx, int level, const double* h_x, double* h_y, double factor) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  if (ensure_stage(ctx, L->ndof)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_x, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
+  if (op_apply_async(ctx, *L, ctx->d_in, ctx->d_out, factor)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(h_y, ctx->d_out, sizeof(double) * L->ndof, cudaMemcpyDeviceToHost, ctx->stream));
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int hpdg_jacobi_setup(hpdg_ctx* ctx, int level, int form) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  if (form == HPDG_JACOBI_DENSE) return jacobi_setup_dense(ctx, *L);
+  if (form == HPDG_JACOBI_FD) return jacobi_setup_fd(ctx, *L);
+  ctx->err = "unknown block-Jacobi form"; return 1;
+}
+int hpdg_jacobi_apply_device(hpdg_ctx* ctx, int level, int form, const double* d_r, double* d_c, double damping) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  if (jacobi_async(ctx, *L, form, d_r, d_c, damping)) return 1;
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int hpdg_jacobi_apply(hpdg_ctx* ctx, int level, int form, const double* h_r, double* h_c, double damping) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  if (ensure_stage(ctx, L->ndof)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_r, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
+  if (jacobi_async(ctx, *L, form, ctx->d_in, ctx->d_out, damping)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(h_c, ctx->d_out, sizeof(double) * L->ndof, cudaMemcpyDeviceToHost, ctx->stream));
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+size_t hpdg_jacobi_bytes(const hpdg_ctx* ctx, int level, int form) {
+  Level* L = get_level(const_cast<hpdg_ctx*>(ctx), level); if (!L) return 0;
+  if (form == HPDG_JACOBI_DENSE) return L->jd.bytes;
+  return (size_t)L->jf.nfac * (kMaxN * kMaxN + kMaxN) * sizeof(double) + (size_t)L->nelem * 3 * sizeof(int);
+}
+int hpdg_diag_block(hpdg_ctx* ctx, int level, long element, double* h_out) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  if (element < 0 || element >= L->nelem) { ctx->err = "element index out of range"; return 1; }
+  int n1 = L->deg[element] + 1, ne = ipow_h(n1, L->dim);
+  double* d = nullptr;
+  HPDG_CUDA(cudaMalloc(&d, sizeof(double) * ne * ne));
+  int rc = diag_block_device(ctx, *L, element, d);
+  if (!rc) { cudaError_t e = cudaMemcpy(h_out, d, sizeof(double) * ne * ne, cudaMemcpyDeviceToHost); if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = 1; } }
+  cudaFree(d);
+  return rc;
+}
+
+static int xfer_host(hpdg_ctx* ctx, int fine_level, const double* h_in, double* h_out, bool restrict_) {
+  Level* F = get_level(ctx, fine_level); if (!F) return 1;
+  int fl = (int)(F - &ctx->levels[0]);
+  if (fl < 1) { ctx->err = "no coarser level below this one"; return 1; }
+  Level& C = ctx->levels[fl - 1];
+  if (ensure_stage(ctx, F->ndof)) return 1;
+  long nin = restrict_ ? F->ndof : C.ndof, nout = restrict_ ? C.ndof : F->ndof;
+  HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_in, sizeof(double) * nin, cudaMemcpyHostToDevice, ctx->stream));
+  if (restrict_ ? launch_restrict(ctx, *F, C, ctx->d_in, ctx->d_out) : launch_prolong(ctx, *F, C, ctx->d_in, ctx->d_out)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(h_out, ctx->d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost, ctx->stream));
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int hpdg_restrict(hpdg_ctx* ctx, int fine_level, const double* h_fine, double* h_coarse) { return xfer_host(ctx, fine_level, h_fine, h_coarse, true); }
+int hpdg_prolong(hpdg_ctx* ctx, int fine_level, const double* h_coarse, double* h_fine) { return xfer_host(ctx, fine_level, h_coarse, h_fine, false); }
+int hpdg_restrict_device(hpdg_ctx* ctx, int fine_level, const double* d_fine, double* d_coarse) {
+  Level* F = get_level(ctx, fine_level); if (!F) return 1;
+  int fl = (int)(F - &ctx->levels[0]);
+  if (fl < 1) { ctx->err = "no coarser level below this one"; return 1; }
+  if (launch_restrict(ctx, *F, ctx->levels[fl - 1], d_fine, d_coarse)) return 1;
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int hpdg_prolong_device(hpdg_ctx* ctx, int fine_level, const double* d_coarse, double* d_fine) {
+  Level* F = get_level(ctx, fine_level); if (!F) return 1;
+  int fl = (int)(F - &ctx->levels[0]);
+  if (fl < 1) { ctx->err = "no coarser level below this one"; return 1; }
+  if (launch_prolong(ctx, *F, ctx->levels[fl - 1], d_coarse, d_fine)) return 1;
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int hpdg_vcycle_device(hpdg_ctx* ctx, int form, double damping, int pre, int post, int coarse_its, double* d_x, double* d_b) {
+  VC v = {form, damping, pre, post, coarse_its};
+  if (vcycle_device(ctx, v, d_x, d_b)) return 1;
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int hpdg_vcycle(hpdg_ctx* ctx, int form, double damping, int pre, int post, int coarse_its, double* h_x, double* h_b) {
+  Level& F = ctx->levels.back();
+  if (ensure_stage(ctx, F.ndof)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_x, sizeof(double) * F.ndof, cudaMemcpyHostToDevice, ctx->stream));
+  HPDG_CUDA(cudaMemcpyAsync(ctx->d_out, h_b, sizeof(double) * F.ndof, cudaMemcpyHostToDevice, ctx->stream));
+  VC v = {form, damping, pre, post, coarse_its};
+  if (vcycle_device(ctx, v, ctx->d_in, ctx->d_out)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(h_x, ctx->d_in, sizeof(double) * F.ndof, cudaMemcpyDeviceToHost, ctx->stream));
+  HPDG_CUDA(cudaMemcpyAsync(h_b, ctx->d_out, sizeof(double) * F.ndof, cudaMemcpyDeviceToHost, ctx->stream));
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int hpdg_dot_device(hpdg_ctx* ctx, int level, const double* d_x, const double* d_y, double* h_result) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  static double* d_res = nullptr;
+  if (!d_res) HPDG_CUDA(cudaMalloc(&d_res, sizeof(double)));
+  if (launch_dot(ctx, L->ndof, d_x, d_y, d_res)) return 1;
+  if (ctx->nranks > 1)
+    HPDG_NCCL(g_nccl.AllReduce(d_res, d_res, 1, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
+  HPDG_CUDA(cudaMemcpyAsync(h_result, d_res, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int hpdg_axpy_device(hpdg_ctx* ctx, int level, double a, const double* d_x, double* d_y) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  return launch_axpy(ctx, L->ndof, a, d_x, d_y);
+}
+
+long hpdg_launch_count(const hpdg_ctx* ctx) { return ctx->launches; }
+int hpdg_uses_uniform_kernel(const hpdg_ctx* ctx, int level) {
+  Level* L = get_level(const_cast<hpdg_ctx*>(ctx), level);
+  return L ? uniform_supported(ctx, *L) : 0;
+}
+int hpdg_time_apply_device(hpdg_ctx* ctx, int level, const double* d_x, double* d_y, int reps, float* ms_per_apply) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  cudaEvent_t e0, e1;
+  HPDG_CUDA(cudaEventCreate(&e0)); HPDG_CUDA(cudaEventCreate(&e1));
+  HPDG_CUDA(cudaEventRecord(e0, ctx->stream));
+  for (int i = 0; i < reps; i++) if (op_apply_async(ctx, *L, d_x, d_y, 1.0)) return 1;
+  HPDG_CUDA(cudaEventRecord(e1, ctx->stream));
+  HPDG_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  HPDG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_per_apply = ms / reps;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,420 @@
+// Uniform-degree 3-D SIPG operator apply on a structured brick: the headline kernel.
+//
+// Replaces Operator::apply over IPDGOperator (reference: matrix-free/operator.hh:41-56,
+// matrix-free/localoperators/ipdgoperator.hh:80-390) / DynamicBCRSMatrix::mv
+// (common/matrixwindow.hh:196-209) when every element has the same degree.
+//
+// Formulation: on an axis-parallel mesh the operator is a Kronecker sum, so with
+// Tt_d = M^-1 T_d (T_d = 1-D SIPG line operator in direction d: block tridiagonal over the elements
+// of a grid line, off-diagonal blocks of rank 2)
+//        y = factor * (M_x M_y M_z) (Tt_x + Tt_y + Tt_z) u .
+// A CTA owns a TX x TY x TZ tile of elements held in shared memory.  Five passes, each with one
+// thread per DoF *line pencil* of the tile (a thread walks the tile's elements along the pass
+// direction, so in-tile neighbour traces stay in registers and no trace exchange is needed):
+//   P1 z-pencils : load u from global (coalesced), w  = Tt_z u        -> smem u, w
+//   P2 x-pencils : w += Tt_x u
+//   P3 y-pencils : w += Tt_y u ; w = M_y w
+//   P4 x-pencils : w  = M_x w
+//   P5 z-pencils : y  = factor * M_z w                                  -> global (coalesced)
+// Traces of the elements just outside the tile come straight from global/L2 (or, on a rank
+// boundary, from the ghost trace buffer filled by the NCCL halo exchange); domain boundaries are
+// folded in as synthetic neighbour traces (Dirichlet / natural).
+// Algorithmic HBM traffic: read u once + write y once = 16 B/DoF.
+#include <cstdio>
+
+#include "ctx.hpp"
+
+namespace hpdg {
+
+template <int N>
+struct UniParams {
+  double Dt[3][N * N];  // kappa_d * M^-1 S
+  double M[N * N];
+  double mt[2][N], mg[2][N], g[2][N];
+  double kap[3];
+  double cpen;
+  double factor;
+  int n[3];
+  int ntile[3];
+  int bmode[6];            // brick face: 1 Dirichlet, 2 natural, 3 ghost traces
+  const double* ghost[6];  // [face elem][node][2] = (der, val) of the remote element at its near side
+  const double* x;
+  double* y;
+  int part;  // 0 all tiles, 1 only tiles not touching a ghost face, 2 only tiles touching one
+};
+
+template <int N> struct Pitch {
+  static constexpr int PP = (N % 2 == 0) ? N * N + 1 : N * N;  // z-plane pitch
+  static constexpr int EP0 = N * PP;
+  static constexpr int EP = EP0 + ((N - EP0 % 16) % 16 + 16) % 16;  // element pitch == N (mod 16)
+};
+
+// acc[e][:] += (Tt_dir v)_e for the elements e < len of one pencil.
+// (pd,pv)/(nd,nv): (der,val) of the element before / after the pencil at its near side;
+// pmode/nmode: 0 use them, 1 Dirichlet boundary, 2 natural boundary.
+template <int N, int T, int DIR>
+__device__ __forceinline__ void pencil_apply(const UniParams<N>& P, const double (&v)[T][N], double (&acc)[T][N],
+                                             int len, double pd, double pv, int pmode, double nd, double nv, int nmode) {
+  double d0[T], d1[T];
+#pragma unroll
+  for (int e = 0; e < T; e++) {
+    double a = 0, b = 0;
+#pragma unroll
+    for (int m = 0; m < N; m++) { a = fma(P.g[0][m], v[e][m], a); b = fma(P.g[1][m], v[e][m], b); }
+    d0[e] = a; d1[e] = b;
+  }
+  const double kap = P.kap[DIR], c = P.cpen;
+#pragma unroll
+  for (int e = 0; e < T; e++) {
+    if (e < len) {
+      double qd, qv, bm = 1.0;
+      int mode = 0;
+      if (e == 0) { qd = pd; qv = pv; mode = pmode; }
+      else { qd = d1[e > 0 ? e - 1 : 0]; qv = v[e > 0 ? e - 1 : 0][N - 1]; }
+      if (mode == 1) { qd = d0[e]; qv = 0.0; bm = 2.0; }
+      else if (mode == 2) { qd = -d0[e]; qv = v[e][0]; }
+      double G = 0.5 * (d0[e] + qd), J = v[e][0] - qv;
+      const double a0 = kap * G + c * J, b0 = 0.5 * kap * bm * J;
+      bm = 1.0; mode = 0;
+      if (e == len - 1) { qd = nd; qv = nv; mode = nmode; }
+      else { qd = d0[e < T - 1 ? e + 1 : e]; qv = v[e < T - 1 ? e + 1 : e][0]; }
+      if (mode == 1) { qd = d1[e]; qv = 0.0; bm = 2.0; }
+      else if (mode == 2) { qd = -d1[e]; qv = v[e][N - 1]; }
+      G = 0.5 * (d1[e] + qd); J = v[e][N - 1] - qv;
+      const double a1 = -kap * G + c * J, b1 = -0.5 * kap * bm * J;
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        double s = acc[e][i];
+#pragma unroll
+        for (int m = 0; m < N; m++) s = fma(P.Dt[DIR][i * N + m], v[e][m], s);
+        s = fma(P.mt[0][i], a0, s); s = fma(P.mg[0][i], b0, s);
+        s = fma(P.mt[1][i], a1, s); s = fma(P.mg[1][i], b1, s);
+        acc[e][i] = s;
+      }
+    }
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void mass_line(const UniParams<N>& P, double (&a)[N]) {
+  double o[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    double s = 0;
+#pragma unroll
+    for (int m = 0; m < N; m++) s = fma(P.M[i * N + m], a[m], s);
+    o[i] = s;
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) a[i] = o[i];
+}
+
+// Trace (der, val) of the element outside the tile across brick-interior faces: read its DoF line.
+template <int N>
+__device__ __forceinline__ void outside_trace(const UniParams<N>& P, const double* __restrict__ line, long stride,
+                                              int side /* near side of that element */, double& der, double& val) {
+  double d = 0, last = 0, first = 0;
+#pragma unroll
+  for (int m = 0; m < N; m++) {
+    double u = __ldg(line + m * stride);
+    d = fma(P.g[side][m], u, d);
+    if (m == 0) first = u;
+    if (m == N - 1) last = u;
+  }
+  der = d; val = side ? last : first;
+}
+
+template <int N, int TX, int TY, int TZ>
+constexpr int uni_threads() {
+  int a = N * N * TY * TZ, b = N * N * TX * TZ, c = N * N * TX * TY;
+  return a > b ? (a > c ? a : c) : (b > c ? b : c);
+}
+
+template <int N, int TX, int TY, int TZ>
+__global__ void __launch_bounds__(uni_threads<N, TX, TY, TZ>())
+k_apply_uniform(const __grid_constant__ UniParams<N> P) {
+  constexpr int PP = Pitch<N>::PP, EP = Pitch<N>::EP;
+  constexpr int N2 = N * N, N3 = N * N * N;
+  extern __shared__ double sm[];
+  double* su = sm;
+  double* sw = sm + TX * TY * TZ * EP;
+
+  int tb = blockIdx.x;
+  const int tx = tb % P.ntile[0]; tb /= P.ntile[0];
+  const int ty = tb % P.ntile[1]; const int tz = tb / P.ntile[1];
+  const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;
+  const int lenx = min(TX, P.n[0] - x0), leny = min(TY, P.n[1] - y0), lenz = min(TZ, P.n[2] - z0);
+  if (P.part != 0) {
+    bool touch = (x0 == 0 && P.bmode[0] == 3) || (x0 + lenx == P.n[0] && P.bmode[1] == 3) ||
+                 (y0 == 0 && P.bmode[2] == 3) || (y0 + leny == P.n[1] && P.bmode[3] == 3) ||
+                 (z0 == 0 && P.bmode[4] == 3) || (z0 + lenz == P.n[2] && P.bmode[5] == 3);
+    if ((P.part == 1) == touch) return;
+  }
+  const long sx = N3, sy = (long)P.n[0] * N3, sz = (long)P.n[0] * P.n[1] * N3;  // element strides in doubles
+  const double* __restrict__ X = P.x;
+  const int tid = threadIdx.x;
+
+  // ---------------- roles ----------------
+  // z-role: (i, j, ex, ey)
+  const int zi = tid % N, zj = (tid / N) % N, zex = (tid / N2) % TX, zey = tid / (N2 * TX);
+  const bool zact = (tid < N2 * TX * TY) && zex < lenx && zey < leny;
+  // x-role: (j, k, ey, ez)
+  const int xj = tid % N, xk = (tid / N) % N, xey = (tid / N2) % TY, xez = tid / (N2 * TY);
+  const bool xact = (tid < N2 * TY * TZ) && xey < leny && xez < lenz;
+  // y-role: (i, ex, k, ez)
+  const int yi = tid % N, yex = (tid / N) % TX, yk = (tid / (N * TX)) % N, yez = tid / (N2 * TX);
+  const bool yact = (tid < N2 * TX * TZ) && yex < lenx && yez < lenz;
+
+  // ---------------- outside traces for the x- and y-roles (issued early) ----------------
+  double xpd = 0, xpv = 0, xnd = 0, xnv = 0; int xpm = 0, xnm = 0;
+  if (xact) {
+    const long erow = (long)(y0 + xey) * sy + (long)(z0 + xez) * sz;  // element (0, y, z)
+    const int node = xj + N * xk;
+    if (x0 == 0) {
+      xpm = P.bmode[0];
+      if (xpm == 3) { const double* gp = P.ghost[0] + (((long)(y0 + xey) + (long)P.n[1] * (z0 + xez)) * N2 + node) * 2; xpd = gp[0]; xpv = gp[1]; xpm = 0; }
+    } else outside_trace<N>(P, X + erow + (long)(x0 - 1) * sx + N * xj + N2 * xk, 1, 1, xpd, xpv);
+    if (x0 + lenx == P.n[0]) {
+      xnm = P.bmode[1];
+      if (xnm == 3) { const double* gp = P.ghost[1] + (((long)(y0 + xey) + (long)P.n[1] * (z0 + xez)) * N2 + node) * 2; xnd = gp[0]; xnv = gp[1]; xnm = 0; }
+    } else outside_trace<N>(P, X + erow + (long)(x0 + lenx) * sx + N * xj + N2 * xk, 1, 0, xnd, xnv);
+  }
+  double ypd = 0, ypv = 0, ynd = 0, ynv = 0; int ypm = 0, ynm = 0;
+  if (yact) {
+    const long ecol = (long)(x0 + yex) * sx + (long)(z0 + yez) * sz;  // element (x, 0, z)
+    const int node = yi + N * yk;
+    if (y0 == 0) {
+      ypm = P.bmode[2];
+      if (ypm == 3) { const double* gp = P.ghost[2] + (((long)(x0 + yex) + (long)P.n[0] * (z0 + yez)) * N2 + node) * 2; ypd = gp[0]; ypv = gp[1]; ypm = 0; }
+    } else outside_trace<N>(P, X + ecol + (long)(y0 - 1) * sy + yi + N2 * yk, N, 1, ypd, ypv);
+    if (y0 + leny == P.n[1]) {
+      ynm = P.bmode[3];
+      if (ynm == 3) { const double* gp = P.ghost[3] + (((long)(x0 + yex) + (long)P.n[0] * (z0 + yez)) * N2 + node) * 2; ynd = gp[0]; ynv = gp[1]; ynm = 0; }
+    } else outside_trace<N>(P, X + ecol + (long)(y0 + leny) * sy + yi + N2 * yk, N, 0, ynd, ynv);
+  }
+
+  // ---------------- P1: z-pencils, global -> registers -> smem ----------------
+  if (zact) {
+    const long ecol = (long)(x0 + zex) * sx + (long)(y0 + zey) * sy;  // element (x, y, 0)
+    const int node = zi + N * zj;
+    double v[TZ][N], acc[TZ][N];
+#pragma unroll
+    for (int e = 0; e < TZ; e++)
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        v[e][k] = (e < lenz) ? __ldg(X + ecol + (long)(z0 + e) * sz + node + N2 * k) : 0.0;
+        acc[e][k] = 0.0;
+      }
+    double pd = 0, pv = 0, nd = 0, nv = 0; int pm = 0, nm = 0;
+    if (z0 == 0) {
+      pm = P.bmode[4];
+      if (pm == 3) { const double* gp = P.ghost[4] + (((long)(x0 + zex) + (long)P.n[0] * (y0 + zey)) * N2 + node) * 2; pd = gp[0]; pv = gp[1]; pm = 0; }
+    } else outside_trace<N>(P, X + ecol + (long)(z0 - 1) * sz + node, N2, 1, pd, pv);
+    if (z0 + lenz == P.n[2]) {
+      nm = P.bmode[5];
+      if (nm == 3) { const double* gp = P.ghost[5] + (((long)(x0 + zex) + (long)P.n[0] * (y0 + zey)) * N2 + node) * 2; nd = gp[0]; nv = gp[1]; nm = 0; }
+    } else outside_trace<N>(P, X + ecol + (long)(z0 + lenz) * sz + node, N2, 0, nd, nv);
+    pencil_apply<N, TZ, 2>(P, v, acc, lenz, pd, pv, pm, nd, nv, nm);
+#pragma unroll
+    for (int e = 0; e < TZ; e++)
+      if (e < lenz) {
+        const int base = (zex + TX * (zey + TY * e)) * EP + node;
+#pragma unroll
+        for (int k = 0; k < N; k++) { su[base + PP * k] = v[e][k]; sw[base + PP * k] = acc[e][k]; }
+      }
+  }
+  __syncthreads();
+
+  // ---------------- P2: x-pencils ----------------
+  if (xact) {
+    double v[TX][N], acc[TX][N];
+#pragma unroll
+    for (int e = 0; e < TX; e++) {
+      const int base = (e + TX * (xey + TY * xez)) * EP + N * xj + PP * xk;
+#pragma unroll
+      for (int i = 0; i < N; i++) { v[e][i] = (e < lenx) ? su[base + i] : 0.0; acc[e][i] = (e < lenx) ? sw[base + i] : 0.0; }
+    }
+    pencil_apply<N, TX, 0>(P, v, acc, lenx, xpd, xpv, xpm, xnd, xnv, xnm);
+#pragma unroll
+    for (int e = 0; e < TX; e++)
+      if (e < lenx) {
+        const int base = (e + TX * (xey + TY * xez)) * EP + N * xj + PP * xk;
+#pragma unroll
+        for (int i = 0; i < N; i++) sw[base + i] = acc[e][i];
+      }
+  }
+  __syncthreads();
+
+  // ---------------- P3: y-pencils, then M_y ----------------
+  if (yact) {
+    double v[TY][N], acc[TY][N];
+#pragma unroll
+    for (int e = 0; e < TY; e++) {
+      const int base = (yex + TX * (e + TY * yez)) * EP + yi + PP * yk;
+#pragma unroll
+      for (int j = 0; j < N; j++) { v[e][j] = (e < leny) ? su[base + N * j] : 0.0; acc[e][j] = (e < leny) ? sw[base + N * j] : 0.0; }
+    }
+    pencil_apply<N, TY, 1>(P, v, acc, leny, ypd, ypv, ypm, ynd, ynv, ynm);
+#pragma unroll
+    for (int e = 0; e < TY; e++)
+      if (e < leny) {
+        mass_line<N>(P, acc[e]);
+        const int base = (yex + TX * (e + TY * yez)) * EP + yi + PP * yk;
+#pragma unroll
+        for (int j = 0; j < N; j++) sw[base + N * j] = acc[e][j];
+      }
+  }
+  __syncthreads();
+
+  // ---------------- P4: M_x ----------------
+  if (xact) {
+#pragma unroll
+    for (int e = 0; e < TX; e++)
+      if (e < lenx) {
+        const int base = (e + TX * (xey + TY * xez)) * EP + N * xj + PP * xk;
+        double a[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) a[i] = sw[base + i];
+        mass_line<N>(P, a);
+#pragma unroll
+        for (int i = 0; i < N; i++) sw[base + i] = a[i];
+      }
+  }
+  __syncthreads();
+
+  // ---------------- P5: M_z, write ----------------
+  if (zact) {
+    const long ecol = (long)(x0 + zex) * sx + (long)(y0 + zey) * sy;
+    const int node = zi + N * zj;
+#pragma unroll
+    for (int e = 0; e < TZ; e++)
+      if (e < lenz) {
+        const int base = (zex + TX * (zey + TY * e)) * EP + node;
+        double a[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) a[k] = sw[base + PP * k];
+        mass_line<N>(P, a);
+        double* yo = P.y + ecol + (long)(z0 + e) * sz + node;
+#pragma unroll
+        for (int k = 0; k < N; k++) yo[N2 * k] = P.factor * a[k];
+      }
+  }
+}
+
+// ---- ghost trace packing (sender side of the halo exchange) -------------------------
+// For brick face f = (d,s): for every boundary element and face node, (der,val) of the element's
+// DoF line normal to the face at side s.  Layout matches UniParams::ghost of the receiving rank.
+template <int N>
+__global__ void k_pack_traces(const double* __restrict__ x, double* __restrict__ out, int n0, int n1, int n2, int d,
+                              int s, const double* __restrict__ g /* g[s][0..N) */) {
+  constexpr int N2 = N * N, N3 = N2 * N;
+  const int na = d == 0 ? n1 : n0, nb = d == 2 ? n1 : n2;  // face element extents (low dim fastest)
+  const long total = (long)na * nb * N2;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int node = (int)(t % N2);
+    const long fe = t / N2;
+    const int a = (int)(fe % na), b = (int)(fe / na);
+    const int p = node % N, q = node / N;
+    long e; int off, stride;
+    if (d == 0) { e = (s ? n0 - 1 : 0) + (long)n0 * (a + (long)n1 * b); off = N * p + N2 * q; stride = 1; }
+    else if (d == 1) { e = a + (long)n0 * ((s ? n1 - 1 : 0) + (long)n1 * b); off = p + N2 * q; stride = N; }
+    else { e = a + (long)n0 * (b + (long)n1 * (s ? n2 - 1 : 0)); off = p + N * q; stride = N2; }
+    const double* line = x + e * N3 + off;
+    double der = 0, val = 0;
+#pragma unroll
+    for (int m = 0; m < N; m++) {
+      double u = line[m * stride];
+      der = fma(g[m], u, der);
+      if (m == (s ? N - 1 : 0)) val = u;
+    }
+    out[2 * t] = der; out[2 * t + 1] = val;
+  }
+}
+
+template <int N, int TX, int TY, int TZ>
+static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part) {
+  static UniParams<N> P;  // rebuilt per call (cheap); static to keep it off the stack
+  const DegTable& T = host_tables().deg[N - 1];
+  double kap[3];
+  for (int d = 0; d < 3; d++) {
+    double k = 1.0 / L.h[d];
+    for (int dd = 0; dd < 3; dd++) if (dd != d) k *= L.h[dd];
+    kap[d] = k; P.kap[d] = k;
+  }
+  for (int d = 0; d < 3; d++)
+    for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) P.Dt[d][i * N + j] = kap[d] * T.MinvS[i * kMaxN + j];
+  for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) P.M[i * N + j] = T.M[i * kMaxN + j];
+  for (int s = 0; s < 2; s++) for (int i = 0; i < N; i++) { P.mt[s][i] = T.mt[s][i]; P.mg[s][i] = T.mg[s][i]; P.g[s][i] = T.g[s][i]; }
+  P.cpen = ctx->sigma * (double)L.pen_uni * L.pen_uni;
+  P.factor = factor;
+  const int tdim[3] = {TX, TY, TZ};
+  for (int d = 0; d < 3; d++) { P.n[d] = L.n[d]; P.ntile[d] = (L.n[d] + tdim[d] - 1) / tdim[d]; }
+  const bool finest = (&L == &ctx->levels.back());
+  for (int f = 0; f < 6; f++) {
+    P.ghost[f] = nullptr;
+    if (ctx->bnd_is_rank[f]) {
+      if (!finest) { ctx->err = "distributed apply is implemented on the finest level only"; return 1; }
+      P.bmode[f] = 3; P.ghost[f] = ctx->ghost.d_recv[f];
+    } else P.bmode[f] = ctx->dirichlet ? 1 : 2;
+  }
+  P.x = x; P.y = y; P.part = part;
+  constexpr int threads = uni_threads<N, TX, TY, TZ>();
+  constexpr size_t smem = sizeof(double) * 2 * TX * TY * TZ * Pitch<N>::EP;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HPDG_CUDA(cudaFuncSetAttribute(k_apply_uniform<N, TX, TY, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const long ntiles = (long)P.ntile[0] * P.ntile[1] * P.ntile[2];
+  k_apply_uniform<N, TX, TY, TZ><<<(unsigned)ntiles, threads, smem, ctx->stream>>>(P);
+  ctx->launches++;
+  HPDG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uniform_supported(const Ctx* ctx, const Level& L) {
+  if (ctx->force_generic) return 0;
+  if (!L.uniform || L.dim != 3) return 0;
+  return L.p_uni >= 1 && L.p_uni <= 5;
+}
+
+int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part) {
+  switch (L.p_uni) {
+    case 1: return launch_uni<2, 4, 4, 4>(ctx, L, x, y, factor, part);
+    case 2: return launch_uni<3, 4, 4, 4>(ctx, L, x, y, factor, part);
+    case 3: return launch_uni<4, 4, 4, 4>(ctx, L, x, y, factor, part);
+    case 4: return launch_uni<5, 4, 4, 2>(ctx, L, x, y, factor, part);
+    case 5: return launch_uni<6, 2, 2, 2>(ctx, L, x, y, factor, part);
+    default: return -1;
+  }
+}
+
+template <int N>
+static int pack_n(Ctx* ctx, Level& L, const double* x) {
+  const DegTable* dt = ctx->d_tab + (N - 1);
+  for (int f = 0; f < 6; f++) {
+    if (!ctx->ghost.active[f]) continue;
+    const int d = f / 2, s = f % 2;
+    const long total = (long)ctx->ghost.count[f] / 2;
+    const int threads = 256;
+    const int blocks = (int)((total + threads - 1) / threads);
+    k_pack_traces<N><<<blocks, threads, 0, ctx->stream>>>(x, ctx->ghost.d_send[f], L.n[0], L.n[1], L.n[2], d, s,
+                                                         &dt->g[s][0]);
+    ctx->launches++;
+    HPDG_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int launch_pack_traces(Ctx* ctx, Level& L, const double* x) {
+  switch (L.p_uni) {
+    case 1: return pack_n<2>(ctx, L, x);
+    case 2: return pack_n<3>(ctx, L, x);
+    case 3: return pack_n<4>(ctx, L, x);
+    case 4: return pack_n<5>(ctx, L, x);
+    case 5: return pack_n<6>(ctx, L, x);
+    default: ctx->err = "pack_traces: unsupported degree"; return 1;
+  }
+}
+
+}  // namespace hpdg

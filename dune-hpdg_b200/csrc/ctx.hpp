@@ -1,0 +1,122 @@
+// Internal context of the B200 SIPG hot path (host structures + device pointers).
+// The public surface is the C ABI in include/hpdg_b200.h; nothing here is exported.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "tables.hpp"
+
+namespace hpdg {
+
+// ---- ghost layer of a rank-local brick (multi-GPU) -------------------------------
+// For each of the 2*dim brick faces that touches another rank, the neighbour rank's boundary
+// elements contribute, per face node, the pair (der, val) = (g_{1-s}.u_line, t_{1-s}.u_line) of
+// their DoF lines normal to the face: "face traces".  Element degree is uniform across ranks in
+// the distributed path (checked at create time).
+struct Ghost {
+  bool active[6] = {false, false, false, false, false, false};
+  double* d_recv[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [nfaceelem][N^(dim-1)][2]
+  double* d_send[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t count[6] = {0, 0, 0, 0, 0, 0};  // doubles per face buffer
+  int peer[6] = {-1, -1, -1, -1, -1, -1};
+};
+
+struct JacobiDense {
+  bool ready = false;
+  double* d_inv = nullptr;      // all inverses, bucket by bucket, element-major inside a bucket
+  std::vector<size_t> bucket_off;  // start (in doubles) of each degree bucket's inverses
+  size_t bytes = 0;
+};
+
+struct JacobiFD {
+  bool ready = false;
+  // Fast-diagonalisation form of D_e^-1 = (Vx x Vy x Vz) diag(1/(lx+ly+lz)) (Vx x Vy x Vz)^T.
+  // 1-D factors are deduplicated: each entry is {V (kMaxN*kMaxN, row-major n x n), lambda (kMaxN)}.
+  double* d_fac = nullptr;      // [nfac][kMaxN*kMaxN + kMaxN]
+  int* d_idx = nullptr;         // [nelem][3] factor index per direction
+  int nfac = 0;
+};
+
+struct Level {
+  int dim = 0;
+  int n[3] = {1, 1, 1};
+  double h[3] = {1, 1, 1};
+  long nelem = 0, ndof = 0;
+  std::vector<int> deg, pdeg;
+  std::vector<long> off;
+  int* d_deg = nullptr;
+  int* d_pdeg = nullptr;
+  long* d_off = nullptr;
+  bool uniform = false;   // all deg equal and all pdeg equal
+  int p_uni = -1, pen_uni = -1;
+  // degree buckets: elements sorted by degree (stable), for launches with a uniform block size
+  std::vector<int> bucket_p;
+  std::vector<long> bucket_begin;  // size buckets+1
+  int* d_elist = nullptr;
+  int maxp = 0;
+  JacobiDense jd;
+  JacobiFD jf;
+  // scratch vectors for the V-cycle (device, ndof each)
+  double *mg_x = nullptr, *mg_r = nullptr, *mg_t1 = nullptr, *mg_t2 = nullptr;
+};
+
+struct Ctx {
+  int device = 0;
+  int dim = 0;
+  double sigma = 2.0;
+  int dirichlet = 1;
+  cudaStream_t stream = nullptr, stream_comm = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  DegTable* d_tab = nullptr;
+  double* d_P = nullptr;
+  double* d_T = nullptr;
+  std::vector<Level> levels;  // [0] coarsest ... back() finest (reference: multigrid_impl.hh:19-20)
+  std::string err;
+  // distributed brick
+  int rank = 0, nranks = 1;
+  int pgrid[3] = {1, 1, 1}, pcoord[3] = {0, 0, 0};
+  bool bnd_is_rank[6] = {false, false, false, false, false, false};
+  Ghost ghost;           // finest level only
+  void* nccl = nullptr;  // ncclComm_t
+  void* nccl_lib = nullptr;
+  // pinned staging for the host-pointer entry points
+  double *d_in = nullptr, *d_out = nullptr;
+  size_t stage_cap = 0;
+  double *h_pin_in = nullptr, *h_pin_out = nullptr;
+  size_t pin_cap = 0;
+  int force_generic = 0;
+  long launches = 0;  // kernels launched by this context (bench.py's gpu_launches)
+};
+
+#define HPDG_CUDA(call)                                                                    \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                      \
+      return 1;                                                                            \
+    }                                                                                      \
+  } while (0)
+
+// ---- kernel launchers (defined in the .cu files) -----------------------------------------------
+int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double factor);
+// returns -1 if (dim, degree) has no specialised kernel
+int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part);
+int uniform_supported(const Ctx* ctx, const Level& L);
+int launch_pack_traces(Ctx* ctx, Level& L, const double* x);
+
+int jacobi_setup_dense(Ctx* ctx, Level& L);
+int jacobi_apply_dense(Ctx* ctx, Level& L, const double* r, double* c, double damping);
+int jacobi_setup_fd(Ctx* ctx, Level& L);
+int jacobi_apply_fd(Ctx* ctx, Level& L, const double* r, double* c, double damping);
+int diag_block_device(Ctx* ctx, Level& L, long e, double* d_out);
+
+int launch_restrict(Ctx* ctx, Level& fine, Level& coarse, const double* xf, double* xc);
+int launch_prolong(Ctx* ctx, Level& fine, Level& coarse, const double* xc, double* xf);
+int launch_axpy(Ctx* ctx, long n, double a, const double* x, double* y);          // y += a x
+int launch_xpay_sub(Ctx* ctx, long n, const double* b, const double* ax, double* r);  // r = b - ax
+int launch_dot(Ctx* ctx, long n, const double* x, const double* y, double* d_result);
+
+}  // namespace hpdg

@@ -1,0 +1,158 @@
+// p-transfer between DG spaces of different order on the same mesh, and the BLAS-1 helpers of the
+// V-cycle.  Replaces DGOrderTransfer::restrict / prolong (transferoperators/ordertransfer.hh:91-119)
+// whose block-diagonal matrix holds, per element, the Kronecker product of the 1-D interpolation
+// matrix T[i][j] = l^coarse_j(x^fine_i) (transferoperators/dynamicordertransfer.hh:48-73), or the
+// identity for elements already at or below the coarse order (ordertransfer.hh:73-77).  The
+// Kronecker structure is applied by sum factorisation, never formed.
+#include "ctx.hpp"
+
+namespace hpdg {
+
+struct XferParams {
+  int dim;
+  const int* degf;
+  const int* degc;
+  const long* offf;
+  const long* offc;
+  const double* T;  // [(c*(kMaxP+1)+f)][i*kMaxN+j], i fine node, j coarse function
+  const double* in;
+  double* out;
+};
+
+__device__ __forceinline__ int ipw3(int b, int e) { int r = 1; for (int i = 0; i < e; i++) r *= b; return r; }
+
+// One CTA per element.  RESTRICT: out_c = (T x T x T)^T in_f ; else out_f = (T x T x T) in_c.
+template <bool RESTRICT>
+__global__ void k_transfer(XferParams P) {
+  extern __shared__ double sm[];
+  const long e = blockIdx.x;
+  const int dim = P.dim;
+  const int pf = P.degf[e], pc = P.degc[e];
+  const int nf = pf + 1, nc = pc + 1;
+  const int nin = RESTRICT ? nf : nc, nout = RESTRICT ? nc : nf;
+  const double* in = P.in + (RESTRICT ? P.offf[e] : P.offc[e]);
+  double* out = P.out + (RESTRICT ? P.offc[e] : P.offf[e]);
+  const int tin = ipw3(nin, dim);
+  if (pf == pc) {
+    for (int i = threadIdx.x; i < tin; i += blockDim.x) out[i] = in[i];
+    return;
+  }
+  const double* T = P.T + ((size_t)pc * (kMaxP + 1) + pf) * kMaxN * kMaxN;
+  const int mx = ipw3(nf, dim);
+  double* a = sm; double* b = sm + mx;
+  for (int i = threadIdx.x; i < tin; i += blockDim.x) a[i] = in[i];
+  __syncthreads();
+  // contract one direction at a time; extents ext[d] switch from nin to nout
+  int ext[3] = {1, 1, 1};
+  for (int d = 0; d < dim; d++) ext[d] = nin;
+  double* src = a; double* dst = b;
+  for (int d = 0; d < dim; d++) {
+    int oext[3] = {ext[0], ext[1], ext[2]};
+    oext[d] = nout;
+    const int tot = oext[0] * oext[1] * oext[2];
+    const int sin_d = d == 0 ? 1 : d == 1 ? ext[0] : ext[0] * ext[1];
+    const bool last = d == dim - 1;
+    for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
+      int i0 = idx % oext[0], i1 = (idx / oext[0]) % oext[1], i2 = idx / (oext[0] * oext[1]);
+      int id[3] = {i0, i1, i2};
+      const int o = id[d];
+      id[d] = 0;
+      const int base = id[0] + ext[0] * (id[1] + ext[1] * id[2]);
+      double s = 0;
+      for (int k = 0; k < nin; k++) {
+        const double t = RESTRICT ? T[k * kMaxN + o] : T[o * kMaxN + k];
+        s += t * src[base + k * sin_d];
+      }
+      if (last) out[idx] = s; else dst[idx] = s;
+    }
+    __syncthreads();
+    ext[d] = nout;
+    double* t = src; src = dst; dst = t;
+  }
+}
+
+static XferParams make_x(Ctx* ctx, Level& fine, Level& coarse, const double* in, double* out) {
+  XferParams P;
+  P.dim = fine.dim; P.degf = fine.d_deg; P.degc = coarse.d_deg; P.offf = fine.d_off; P.offc = coarse.d_off;
+  P.T = ctx->d_T; P.in = in; P.out = out;
+  return P;
+}
+
+static int xfer_launch(Ctx* ctx, Level& fine, Level& coarse, const double* in, double* out, bool restrict_) {
+  XferParams P = make_x(ctx, fine, coarse, in, out);
+  int n1 = fine.maxp + 1, mx = 1;
+  for (int d = 0; d < fine.dim; d++) mx *= n1;
+  size_t smem = 2 * (size_t)mx * sizeof(double);
+  int threads = mx <= 32 ? 32 : mx <= 64 ? 64 : mx <= 128 ? 128 : 256;
+  if (restrict_) {
+    if (smem > 48 * 1024) HPDG_CUDA(cudaFuncSetAttribute(k_transfer<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_transfer<true><<<(unsigned)fine.nelem, threads, smem, ctx->stream>>>(P);
+  } else {
+    if (smem > 48 * 1024) HPDG_CUDA(cudaFuncSetAttribute(k_transfer<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_transfer<false><<<(unsigned)fine.nelem, threads, smem, ctx->stream>>>(P);
+  }
+  ctx->launches++;
+  HPDG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_restrict(Ctx* ctx, Level& fine, Level& coarse, const double* xf, double* xc) {
+  return xfer_launch(ctx, fine, coarse, xf, xc, true);
+}
+int launch_prolong(Ctx* ctx, Level& fine, Level& coarse, const double* xc, double* xf) {
+  return xfer_launch(ctx, fine, coarse, xc, xf, false);
+}
+
+// ---- BLAS-1 on the flat DynamicBlockVector storage (common/dynamicbvector.hh:185-314) ----------
+__global__ void k_axpy(long n, double a, const double* __restrict__ x, double* __restrict__ y) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) y[i] += a * x[i];
+}
+__global__ void k_sub(long n, const double* __restrict__ b, const double* __restrict__ ax, double* __restrict__ r) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) r[i] = b[i] - ax[i];
+}
+// deterministic two-stage dot product: fixed grid, fixed tree
+constexpr int kDotBlocks = 592, kDotThreads = 256;
+__global__ void k_dot1(long n, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ part) {
+  __shared__ double sh[kDotThreads];
+  double s = 0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) s = fma(x[i], y[i], s);
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = kDotThreads / 2; w > 0; w >>= 1) { if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w]; __syncthreads(); }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+__global__ void k_dot2(const double* __restrict__ part, double* __restrict__ out) {
+  __shared__ double sh[1024];
+  double s = 0;
+  for (int i = threadIdx.x; i < kDotBlocks; i += blockDim.x) s += part[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1) { if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w]; __syncthreads(); }
+  if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+static int grid_for(long n) { long b = (n + 255) / 256; return (int)(b < 148 * 8 ? (b < 1 ? 1 : b) : 148 * 8); }
+
+int launch_axpy(Ctx* ctx, long n, double a, const double* x, double* y) {
+  k_axpy<<<grid_for(n), 256, 0, ctx->stream>>>(n, a, x, y);
+  ctx->launches++;
+  HPDG_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_xpay_sub(Ctx* ctx, long n, const double* b, const double* ax, double* r) {
+  k_sub<<<grid_for(n), 256, 0, ctx->stream>>>(n, b, ax, r);
+  ctx->launches++;
+  HPDG_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_dot(Ctx* ctx, long n, const double* x, const double* y, double* d_result) {
+  static double* d_part = nullptr;
+  if (!d_part) HPDG_CUDA(cudaMalloc(&d_part, kDotBlocks * sizeof(double)));
+  k_dot1<<<kDotBlocks, kDotThreads, 0, ctx->stream>>>(n, x, y, d_part);
+  k_dot2<<<1, 1024, 0, ctx->stream>>>(d_part, d_result);
+  ctx->launches += 2;
+  HPDG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace hpdg

@@ -1,0 +1,314 @@
+"""Python host-side mirror of the reference interface over the C ABI (include/hpdg_b200.h).
+
+This is the ctypes stub a maintainer would add on the reference side (INTEGRATION.md shows the C++
+one); it carries no arithmetic.  Names follow the reference: `Operator.apply(x, Ax)`
+(matrix-free/operator.hh:41), `BlockJacobi` as a `Smoother(c, r)` (iterationsteps/mg/multigrid.hh:13-14),
+`OrderTransfer.restrict/prolong` (transferoperators/ordertransfer.hh:91-119), `Multigrid.apply(x, b)`
+(iterationsteps/mg/multigrid_impl.hh:16).  The library has NO CPU fallback: constructing a Context
+without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libhpdg_b200.so")
+
+FINEST = -1
+JACOBI_DENSE = 0
+JACOBI_FD = 1
+
+_lib = None
+_vp = C.c_void_p
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_lp = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+
+# every symbol include/hpdg_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "hpdg_create": (C.c_int, [C.POINTER(_vp), C.c_int, _ip, _dp, _ip, C.c_long, C.c_double, C.c_int, C.c_int]),
+    "hpdg_create_distributed": (C.c_int, [C.POINTER(_vp), C.c_int, _ip, _dp, C.c_int, C.c_double, C.c_int, C.c_int,
+                                          _ip, C.c_int, C.c_int, C.c_void_p]),
+    "hpdg_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "hpdg_destroy": (None, [_vp]),
+    "hpdg_last_error": (C.c_char_p, [_vp]),
+    "hpdg_set_option": (C.c_int, [_vp, C.c_char_p, C.c_long]),
+    "hpdg_num_levels": (C.c_int, [_vp]),
+    "hpdg_num_elements": (C.c_long, [_vp]),
+    "hpdg_dimension": (C.c_long, [_vp, C.c_int]),
+    "hpdg_block_offsets": (C.c_int, [_vp, C.c_int, _lp]),
+    "hpdg_level_degrees": (C.c_int, [_vp, C.c_int, _ip]),
+    "hpdg_build_p_hierarchy": (C.c_int, [_vp]),
+    "hpdg_vec_alloc": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
+    "hpdg_vec_free": (C.c_int, [_vp, _vp]),
+    "hpdg_vec_upload": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "hpdg_vec_download": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "hpdg_host_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "hpdg_host_free": (C.c_int, [_vp, _vp]),
+    "hpdg_sync": (C.c_int, [_vp]),
+    "hpdg_stream": (_vp, [_vp]),
+    "hpdg_op_apply": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_double]),
+    "hpdg_op_apply_device": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_double]),
+    "hpdg_op_apply_async": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_double]),
+    "hpdg_jacobi_setup": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "hpdg_jacobi_apply": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_double]),
+    "hpdg_jacobi_apply_device": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_double]),
+    "hpdg_jacobi_bytes": (C.c_size_t, [_vp, C.c_int, C.c_int]),
+    "hpdg_diag_block": (C.c_int, [_vp, C.c_int, C.c_long, _dp]),
+    "hpdg_restrict": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "hpdg_prolong": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "hpdg_restrict_device": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "hpdg_prolong_device": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "hpdg_vcycle": (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "hpdg_vcycle_device": (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "hpdg_dot_device": (C.c_int, [_vp, C.c_int, _vp, _vp, C.POINTER(C.c_double)]),
+    "hpdg_axpy_device": (C.c_int, [_vp, C.c_int, C.c_double, _vp, _vp]),
+    "hpdg_launch_count": (C.c_long, [_vp]),
+    "hpdg_uses_uniform_kernel": (C.c_int, [_vp, C.c_int]),
+    "hpdg_time_apply_device": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.POINTER(C.c_float)]),
+}
+
+
+class HpdgError(RuntimeError):
+    """Raised where the reference would DUNE_THROW (e.g. iterationsteps/dynamicblockgs.hh:117)."""
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HpdgError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _hptr(a):
+    """host pointer of a numpy array or a raw integer address"""
+    if isinstance(a, np.ndarray):
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    return int(a)
+
+
+class Context:
+    """One GPU's view of the problem: mesh brick + degree map + penalty (replaces the reference's
+    basis + IPDGOperator constructor arguments)."""
+
+    def __init__(self, n, L=None, degree=1, sigma=2.0, dirichlet=True, device=0, pgrid=None, rank=0, nranks=1,
+                 nccl_id=None):
+        self._h = _vp()
+        self.dim = len(n)
+        n = np.ascontiguousarray(n, dtype=np.int32)
+        L = np.ascontiguousarray(L if L is not None else [1.0] * self.dim, dtype=np.float64)
+        deg = np.ascontiguousarray(np.atleast_1d(degree), dtype=np.int32)
+        if pgrid is None:
+            rc = lib().hpdg_create(C.byref(self._h), self.dim, n, L, deg, deg.size, sigma, int(dirichlet), device)
+        else:
+            pg = np.ascontiguousarray(pgrid, dtype=np.int32)
+            idp = C.c_char_p(nccl_id) if nccl_id is not None else None
+            rc = lib().hpdg_create_distributed(C.byref(self._h), self.dim, n, L, int(deg[0]), sigma, int(dirichlet),
+                                               device, pg, rank, nranks, idp)
+        if rc:
+            msg = lib().hpdg_last_error(None).decode()
+            self._h = None
+            raise HpdgError(msg)
+        self.n = n
+
+    def _ck(self, rc):
+        if rc:
+            raise HpdgError(lib().hpdg_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().hpdg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # sizes ------------------------------------------------------------------------------------
+    @property
+    def num_levels(self):
+        return lib().hpdg_num_levels(self._h)
+
+    @property
+    def num_elements(self):
+        return lib().hpdg_num_elements(self._h)
+
+    def dimension(self, level=FINEST):
+        return lib().hpdg_dimension(self._h, level)
+
+    def block_offsets(self, level=FINEST):
+        off = np.zeros(self.num_elements + 1, dtype=np.int64)
+        self._ck(lib().hpdg_block_offsets(self._h, level, off))
+        return off
+
+    def level_degrees(self, level=FINEST):
+        d = np.zeros(self.num_elements, dtype=np.int32)
+        self._ck(lib().hpdg_level_degrees(self._h, level, d))
+        return d
+
+    def build_p_hierarchy(self):
+        self._ck(lib().hpdg_build_p_hierarchy(self._h))
+        return self.num_levels
+
+    def set_option(self, name, value):
+        self._ck(lib().hpdg_set_option(self._h, name.encode(), int(value)))
+
+    # device vectors ---------------------------------------------------------------------------
+    def vec_alloc(self, level=FINEST):
+        p = _vp()
+        self._ck(lib().hpdg_vec_alloc(self._h, level, C.byref(p)))
+        return p.value
+
+    def vec_free(self, d):
+        self._ck(lib().hpdg_vec_free(self._h, d))
+
+    def upload(self, h, d=None, level=FINEST):
+        if d is None:
+            d = self.vec_alloc(level)
+        self._ck(lib().hpdg_vec_upload(self._h, level, _hptr(h), d))
+        return d
+
+    def download(self, d, level=FINEST, out=None):
+        if out is None:
+            out = np.zeros(self.dimension(level))
+        self._ck(lib().hpdg_vec_download(self._h, level, d, _hptr(out)))
+        return out
+
+    def host_alloc(self, ndoubles):
+        """pinned host array (numpy view)"""
+        p = _vp()
+        self._ck(lib().hpdg_host_alloc(self._h, ndoubles * 8, C.byref(p)))
+        buf = (C.c_double * ndoubles).from_address(p.value)
+        a = np.frombuffer(buf, dtype=np.float64)
+        a._hpdg_keep = buf
+        return a, p.value
+
+    def host_free(self, p):
+        self._ck(lib().hpdg_host_free(self._h, p))
+
+    def sync(self):
+        self._ck(lib().hpdg_sync(self._h))
+
+    @property
+    def stream(self):
+        return lib().hpdg_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return lib().hpdg_launch_count(self._h)
+
+    def uses_uniform_kernel(self, level=FINEST):
+        return bool(lib().hpdg_uses_uniform_kernel(self._h, level))
+
+    def dot_device(self, dx, dy, level=FINEST):
+        r = C.c_double()
+        self._ck(lib().hpdg_dot_device(self._h, level, dx, dy, C.byref(r)))
+        return r.value
+
+    def axpy_device(self, a, dx, dy, level=FINEST):
+        self._ck(lib().hpdg_axpy_device(self._h, level, a, dx, dy))
+
+    def time_apply_device(self, dx, dy, reps, level=FINEST):
+        ms = C.c_float()
+        self._ck(lib().hpdg_time_apply_device(self._h, level, dx, dy, reps, C.byref(ms)))
+        return ms.value
+
+
+class Operator:
+    """`Operator::apply(x, Ax)` with a single IPDGOperator local operator and its factor
+    (matrix-free/operator.hh:41-56, matrix-free/localoperators/localoperator.hh:41-49)."""
+
+    def __init__(self, ctx, level=FINEST, factor=1.0):
+        self.ctx, self.level, self._factor = ctx, level, factor
+
+    def factor(self):
+        return self._factor
+
+    def setFactor(self, f):
+        self._factor = f
+
+    def apply(self, x, Ax=None):
+        if Ax is None:
+            Ax = np.zeros(self.ctx.dimension(self.level))
+        self.ctx._ck(lib().hpdg_op_apply(self.ctx._h, self.level, _hptr(x), _hptr(Ax), self._factor))
+        return Ax
+
+    def apply_device(self, dx, dy, sync=True):
+        f = lib().hpdg_op_apply_device if sync else lib().hpdg_op_apply_async
+        self.ctx._ck(f(self.ctx._h, self.level, dx, dy, self._factor))
+
+
+class BlockJacobi:
+    """Smoother<V>(c, r): c = damping * sum_e P_e^T D_e^-1 P_e r (ipdgblockjacobi.hh:58-178)."""
+
+    def __init__(self, ctx, level=FINEST, form=JACOBI_DENSE, damping=1.0):
+        self.ctx, self.level, self.form, self.damping = ctx, level, form, damping
+        ctx._ck(lib().hpdg_jacobi_setup(ctx._h, level, form))
+
+    def __call__(self, r, c=None):
+        if c is None:
+            c = np.zeros(self.ctx.dimension(self.level))
+        self.ctx._ck(lib().hpdg_jacobi_apply(self.ctx._h, self.level, self.form, _hptr(r), _hptr(c), self.damping))
+        return c
+
+    def apply_device(self, dr, dc):
+        self.ctx._ck(lib().hpdg_jacobi_apply_device(self.ctx._h, self.level, self.form, dr, dc, self.damping))
+
+    @property
+    def bytes(self):
+        return lib().hpdg_jacobi_bytes(self.ctx._h, self.level, self.form)
+
+    def diag_block(self, e):
+        off = self.ctx.block_offsets(self.level)
+        n = int(off[e + 1] - off[e])
+        out = np.zeros((n, n))
+        self.ctx._ck(lib().hpdg_diag_block(self.ctx._h, self.level, e, out))
+        return out
+
+
+class OrderTransfer:
+    """DGOrderTransfer between `fine_level` and `fine_level - 1` (ordertransfer.hh:91-119)."""
+
+    def __init__(self, ctx, fine_level):
+        self.ctx = ctx
+        self.fine = fine_level if fine_level != FINEST else ctx.num_levels - 1
+
+    def restrict(self, fine_vec, coarse_vec=None):
+        if coarse_vec is None:
+            coarse_vec = np.zeros(self.ctx.dimension(self.fine - 1))
+        self.ctx._ck(lib().hpdg_restrict(self.ctx._h, self.fine, _hptr(fine_vec), _hptr(coarse_vec)))
+        return coarse_vec
+
+    def prolong(self, coarse_vec, fine_vec=None):
+        if fine_vec is None:
+            fine_vec = np.zeros(self.ctx.dimension(self.fine))
+        self.ctx._ck(lib().hpdg_prolong(self.ctx._h, self.fine, _hptr(coarse_vec), _hptr(fine_vec)))
+        return fine_vec
+
+
+class Multigrid:
+    """Multigrid<Vector>::apply(x, b) (mg/multigrid_impl.hh:16-61) with block-Jacobi smoothing."""
+
+    def __init__(self, ctx, form=JACOBI_FD, damping=0.75, pre=5, post=5, coarse_its=5):
+        self.ctx, self.form, self.damping, self.pre, self.post, self.coarse_its = ctx, form, damping, pre, post, coarse_its
+
+    def apply(self, x, b):
+        self.ctx._ck(lib().hpdg_vcycle(self.ctx._h, self.form, self.damping, self.pre, self.post, self.coarse_its,
+                                       _hptr(x), _hptr(b)))
+        return x, b
+
+    def apply_device(self, dx, db):
+        self.ctx._ck(lib().hpdg_vcycle_device(self.ctx._h, self.form, self.damping, self.pre, self.post,
+                                              self.coarse_its, dx, db))

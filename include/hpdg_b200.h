@@ -1,0 +1,123 @@
+/*
+ * hpdg_b200.h -- C ABI of the B200-native SIPG hot path (drop-in boundary).
+ *
+ * One opaque context per GPU / rank.  Vectors are plain `double` arrays in the layout of the
+ * reference's DynamicBlockVector (dune/hpdg/common/dynamicbvector.hh:366-379): one contiguous
+ * array, element block i of (p_i+1)^dim doubles at offset sum_{j<i} (p_j+1)^dim, local index
+ * x-fastest (dune/hpdg/localfunctions/lagrange/qkgausslobatto/qkgllocalbasis.hh:69-78); elements
+ * numbered x-fastest like YaspGrid's leaf index.
+ *
+ * Every entry point returns 0 on success, non-zero on failure; hpdg_last_error() then describes the
+ * failure (the C++ shim include/hpdg_b200.hh rethrows it as an exception, mirroring DUNE_THROW).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Entry points come in two flavours: `*_device` take device pointers (vectors resident in HBM, the
+ * normal mode inside a solver loop) and the plain names take HOST pointers and stage the copies
+ * (the literal drop-in for code holding DUNE containers).  Calls on one context are serialised by
+ * the caller, like the reference's non-reentrant local operators (ipdgoperator.hh:233,397-401).
+ */
+#ifndef HPDG_B200_H
+#define HPDG_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hpdg_ctx hpdg_ctx;
+
+#define HPDG_FINEST (-1)          /* level argument: finest level */
+#define HPDG_JACOBI_DENSE 0       /* precomputed dense per-element inverses, batched by block size */
+#define HPDG_JACOBI_FD 1          /* same inverse in Kronecker (fast diagonalisation) form */
+
+/* -- problem description -------------------------------------------------------------------------
+ * Replaces: DynamicDGQkGLBlockBasis(gridView, k | degree map) (functionspacebases/dynamicdgqkglbasis.hh:54-69),
+ * YaspGrid extents (matrix-free/test/testdg.cc:144) and IPDGOperator(basis, penalty, dirichlet)
+ * (matrix-free/localoperators/ipdgoperator.hh:40).  degree: ndegree == 1 -> uniform, else one entry per
+ * element (ndegree == n[0]*..*n[dim-1]).  Domain is [0,L[0]] x .. ; dim = 2 or 3. */
+int hpdg_create(hpdg_ctx** out, int dim, const int* n, const double* L, const int* degree, long ndegree,
+                double sigma, int dirichlet, int device);
+
+/* Rank-local brick of a structured mesh split over pgrid[0]*pgrid[1]*pgrid[2] ranks (rank = px + pgrid[0]*(py +
+ * pgrid[1]*pz)); n and L describe the LOCAL brick.  Models the reference's element-wise owner/overlap
+ * decomposition (parallel/communicationhpdg.hh:261-263) with a face-trace halo instead of whole ghost
+ * blocks.  nccl_id: the 128-byte ncclUniqueId produced by hpdg_nccl_unique_id on rank 0 and broadcast by the
+ * caller.  Uniform degree only. */
+int hpdg_create_distributed(hpdg_ctx** out, int dim, const int* n, const double* L, int degree, double sigma,
+                            int dirichlet, int device, const int* pgrid, int rank, int nranks,
+                            const void* nccl_id);
+int hpdg_nccl_unique_id(void* out128);
+void hpdg_destroy(hpdg_ctx* ctx);
+const char* hpdg_last_error(const hpdg_ctx* ctx); /* ctx may be NULL after a failed create */
+int hpdg_set_option(hpdg_ctx* ctx, const char* name, long value); /* "force_generic" */
+
+/* -- sizes (DynamicBlockVector::dimension(), blockRows(i): dynamicbvector.hh:134-143,282) ---------- */
+int hpdg_num_levels(const hpdg_ctx* ctx);
+long hpdg_num_elements(const hpdg_ctx* ctx);
+long hpdg_dimension(const hpdg_ctx* ctx, int level);
+int hpdg_block_offsets(const hpdg_ctx* ctx, int level, long* offsets /* nelem+1 */);
+int hpdg_level_degrees(const hpdg_ctx* ctx, int level, int* degree /* nelem */);
+
+/* p-multigrid hierarchy as MultigridSetup::setupData builds it (iterationsteps/solversetup.hh:71-108):
+ * pLevels = floor(log2(p_max)) coarse levels with order caps p_max/(2*(pLevels-idx)); coarse operators are the
+ * Galerkin products (ordertransfer.hh:124-144), i.e. the same form with the FINE face penalties. */
+int hpdg_build_p_hierarchy(hpdg_ctx* ctx);
+
+/* -- device vectors ------------------------------------------------------------------------------- */
+int hpdg_vec_alloc(hpdg_ctx* ctx, int level, double** d_vec);
+int hpdg_vec_free(hpdg_ctx* ctx, double* d_vec);
+int hpdg_vec_upload(hpdg_ctx* ctx, int level, const double* h_src, double* d_dst);
+int hpdg_vec_download(hpdg_ctx* ctx, int level, const double* d_src, double* h_dst);
+int hpdg_host_alloc(hpdg_ctx* ctx, size_t bytes, void** h_ptr); /* pinned */
+int hpdg_host_free(hpdg_ctx* ctx, void* h_ptr);
+int hpdg_sync(hpdg_ctx* ctx);
+void* hpdg_stream(hpdg_ctx* ctx); /* cudaStream_t the context launches on */
+
+/* -- operator: y = factor * A x ---------------------------------------------------------------------
+ * Replaces Operator<V,GV,IPDGOperator>::apply(x, Ax) (matrix-free/operator.hh:41-56 with the local operator's
+ * factor, ipdgoperator.hh:62-67) and the assembled matrix.mv(x, y) behind operatorFromMatrix
+ * (iterationsteps/mg/multigrid.hh:137-155).  y is overwritten. */
+int hpdg_op_apply(hpdg_ctx* ctx, int level, const double* h_x, double* h_y, double factor);
+int hpdg_op_apply_device(hpdg_ctx* ctx, int level, const double* d_x, double* d_y, double factor);
+int hpdg_op_apply_async(hpdg_ctx* ctx, int level, const double* d_x, double* d_y, double factor);
+
+/* -- block Jacobi: c = damping * sum_e P_e^T D_e^-1 P_e r -------------------------------------------
+ * Replaces IPDGBlockJacobi inside Operator::apply (matrix-free/localoperators/ipdgblockjacobi.hh:58-178) used
+ * as Smoother<V>(c, r) (iterationsteps/mg/multigrid.hh:13-14); damping is the caller's `c *= 0.75`
+ * (matrix-free/test/testdgblockjacobi.cc:103). */
+int hpdg_jacobi_setup(hpdg_ctx* ctx, int level, int form);
+int hpdg_jacobi_apply(hpdg_ctx* ctx, int level, int form, const double* h_r, double* h_c, double damping);
+int hpdg_jacobi_apply_device(hpdg_ctx* ctx, int level, int form, const double* d_r, double* d_c, double damping);
+size_t hpdg_jacobi_bytes(const hpdg_ctx* ctx, int level, int form);
+/* MatrixCreator protocol bind(e) + matrix() (matrix-free/localoperators/ipdgdiagonalblock.hh:29-360,
+ * slowipdgdiag.hh:32-218): the diagonal block A_ee, n_e x n_e row-major, to host memory. */
+int hpdg_diag_block(hpdg_ctx* ctx, int level, long element, double* h_out);
+
+/* -- p-transfer between level and level-1 (transferoperators/ordertransfer.hh:91-119) ------------- */
+int hpdg_restrict(hpdg_ctx* ctx, int fine_level, const double* h_fine, double* h_coarse);
+int hpdg_prolong(hpdg_ctx* ctx, int fine_level, const double* h_coarse, double* h_fine);
+int hpdg_restrict_device(hpdg_ctx* ctx, int fine_level, const double* d_fine, double* d_coarse);
+int hpdg_prolong_device(hpdg_ctx* ctx, int fine_level, const double* d_coarse, double* d_fine);
+
+/* -- one multigrid cycle: Multigrid<Vector>::apply(x, b) (iterationsteps/mg/multigrid_impl.hh:16-117) with the
+ * block-Jacobi smoother on every level and `coarse_its` damped Jacobi iterations as coarse solver
+ * (the reference default is 5 block-GS iterations, solversetup.hh:198-215).  On return x += correction and
+ * b holds the residual (multigrid_impl.hh:60-61). */
+int hpdg_vcycle(hpdg_ctx* ctx, int form, double damping, int pre, int post, int coarse_its, double* h_x, double* h_b);
+int hpdg_vcycle_device(hpdg_ctx* ctx, int form, double damping, int pre, int post, int coarse_its, double* d_x,
+                       double* d_b);
+
+/* -- BLAS-1 used by the Krylov / MG drivers (DynamicBlockVector::operator*, two_norm:
+ * common/dynamicbvector.hh:258-264,300-314); sums over all ranks of a distributed context. */
+int hpdg_dot_device(hpdg_ctx* ctx, int level, const double* d_x, const double* d_y, double* h_result);
+int hpdg_axpy_device(hpdg_ctx* ctx, int level, double a, const double* d_x, double* d_y);
+
+/* -- introspection --------------------------------------------------------------------------------- */
+long hpdg_launch_count(const hpdg_ctx* ctx);      /* kernels launched so far by this context */
+int hpdg_uses_uniform_kernel(const hpdg_ctx* ctx, int level);
+/* time `reps` back-to-back operator applies with CUDA events on the context stream; ms per apply */
+int hpdg_time_apply_device(hpdg_ctx* ctx, int level, const double* d_x, double* d_y, int reps, float* ms_per_apply);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,196 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Bar: relative L2 <= 1e-12 (FP64)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("dirichlet", [True, False])
+def test_uniform_3d_vs_assembled(orc, hp, p, dirichlet):
+    # ragged extents (not multiples of the 4x4x4 tile), anisotropic spacing
+    n, L = (5, 6, 3), [1.0, 1.5, 0.5]
+    m = orc.Mesh(n, L=L, degree=p, sigma=2.0, dirichlet=dirichlet)
+    x = orc.fill_random(m.ndof)
+    ref = m.assemble().mv(x)
+    ctx = hp.Context(n, L=L, degree=p, sigma=2.0, dirichlet=dirichlet)
+    assert ctx.dimension() == m.ndof and ctx.uses_uniform_kernel()
+    y = hp.Operator(ctx).apply(x)
+    assert rel(y, ref) < TOL
+    ctx.set_option("force_generic", 1)
+    assert not ctx.uses_uniform_kernel()
+    yg = hp.Operator(ctx, factor=0.5).apply(x)
+    assert rel(yg, 0.5 * ref) < TOL
+
+
+@pytest.mark.parametrize("n", [(1, 1, 1), (2, 1, 3), (4, 4, 4), (8, 8, 8), (9, 4, 5)])
+def test_uniform_q3_edge_meshes(orc, hp, n):
+    m = orc.Mesh(n, degree=3, sigma=2.0, dirichlet=True)
+    x = orc.fill_random(m.ndof)
+    ref = m.apply_mf(x, threads=orc.max_threads())
+    y = hp.Operator(hp.Context(n, degree=3)).apply(x)
+    assert rel(y, ref) < TOL
+
+
+def test_cfg1_2d_q2_testdg(orc, hp):
+    # BASELINE config 1 / matrix-free/test/testdg.cc: 16x16 Q2, x = |x|^2, factor 0.5, energy error < 1e-14
+    m = orc.Mesh((16, 16), degree=2, sigma=2.0, dirichlet=True)
+    A = m.assemble()
+    x = m.interpolate_normsq()
+    ctx = hp.Context((16, 16), degree=2, sigma=2.0, dirichlet=True)
+    Ax = hp.Operator(ctx, factor=0.5).apply(x) / 0.5
+    d = Ax - A.mv(x)
+    assert 0 <= d @ A.mv(d) < 1e-14
+    assert rel(Ax, A.mv(x)) < TOL
+
+
+@pytest.mark.parametrize("dim,n", [(2, (7, 5)), (3, (4, 3, 5))])
+@pytest.mark.parametrize("dirichlet", [True, False])
+def test_hp_random_degrees(orc, hp, dim, n, dirichlet):
+    # BASELINE config 3 in small: per-element degree 1..6, random
+    rng = np.random.default_rng(1887)
+    deg = rng.integers(1, 7, int(np.prod(n))).astype(np.int32)
+    m = orc.Mesh(n, degree=deg, sigma=2.0, dirichlet=dirichlet)
+    x = orc.fill_random(m.ndof)
+    ref = m.apply_mf(x, threads=orc.max_threads())
+    ctx = hp.Context(n, degree=deg, sigma=2.0, dirichlet=dirichlet)
+    assert np.array_equal(ctx.block_offsets(), m.offsets)
+    y = hp.Operator(ctx).apply(x)
+    assert rel(y, ref) < TOL
+
+
+def test_hp_single_high_element(orc, hp):
+    # matrix-free/test/testsumfactor.cc: first element has degree k+1
+    for k in (1, 2, 3, 4):
+        deg = np.full(64, k, dtype=np.int32)
+        deg[0] = k + 1
+        m = orc.Mesh((8, 8), degree=deg)
+        x = orc.fill_random(m.ndof)
+        y = hp.Operator(hp.Context((8, 8), degree=deg)).apply(x)
+        assert rel(y, m.assemble().mv(x)) < TOL
+
+
+def test_high_order_and_q0(orc, hp):
+    for p in (0, 7, 9, 13):
+        n = (3, 2, 2) if p < 13 else (2, 2)
+        m = orc.Mesh(n, degree=p)
+        x = orc.fill_random(m.ndof)
+        y = hp.Operator(hp.Context(n, degree=p)).apply(x)
+        assert rel(y, m.apply_mf(x, threads=orc.max_threads())) < (1e-11 if p == 13 else TOL)
+
+
+def test_cfg2_full_size(orc, hp):
+    # BASELINE config 2: 64^3 Q3.  Direct comparison with the (threaded) matrix-free oracle plus
+    # size-independent properties: symmetry and linearity.
+    n = (64, 64, 64)
+    m = orc.Mesh(n, degree=3, sigma=2.0, dirichlet=True)
+    x = orc.fill_random(m.ndof)
+    ctx = hp.Context(n, degree=3, sigma=2.0, dirichlet=True)
+    op = hp.Operator(ctx)
+    y = op.apply(x)
+    ref = m.apply_mf(x, threads=orc.max_threads())
+    assert rel(y, ref) < TOL
+    z = orc.fill_random(m.ndof, seed=7)
+    Az = op.apply(z)
+    assert abs(z @ y - x @ Az) <= 1e-11 * abs(z @ y)
+    assert rel(op.apply(2.0 * x - 3.0 * z), 2.0 * y - 3.0 * Az) < TOL
+
+
+def test_device_resident_api(orc, hp):
+    n = (6, 6, 6)
+    m = orc.Mesh(n, degree=3)
+    x = orc.fill_random(m.ndof)
+    ctx = hp.Context(n, degree=3)
+    dx = ctx.upload(x)
+    dy = ctx.vec_alloc()
+    before = ctx.launch_count
+    hp.Operator(ctx).apply_device(dx, dy)
+    assert ctx.launch_count == before + 1
+    assert rel(ctx.download(dy), m.apply_mf(x)) < TOL
+    assert abs(ctx.dot_device(dx, dx) - x @ x) < 1e-10 * (x @ x)
+    ms = ctx.time_apply_device(dx, dy, 3)
+    assert ms > 0
+    ctx.vec_free(dx)
+    ctx.vec_free(dy)
+
+
+@pytest.mark.parametrize("form", [0, 1])
+def test_block_jacobi_vs_oracle(orc, hp, form):
+    rng = np.random.default_rng(2)
+    for n, deg in [((4, 3, 3), rng.integers(1, 5, 36).astype(np.int32)), ((5, 4), rng.integers(1, 7, 20).astype(np.int32)),
+                   ((3, 3, 3), 3)]:
+        for dirichlet in (True, False):
+            m = orc.Mesh(n, degree=deg, dirichlet=dirichlet)
+            r = orc.fill_random(m.ndof)
+            ref = m.blockjacobi_apply(r, factor=0.75)
+            ctx = hp.Context(n, degree=deg, dirichlet=dirichlet)
+            jac = hp.BlockJacobi(ctx, form=form, damping=0.75)
+            assert rel(jac(r), ref) < 1e-11
+            for e in (0, m.nelem // 2, m.nelem - 1):
+                assert np.abs(jac.diag_block(e) - m.diag_block_mf(e)).max() < 1e-12 * np.abs(m.diag_block_mf(e)).max()
+
+
+def test_transfer_vs_oracle(orc, hp):
+    rng = np.random.default_rng(4)
+    for n in [(3, 4, 2), (5, 3)]:
+        deg = rng.integers(1, 7, int(np.prod(n))).astype(np.int32)
+        deg[0] = 6
+        fine = orc.Mesh(n, degree=deg)
+        ctx = hp.Context(n, degree=deg)
+        nl = ctx.build_p_hierarchy()
+        assert nl == 3  # p_max = 6: caps 6/4 = 1, 6/2 = 3 (solversetup.hh:77,94)
+        l1 = fine.coarsen(3)
+        l0 = l1.coarsen(1)
+        assert np.array_equal(ctx.level_degrees(1), l1.degree) and np.array_equal(ctx.level_degrees(0), l0.degree)
+        xf = orc.fill_random(fine.ndof)
+        t2 = hp.OrderTransfer(ctx, 2)
+        xc = t2.restrict(xf)
+        assert rel(xc, fine.restrict(l1, xf)) < TOL
+        assert rel(t2.prolong(xc), fine.prolong(l1, xc)) < TOL
+        t1 = hp.OrderTransfer(ctx, 1)
+        xcc = t1.restrict(xc)
+        assert rel(xcc, l1.restrict(l0, xc)) < TOL
+        assert rel(t1.prolong(xcc), l1.prolong(l0, xcc)) < TOL
+
+
+def test_coarse_level_operator_is_galerkin_product(orc, hp):
+    # level operators below the finest are T^T A T (ordertransfer.hh:124-144)
+    n = (3, 3, 2)
+    fine = orc.Mesh(n, degree=4)
+    l1 = fine.coarsen(2)
+    l0 = l1.coarsen(1)
+    Af = fine.assemble()
+    A1 = fine.galerkin_restrict(l1, Af)
+    A0 = l1.galerkin_restrict(l0, A1)
+    ctx = hp.Context(n, degree=4)
+    assert ctx.build_p_hierarchy() == 3
+    for lvl, mesh, A in ((1, l1, A1), (0, l0, A0)):
+        x = orc.fill_random(mesh.ndof)
+        assert rel(hp.Operator(ctx, level=lvl).apply(x), A.mv(x)) < TOL
+        assert ctx.uses_uniform_kernel(lvl)
+
+
+@pytest.mark.parametrize("form", [0, 1])
+def test_vcycle_vs_oracle(orc, hp, form):
+    # BASELINE config 4 in small: Q4 -> Q2 -> Q1, 5 pre + 5 post damped block-Jacobi steps, 5 coarse iterations
+    n = (4, 4, 4)
+    fine = orc.Mesh(n, degree=4)
+    l1 = fine.coarsen(2)
+    l0 = l1.coarsen(1)
+    b = orc.fill_random(fine.ndof)
+    x0 = orc.fill_random(fine.ndof, seed=3) * 0.1
+    xr, rr = orc.vcycle([l0, l1, fine], None, x0, b, smoother=1, damping=0.75)
+    ctx = hp.Context(n, degree=4)
+    ctx.build_p_hierarchy()
+    mg = hp.Multigrid(ctx, form=form, damping=0.75)
+    x = x0.copy()
+    bb = b.copy()
+    mg.apply(x, bb)
+    assert rel(x, xr) < 1e-11 and rel(bb, rr) < 1e-10
+    # the returned b is the residual of the returned x (multigrid_impl.hh:60-61)
+    assert rel(bb, b - fine.apply_mf(x, threads=orc.max_threads())) < 1e-10
