@@ -338,6 +338,7 @@ const char* hpdg_last_error(const hpdg_ctx* ctx) { return ctx ? ctx->err.c_str()
 
 int hpdg_set_option(hpdg_ctx* ctx, const char* name, long value) {
   if (!strcmp(name, "force_generic")) { ctx->force_generic = (int)value; return 0; }
+  if (!strcmp(name, "variant")) { ctx->variant = (int)value; return 0; }
   ctx->err = std::string("unknown option ") + name; return 1;
 }
 

@@ -28,11 +28,13 @@ namespace hpdg {
 
 template <int N>
 struct UniParams {
-  double Dt[3][N * N];  // kappa_d * M^-1 S
+  // Dp = kappa_d M^-1 S + the element's own face terms (interior faces on both sides) folded in;
+  // (A0,B0)/(A1,B1): response to the (der,val) trace of the previous/next element
+  double Dp[3][N * N];
+  double A0[3][N], B0[3][N], A1[3][N], B1[3][N];
   double M[N * N];
-  double mt[2][N], mg[2][N], g[2][N];
-  double kap[3];
-  double cpen;
+  double g[2][N];
+  double cohk[3];  // cpen / (kappa_d / 2)
   double factor;
   int n[3];
   int ntile[3];
@@ -51,10 +53,13 @@ template <int N> struct Pitch {
 
 // acc[e][:] += (Tt_dir v)_e for the elements e < len of one pencil.
 // (pd,pv)/(nd,nv): (der,val) of the element before / after the pencil at its near side;
-// pmode/nmode: 0 use them, 1 Dirichlet boundary, 2 natural boundary.
-template <int N, int T, int DIR>
+// pmode/nmode: 0 use them, 1 Dirichlet boundary, 2 natural boundary.  Boundaries are folded in as
+// synthetic neighbour traces so the inner loop is branch free:
+//   Dirichlet: (der -/+ (c/hk) val, -val)   natural: (-der, val)   of the element's own trace.
+template <int N, int T, int DIR, bool FULL>
 __device__ __forceinline__ void pencil_apply(const UniParams<N>& P, const double (&v)[T][N], double (&acc)[T][N],
-                                             int len, double pd, double pv, int pmode, double nd, double nv, int nmode) {
+                                             int len_rt, double pd, double pv, int pmode, double nd, double nv, int nmode) {
+  const int len = FULL ? T : len_rt;
   double d0[T], d1[T];
 #pragma unroll
   for (int e = 0; e < T; e++) {
@@ -63,32 +68,32 @@ __device__ __forceinline__ void pencil_apply(const UniParams<N>& P, const double
     for (int m = 0; m < N; m++) { a = fma(P.g[0][m], v[e][m], a); b = fma(P.g[1][m], v[e][m], b); }
     d0[e] = a; d1[e] = b;
   }
-  const double kap = P.kap[DIR], c = P.cpen;
+  if (pmode == 1) { pd = fma(-P.cohk[DIR], v[0][0], d0[0]); pv = -v[0][0]; }
+  else if (pmode == 2) { pd = -d0[0]; pv = v[0][0]; }
+  {
+    double dl = d1[T - 1], vl = v[T - 1][N - 1];
+    if (!FULL) {
+#pragma unroll
+      for (int e = 0; e < T - 1; e++) if (e == len - 1) { dl = d1[e]; vl = v[e][N - 1]; }
+    }
+    if (nmode == 1) { nd = fma(P.cohk[DIR], vl, dl); nv = -vl; }
+    else if (nmode == 2) { nd = -dl; nv = vl; }
+  }
 #pragma unroll
   for (int e = 0; e < T; e++) {
-    if (e < len) {
-      double qd, qv, bm = 1.0;
-      int mode = 0;
-      if (e == 0) { qd = pd; qv = pv; mode = pmode; }
-      else { qd = d1[e > 0 ? e - 1 : 0]; qv = v[e > 0 ? e - 1 : 0][N - 1]; }
-      if (mode == 1) { qd = d0[e]; qv = 0.0; bm = 2.0; }
-      else if (mode == 2) { qd = -d0[e]; qv = v[e][0]; }
-      double G = 0.5 * (d0[e] + qd), J = v[e][0] - qv;
-      const double a0 = kap * G + c * J, b0 = 0.5 * kap * bm * J;
-      bm = 1.0; mode = 0;
-      if (e == len - 1) { qd = nd; qv = nv; mode = nmode; }
-      else { qd = d0[e < T - 1 ? e + 1 : e]; qv = v[e < T - 1 ? e + 1 : e][0]; }
-      if (mode == 1) { qd = d1[e]; qv = 0.0; bm = 2.0; }
-      else if (mode == 2) { qd = -d1[e]; qv = v[e][N - 1]; }
-      G = 0.5 * (d1[e] + qd); J = v[e][N - 1] - qv;
-      const double a1 = -kap * G + c * J, b1 = -0.5 * kap * bm * J;
+    if (FULL || e < len) {
+      const double qd = (e == 0) ? pd : d1[e > 0 ? e - 1 : 0];
+      const double qv = (e == 0) ? pv : v[e > 0 ? e - 1 : 0][N - 1];
+      double rd = (e == T - 1) ? nd : d0[e < T - 1 ? e + 1 : e];
+      double rv = (e == T - 1) ? nv : v[e < T - 1 ? e + 1 : e][0];
+      if (!FULL && e == len - 1) { rd = nd; rv = nv; }
 #pragma unroll
       for (int i = 0; i < N; i++) {
         double s = acc[e][i];
 #pragma unroll
-        for (int m = 0; m < N; m++) s = fma(P.Dt[DIR][i * N + m], v[e][m], s);
-        s = fma(P.mt[0][i], a0, s); s = fma(P.mg[0][i], b0, s);
-        s = fma(P.mt[1][i], a1, s); s = fma(P.mg[1][i], b1, s);
+        for (int m = 0; m < N; m++) s = fma(P.Dp[DIR][i * N + m], v[e][m], s);
+        s = fma(P.A0[DIR][i], qd, s); s = fma(P.B0[DIR][i], qv, s);
+        s = fma(P.A1[DIR][i], rd, s); s = fma(P.B1[DIR][i], rv, s);
         acc[e][i] = s;
       }
     }
@@ -130,26 +135,14 @@ constexpr int uni_threads() {
   return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
-template <int N, int TX, int TY, int TZ>
-__global__ void __launch_bounds__(uni_threads<N, TX, TY, TZ>())
-k_apply_uniform(const __grid_constant__ UniParams<N> P) {
+// One tile.  FULL: the tile lies completely inside the brick (all masks compile away).
+template <int N, int TX, int TY, int TZ, bool FULL, bool EARLY>
+__device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restrict__ su, double* __restrict__ sw,
+                                          const int x0, const int y0, const int z0, const int lenx_rt, const int leny_rt,
+                                          const int lenz_rt) {
   constexpr int PP = Pitch<N>::PP, EP = Pitch<N>::EP;
   constexpr int N2 = N * N, N3 = N * N * N;
-  extern __shared__ double sm[];
-  double* su = sm;
-  double* sw = sm + TX * TY * TZ * EP;
-
-  int tb = blockIdx.x;
-  const int tx = tb % P.ntile[0]; tb /= P.ntile[0];
-  const int ty = tb % P.ntile[1]; const int tz = tb / P.ntile[1];
-  const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;
-  const int lenx = min(TX, P.n[0] - x0), leny = min(TY, P.n[1] - y0), lenz = min(TZ, P.n[2] - z0);
-  if (P.part != 0) {
-    bool touch = (x0 == 0 && P.bmode[0] == 3) || (x0 + lenx == P.n[0] && P.bmode[1] == 3) ||
-                 (y0 == 0 && P.bmode[2] == 3) || (y0 + leny == P.n[1] && P.bmode[3] == 3) ||
-                 (z0 == 0 && P.bmode[4] == 3) || (z0 + lenz == P.n[2] && P.bmode[5] == 3);
-    if ((P.part == 1) == touch) return;
-  }
+  const int lenx = FULL ? TX : lenx_rt, leny = FULL ? TY : leny_rt, lenz = FULL ? TZ : lenz_rt;
   const long sx = N3, sy = (long)P.n[0] * N3, sz = (long)P.n[0] * P.n[1] * N3;  // element strides in doubles
   const double* __restrict__ X = P.x;
   const int tid = threadIdx.x;
@@ -167,6 +160,7 @@ k_apply_uniform(const __grid_constant__ UniParams<N> P) {
 
   // ---------------- outside traces for the x- and y-roles (issued early) ----------------
   double xpd = 0, xpv = 0, xnd = 0, xnv = 0; int xpm = 0, xnm = 0;
+  auto load_xtr = [&]() {
   if (xact) {
     const long erow = (long)(y0 + xey) * sy + (long)(z0 + xez) * sz;  // element (0, y, z)
     const int node = xj + N * xk;
@@ -179,7 +173,9 @@ k_apply_uniform(const __grid_constant__ UniParams<N> P) {
       if (xnm == 3) { const double* gp = P.ghost[1] + (((long)(y0 + xey) + (long)P.n[1] * (z0 + xez)) * N2 + node) * 2; xnd = gp[0]; xnv = gp[1]; xnm = 0; }
     } else outside_trace<N>(P, X + erow + (long)(x0 + lenx) * sx + N * xj + N2 * xk, 1, 0, xnd, xnv);
   }
+  };
   double ypd = 0, ypv = 0, ynd = 0, ynv = 0; int ypm = 0, ynm = 0;
+  auto load_ytr = [&]() {
   if (yact) {
     const long ecol = (long)(x0 + yex) * sx + (long)(z0 + yez) * sz;  // element (x, 0, z)
     const int node = yi + N * yk;
@@ -192,6 +188,8 @@ k_apply_uniform(const __grid_constant__ UniParams<N> P) {
       if (ynm == 3) { const double* gp = P.ghost[3] + (((long)(x0 + yex) + (long)P.n[0] * (z0 + yez)) * N2 + node) * 2; ynd = gp[0]; ynv = gp[1]; ynm = 0; }
     } else outside_trace<N>(P, X + ecol + (long)(y0 + leny) * sy + yi + N2 * yk, N, 0, ynd, ynv);
   }
+  };
+  if (EARLY) { load_xtr(); load_ytr(); }
 
   // ---------------- P1: z-pencils, global -> registers -> smem ----------------
   if (zact) {
@@ -202,7 +200,7 @@ k_apply_uniform(const __grid_constant__ UniParams<N> P) {
     for (int e = 0; e < TZ; e++)
 #pragma unroll
       for (int k = 0; k < N; k++) {
-        v[e][k] = (e < lenz) ? __ldg(X + ecol + (long)(z0 + e) * sz + node + N2 * k) : 0.0;
+        v[e][k] = (FULL || e < lenz) ? __ldg(X + ecol + (long)(z0 + e) * sz + node + N2 * k) : 0.0;
         acc[e][k] = 0.0;
       }
     double pd = 0, pv = 0, nd = 0, nv = 0; int pm = 0, nm = 0;
@@ -214,10 +212,10 @@ k_apply_uniform(const __grid_constant__ UniParams<N> P) {
       nm = P.bmode[5];
       if (nm == 3) { const double* gp = P.ghost[5] + (((long)(x0 + zex) + (long)P.n[0] * (y0 + zey)) * N2 + node) * 2; nd = gp[0]; nv = gp[1]; nm = 0; }
     } else outside_trace<N>(P, X + ecol + (long)(z0 + lenz) * sz + node, N2, 0, nd, nv);
-    pencil_apply<N, TZ, 2>(P, v, acc, lenz, pd, pv, pm, nd, nv, nm);
+    pencil_apply<N, TZ, 2, FULL>(P, v, acc, lenz, pd, pv, pm, nd, nv, nm);
 #pragma unroll
     for (int e = 0; e < TZ; e++)
-      if (e < lenz) {
+      if (FULL || e < lenz) {
         const int base = (zex + TX * (zey + TY * e)) * EP + node;
 #pragma unroll
         for (int k = 0; k < N; k++) { su[base + PP * k] = v[e][k]; sw[base + PP * k] = acc[e][k]; }
@@ -226,18 +224,19 @@ k_apply_uniform(const __grid_constant__ UniParams<N> P) {
   __syncthreads();
 
   // ---------------- P2: x-pencils ----------------
+  if (!EARLY) { load_xtr(); load_ytr(); }
   if (xact) {
     double v[TX][N], acc[TX][N];
 #pragma unroll
     for (int e = 0; e < TX; e++) {
       const int base = (e + TX * (xey + TY * xez)) * EP + N * xj + PP * xk;
 #pragma unroll
-      for (int i = 0; i < N; i++) { v[e][i] = (e < lenx) ? su[base + i] : 0.0; acc[e][i] = (e < lenx) ? sw[base + i] : 0.0; }
+      for (int i = 0; i < N; i++) { v[e][i] = (FULL || e < lenx) ? su[base + i] : 0.0; acc[e][i] = (FULL || e < lenx) ? sw[base + i] : 0.0; }
     }
-    pencil_apply<N, TX, 0>(P, v, acc, lenx, xpd, xpv, xpm, xnd, xnv, xnm);
+    pencil_apply<N, TX, 0, FULL>(P, v, acc, lenx, xpd, xpv, xpm, xnd, xnv, xnm);
 #pragma unroll
     for (int e = 0; e < TX; e++)
-      if (e < lenx) {
+      if (FULL || e < lenx) {
         const int base = (e + TX * (xey + TY * xez)) * EP + N * xj + PP * xk;
 #pragma unroll
         for (int i = 0; i < N; i++) sw[base + i] = acc[e][i];
@@ -252,12 +251,12 @@ k_apply_uniform(const __grid_constant__ UniParams<N> P) {
     for (int e = 0; e < TY; e++) {
       const int base = (yex + TX * (e + TY * yez)) * EP + yi + PP * yk;
 #pragma unroll
-      for (int j = 0; j < N; j++) { v[e][j] = (e < leny) ? su[base + N * j] : 0.0; acc[e][j] = (e < leny) ? sw[base + N * j] : 0.0; }
+      for (int j = 0; j < N; j++) { v[e][j] = (FULL || e < leny) ? su[base + N * j] : 0.0; acc[e][j] = (FULL || e < leny) ? sw[base + N * j] : 0.0; }
     }
-    pencil_apply<N, TY, 1>(P, v, acc, leny, ypd, ypv, ypm, ynd, ynv, ynm);
+    pencil_apply<N, TY, 1, FULL>(P, v, acc, leny, ypd, ypv, ypm, ynd, ynv, ynm);
 #pragma unroll
     for (int e = 0; e < TY; e++)
-      if (e < leny) {
+      if (FULL || e < leny) {
         mass_line<N>(P, acc[e]);
         const int base = (yex + TX * (e + TY * yez)) * EP + yi + PP * yk;
 #pragma unroll
@@ -270,7 +269,7 @@ k_apply_uniform(const __grid_constant__ UniParams<N> P) {
   if (xact) {
 #pragma unroll
     for (int e = 0; e < TX; e++)
-      if (e < lenx) {
+      if (FULL || e < lenx) {
         const int base = (e + TX * (xey + TY * xez)) * EP + N * xj + PP * xk;
         double a[N];
 #pragma unroll
@@ -288,7 +287,7 @@ k_apply_uniform(const __grid_constant__ UniParams<N> P) {
     const int node = zi + N * zj;
 #pragma unroll
     for (int e = 0; e < TZ; e++)
-      if (e < lenz) {
+      if (FULL || e < lenz) {
         const int base = (zex + TX * (zey + TY * e)) * EP + node;
         double a[N];
 #pragma unroll
@@ -299,6 +298,28 @@ k_apply_uniform(const __grid_constant__ UniParams<N> P) {
         for (int k = 0; k < N; k++) yo[N2 * k] = P.factor * a[k];
       }
   }
+}
+
+template <int N, int TX, int TY, int TZ, int MINB, bool EARLY>
+__global__ void __launch_bounds__(uni_threads<N, TX, TY, TZ>(), MINB)
+k_apply_uniform(const __grid_constant__ UniParams<N> P) {
+  constexpr int EP = Pitch<N>::EP;
+  extern __shared__ double sm[];
+  double* su = sm;
+  double* sw = sm + TX * TY * TZ * EP;
+  int tb = blockIdx.x;
+  const int tx = tb % P.ntile[0]; tb /= P.ntile[0];
+  const int ty = tb % P.ntile[1]; const int tz = tb / P.ntile[1];
+  const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;
+  const int lenx = min(TX, P.n[0] - x0), leny = min(TY, P.n[1] - y0), lenz = min(TZ, P.n[2] - z0);
+  if (P.part != 0) {
+    bool touch = (x0 == 0 && P.bmode[0] == 3) || (x0 + lenx == P.n[0] && P.bmode[1] == 3) ||
+                 (y0 == 0 && P.bmode[2] == 3) || (y0 + leny == P.n[1] && P.bmode[3] == 3) ||
+                 (z0 == 0 && P.bmode[4] == 3) || (z0 + lenz == P.n[2] && P.bmode[5] == 3);
+    if ((P.part == 1) == touch) return;
+  }
+  if (lenx == TX && leny == TY && lenz == TZ) tile_body<N, TX, TY, TZ, true, EARLY>(P, su, sw, x0, y0, z0, TX, TY, TZ);
+  else tile_body<N, TX, TY, TZ, false, EARLY>(P, su, sw, x0, y0, z0, lenx, leny, lenz);
 }
 
 // ---- ghost trace packing (sender side of the halo exchange) -------------------------
@@ -331,21 +352,29 @@ __global__ void k_pack_traces(const double* __restrict__ x, double* __restrict__
   }
 }
 
-template <int N, int TX, int TY, int TZ>
+template <int N, int TX, int TY, int TZ, int MINB, bool EARLY = true>
 static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part) {
   static UniParams<N> P;  // rebuilt per call (cheap); static to keep it off the stack
   const DegTable& T = host_tables().deg[N - 1];
-  double kap[3];
+  const double c = ctx->sigma * (double)L.pen_uni * L.pen_uni;
   for (int d = 0; d < 3; d++) {
-    double k = 1.0 / L.h[d];
-    for (int dd = 0; dd < 3; dd++) if (dd != d) k *= L.h[dd];
-    kap[d] = k; P.kap[d] = k;
+    double kap = 1.0 / L.h[d];
+    for (int dd = 0; dd < 3; dd++) if (dd != d) kap *= L.h[dd];
+    const double hk = 0.5 * kap;
+    P.cohk[d] = c / hk;
+    for (int i = 0; i < N; i++) {
+      for (int j = 0; j < N; j++)
+        P.Dp[d][i * N + j] = kap * T.MinvS[i * kMaxN + j]
+                             + T.mt[0][i] * (hk * T.g[0][j] + c * T.t[0][j]) + T.mg[0][i] * (hk * T.t[0][j])
+                             + T.mt[1][i] * (-hk * T.g[1][j] + c * T.t[1][j]) + T.mg[1][i] * (-hk * T.t[1][j]);
+      P.A0[d][i] = hk * T.mt[0][i];
+      P.B0[d][i] = -c * T.mt[0][i] - hk * T.mg[0][i];
+      P.A1[d][i] = -hk * T.mt[1][i];
+      P.B1[d][i] = -c * T.mt[1][i] + hk * T.mg[1][i];
+    }
   }
-  for (int d = 0; d < 3; d++)
-    for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) P.Dt[d][i * N + j] = kap[d] * T.MinvS[i * kMaxN + j];
   for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) P.M[i * N + j] = T.M[i * kMaxN + j];
-  for (int s = 0; s < 2; s++) for (int i = 0; i < N; i++) { P.mt[s][i] = T.mt[s][i]; P.mg[s][i] = T.mg[s][i]; P.g[s][i] = T.g[s][i]; }
-  P.cpen = ctx->sigma * (double)L.pen_uni * L.pen_uni;
+  for (int s = 0; s < 2; s++) for (int i = 0; i < N; i++) P.g[s][i] = T.g[s][i];
   P.factor = factor;
   const int tdim[3] = {TX, TY, TZ};
   for (int d = 0; d < 3; d++) { P.n[d] = L.n[d]; P.ntile[d] = (L.n[d] + tdim[d] - 1) / tdim[d]; }
@@ -362,11 +391,11 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
   constexpr size_t smem = sizeof(double) * 2 * TX * TY * TZ * Pitch<N>::EP;
   static bool attr_set = false;
   if (!attr_set) {
-    HPDG_CUDA(cudaFuncSetAttribute(k_apply_uniform<N, TX, TY, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HPDG_CUDA(cudaFuncSetAttribute(k_apply_uniform<N, TX, TY, TZ, MINB, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const long ntiles = (long)P.ntile[0] * P.ntile[1] * P.ntile[2];
-  k_apply_uniform<N, TX, TY, TZ><<<(unsigned)ntiles, threads, smem, ctx->stream>>>(P);
+  k_apply_uniform<N, TX, TY, TZ, MINB, EARLY><<<(unsigned)ntiles, threads, smem, ctx->stream>>>(P);
   ctx->launches++;
   HPDG_CUDA(cudaGetLastError());
   return 0;
@@ -380,11 +409,22 @@ int uniform_supported(const Ctx* ctx, const Level& L) {
 
 int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part) {
   switch (L.p_uni) {
-    case 1: return launch_uni<2, 4, 4, 4>(ctx, L, x, y, factor, part);
-    case 2: return launch_uni<3, 4, 4, 4>(ctx, L, x, y, factor, part);
-    case 3: return launch_uni<4, 4, 4, 4>(ctx, L, x, y, factor, part);
-    case 4: return launch_uni<5, 4, 4, 2>(ctx, L, x, y, factor, part);
-    case 5: return launch_uni<6, 2, 2, 2>(ctx, L, x, y, factor, part);
+    case 1: return launch_uni<2, 4, 4, 4, 4>(ctx, L, x, y, factor, part);
+    case 2: return launch_uni<3, 4, 4, 4, 3>(ctx, L, x, y, factor, part);
+    case 3:
+      switch (ctx->variant) {
+        case 1: return launch_uni<4, 4, 4, 4, 2, true>(ctx, L, x, y, factor, part);
+        case 2: return launch_uni<4, 4, 4, 4, 3, false>(ctx, L, x, y, factor, part);
+        case 3: return launch_uni<4, 4, 4, 4, 2, false>(ctx, L, x, y, factor, part);
+        case 4: return launch_uni<4, 4, 4, 2, 4, false>(ctx, L, x, y, factor, part);
+        case 5: return launch_uni<4, 4, 4, 2, 3, false>(ctx, L, x, y, factor, part);
+        case 6: return launch_uni<4, 4, 4, 2, 4, true>(ctx, L, x, y, factor, part);
+        case 7: return launch_uni<4, 4, 2, 4, 4, false>(ctx, L, x, y, factor, part);
+        case 8: return launch_uni<4, 2, 4, 4, 4, false>(ctx, L, x, y, factor, part);
+        default: return launch_uni<4, 4, 4, 4, 3, true>(ctx, L, x, y, factor, part);
+      }
+    case 4: return launch_uni<5, 4, 4, 2, 2>(ctx, L, x, y, factor, part);
+    case 5: return launch_uni<6, 2, 2, 2, 2>(ctx, L, x, y, factor, part);
     default: return -1;
   }
 }

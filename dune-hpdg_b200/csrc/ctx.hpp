@@ -88,6 +88,7 @@ struct Ctx {
   double *h_pin_in = nullptr, *h_pin_out = nullptr;
   size_t pin_cap = 0;
   int force_generic = 0;
+  int variant = 0;  // kernel variant selector for tuning experiments
   long launches = 0;  // kernels launched by this context (bench.py's gpu_launches)
 };
 

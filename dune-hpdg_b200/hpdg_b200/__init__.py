@@ -192,7 +192,7 @@ class Context:
         self._ck(lib().hpdg_host_alloc(self._h, ndoubles * 8, C.byref(p)))
         buf = (C.c_double * ndoubles).from_address(p.value)
         a = np.frombuffer(buf, dtype=np.float64)
-        a._hpdg_keep = buf
+        self.__dict__.setdefault('_pinned', []).append(buf)
         return a, p.value
 
     def host_free(self, p):
