@@ -20,6 +20,7 @@
 // boundary, from the ghost trace buffer filled by the NCCL halo exchange); domain boundaries are
 // folded in as synthetic neighbour traces (Dirichlet / natural).
 // Algorithmic HBM traffic: read u once + write y once = 16 B/DoF.
+#include <algorithm>
 #include <cstdio>
 
 #include "ctx.hpp"
@@ -42,6 +43,7 @@ struct UniParams {
   const double* ghost[6];  // [face elem][node][2] = (der, val) of the remote element at its near side
   const double* x;
   double* y;
+  int dbg;   // timing experiments only: 1 = skip outside-trace loads (wrong results)
   int part;  // 0 all tiles, 1 only tiles not touching a ghost face, 2 only tiles touching one
 };
 
@@ -56,9 +58,11 @@ template <int N> struct Pitch {
 // pmode/nmode: 0 use them, 1 Dirichlet boundary, 2 natural boundary.  Boundaries are folded in as
 // synthetic neighbour traces so the inner loop is branch free:
 //   Dirichlet: (der -/+ (c/hk) val, -val)   natural: (-der, val)   of the element's own trace.
-template <int N, int T, int DIR, bool FULL>
-__device__ __forceinline__ void pencil_apply(const UniParams<N>& P, const double (&v)[T][N], double (&acc)[T][N],
-                                             int len_rt, double pd, double pv, int pmode, double nd, double nv, int nmode) {
+// accin(e,i) supplies the accumulator's initial value, out(e,a) consumes element e's N results
+// right after they are formed (keeps the live register set to one element's worth).
+template <int N, int T, int DIR, bool FULL, class AccIn, class Out>
+__device__ __forceinline__ void pencil_apply(const UniParams<N>& P, const double (&v)[T][N], int len_rt, double pd,
+                                             double pv, int pmode, double nd, double nv, int nmode, AccIn accin, Out out) {
   const int len = FULL ? T : len_rt;
   double d0[T], d1[T];
 #pragma unroll
@@ -87,15 +91,17 @@ __device__ __forceinline__ void pencil_apply(const UniParams<N>& P, const double
       double rd = (e == T - 1) ? nd : d0[e < T - 1 ? e + 1 : e];
       double rv = (e == T - 1) ? nv : v[e < T - 1 ? e + 1 : e][0];
       if (!FULL && e == len - 1) { rd = nd; rv = nv; }
+      double a[N];
 #pragma unroll
       for (int i = 0; i < N; i++) {
-        double s = acc[e][i];
+        double s = accin(e, i);
 #pragma unroll
         for (int m = 0; m < N; m++) s = fma(P.Dp[DIR][i * N + m], v[e][m], s);
         s = fma(P.A0[DIR][i], qd, s); s = fma(P.B0[DIR][i], qv, s);
         s = fma(P.A1[DIR][i], rd, s); s = fma(P.B1[DIR][i], rv, s);
-        acc[e][i] = s;
+        a[i] = s;
       }
+      out(e, a);
     }
   }
 }
@@ -118,6 +124,7 @@ __device__ __forceinline__ void mass_line(const UniParams<N>& P, double (&a)[N])
 template <int N>
 __device__ __forceinline__ void outside_trace(const UniParams<N>& P, const double* __restrict__ line, long stride,
                                               int side /* near side of that element */, double& der, double& val) {
+  if (P.dbg & 1) { der = 0; val = 0; return; }
   double d = 0, last = 0, first = 0;
 #pragma unroll
   for (int m = 0; m < N; m++) {
@@ -136,10 +143,15 @@ constexpr int uni_threads() {
 }
 
 // One tile.  FULL: the tile lies completely inside the brick (all masks compile away).
-template <int N, int TX, int TY, int TZ, bool FULL, bool EARLY>
+struct ZTrace { double pd, pv, nd, nv; int pm, nm; };
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// PIPE: u of the tile is already in su (cp.async prefetch) and the z traces come in through zt;
+// hook() runs between P3 and P4 (the pipelined kernel issues the next tile's z-halo loads there).
+template <int N, int TX, int TY, int TZ, bool FULL, bool EARLY, bool PIPE = false, class Hook = NoHook>
 __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restrict__ su, double* __restrict__ sw,
                                           const int x0, const int y0, const int z0, const int lenx_rt, const int leny_rt,
-                                          const int lenz_rt) {
+                                          const int lenz_rt, const ZTrace zt = ZTrace(), Hook hook = Hook()) {
   constexpr int PP = Pitch<N>::PP, EP = Pitch<N>::EP;
   constexpr int N2 = N * N, N3 = N * N * N;
   const int lenx = FULL ? TX : lenx_rt, leny = FULL ? TY : leny_rt, lenz = FULL ? TZ : lenz_rt;
@@ -195,15 +207,18 @@ __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restr
   if (zact) {
     const long ecol = (long)(x0 + zex) * sx + (long)(y0 + zey) * sy;  // element (x, y, 0)
     const int node = zi + N * zj;
-    double v[TZ][N], acc[TZ][N];
+    double v[TZ][N];
+    const int zbase = (zex + TX * zey) * EP + node;
 #pragma unroll
     for (int e = 0; e < TZ; e++)
 #pragma unroll
       for (int k = 0; k < N; k++) {
-        v[e][k] = (FULL || e < lenz) ? __ldg(X + ecol + (long)(z0 + e) * sz + node + N2 * k) : 0.0;
-        acc[e][k] = 0.0;
+        if (PIPE) v[e][k] = (FULL || e < lenz) ? su[zbase + TX * TY * EP * e + PP * k] : 0.0;
+        else v[e][k] = (FULL || e < lenz) ? __ldg(X + ecol + (long)(z0 + e) * sz + node + N2 * k) : 0.0;
       }
     double pd = 0, pv = 0, nd = 0, nv = 0; int pm = 0, nm = 0;
+    if (PIPE) { pd = zt.pd; pv = zt.pv; nd = zt.nd; nv = zt.nv; pm = zt.pm; nm = zt.nm; }
+    else {
     if (z0 == 0) {
       pm = P.bmode[4];
       if (pm == 3) { const double* gp = P.ghost[4] + (((long)(x0 + zex) + (long)P.n[0] * (y0 + zey)) * N2 + node) * 2; pd = gp[0]; pv = gp[1]; pm = 0; }
@@ -212,58 +227,56 @@ __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restr
       nm = P.bmode[5];
       if (nm == 3) { const double* gp = P.ghost[5] + (((long)(x0 + zex) + (long)P.n[0] * (y0 + zey)) * N2 + node) * 2; nd = gp[0]; nv = gp[1]; nm = 0; }
     } else outside_trace<N>(P, X + ecol + (long)(z0 + lenz) * sz + node, N2, 0, nd, nv);
-    pencil_apply<N, TZ, 2, FULL>(P, v, acc, lenz, pd, pv, pm, nd, nv, nm);
+    }
+    pencil_apply<N, TZ, 2, FULL>(P, v, lenz, pd, pv, pm, nd, nv, nm,
+      [](int, int) { return 0.0; },
+      [&](int e, const double (&a)[N]) {
+        const int base = zbase + TX * TY * EP * e;
 #pragma unroll
-    for (int e = 0; e < TZ; e++)
-      if (FULL || e < lenz) {
-        const int base = (zex + TX * (zey + TY * e)) * EP + node;
-#pragma unroll
-        for (int k = 0; k < N; k++) { su[base + PP * k] = v[e][k]; sw[base + PP * k] = acc[e][k]; }
-      }
+        for (int k = 0; k < N; k++) { if (!PIPE) su[base + PP * k] = v[e][k]; sw[base + PP * k] = a[k]; }
+      });
   }
   __syncthreads();
 
   // ---------------- P2: x-pencils ----------------
   if (!EARLY) { load_xtr(); load_ytr(); }
   if (xact) {
-    double v[TX][N], acc[TX][N];
-#pragma unroll
-    for (int e = 0; e < TX; e++) {
-      const int base = (e + TX * (xey + TY * xez)) * EP + N * xj + PP * xk;
-#pragma unroll
-      for (int i = 0; i < N; i++) { v[e][i] = (FULL || e < lenx) ? su[base + i] : 0.0; acc[e][i] = (FULL || e < lenx) ? sw[base + i] : 0.0; }
-    }
-    pencil_apply<N, TX, 0, FULL>(P, v, acc, lenx, xpd, xpv, xpm, xnd, xnv, xnm);
+    double v[TX][N];
+    const int xbase = TX * (xey + TY * xez) * EP + N * xj + PP * xk;
 #pragma unroll
     for (int e = 0; e < TX; e++)
-      if (FULL || e < lenx) {
-        const int base = (e + TX * (xey + TY * xez)) * EP + N * xj + PP * xk;
 #pragma unroll
-        for (int i = 0; i < N; i++) sw[base + i] = acc[e][i];
-      }
+      for (int i = 0; i < N; i++) v[e][i] = (FULL || e < lenx) ? su[xbase + e * EP + i] : 0.0;
+    pencil_apply<N, TX, 0, FULL>(P, v, lenx, xpd, xpv, xpm, xnd, xnv, xnm,
+      [&](int e, int i) { return sw[xbase + e * EP + i]; },
+      [&](int e, const double (&a)[N]) {
+#pragma unroll
+        for (int i = 0; i < N; i++) sw[xbase + e * EP + i] = a[i];
+      });
   }
   __syncthreads();
 
   // ---------------- P3: y-pencils, then M_y ----------------
   if (yact) {
-    double v[TY][N], acc[TY][N];
-#pragma unroll
-    for (int e = 0; e < TY; e++) {
-      const int base = (yex + TX * (e + TY * yez)) * EP + yi + PP * yk;
-#pragma unroll
-      for (int j = 0; j < N; j++) { v[e][j] = (FULL || e < leny) ? su[base + N * j] : 0.0; acc[e][j] = (FULL || e < leny) ? sw[base + N * j] : 0.0; }
-    }
-    pencil_apply<N, TY, 1, FULL>(P, v, acc, leny, ypd, ypv, ypm, ynd, ynv, ynm);
+    double v[TY][N];
+    const int ybase = (yex + TX * TY * yez) * EP + yi + PP * yk;
 #pragma unroll
     for (int e = 0; e < TY; e++)
-      if (FULL || e < leny) {
-        mass_line<N>(P, acc[e]);
-        const int base = (yex + TX * (e + TY * yez)) * EP + yi + PP * yk;
 #pragma unroll
-        for (int j = 0; j < N; j++) sw[base + N * j] = acc[e][j];
-      }
+      for (int j = 0; j < N; j++) v[e][j] = (FULL || e < leny) ? su[ybase + TX * EP * e + N * j] : 0.0;
+    pencil_apply<N, TY, 1, FULL>(P, v, leny, ypd, ypv, ypm, ynd, ynv, ynm,
+      [&](int e, int j) { return sw[ybase + TX * EP * e + N * j]; },
+      [&](int e, const double (&a)[N]) {
+        double b[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) b[j] = a[j];
+        mass_line<N>(P, b);
+#pragma unroll
+        for (int j = 0; j < N; j++) sw[ybase + TX * EP * e + N * j] = b[j];
+      });
   }
   __syncthreads();
+  hook();
 
   // ---------------- P4: M_x ----------------
   if (xact) {
@@ -320,6 +333,139 @@ k_apply_uniform(const __grid_constant__ UniParams<N> P) {
   }
   if (lenx == TX && leny == TY && lenz == TZ) tile_body<N, TX, TY, TZ, true, EARLY>(P, su, sw, x0, y0, z0, TX, TY, TZ);
   else tile_body<N, TX, TY, TZ, false, EARLY>(P, su, sw, x0, y0, z0, lenx, leny, lenz);
+}
+
+// ---- persistent, software-pipelined variant -----------------------------------------------------
+// One CTA per SM slot loops over tiles (stride gridDim.x, x-fastest so concurrently running CTAs work on
+// neighbouring tiles and their halo reads hit L2).  While tile t is computed, tile t+1's DoF blocks stream
+// from HBM straight into the second shared-memory u buffer with cp.async (no registers held), and its
+// z-halo lines are fetched between P3 and P4; a CTA therefore always has ~one tile of HBM reads in flight.
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K) : "memory"); }
+
+template <int N, int TX, int TY, int TZ>
+__global__ void __launch_bounds__(uni_threads<N, TX, TY, TZ>(), 2)
+k_apply_uniform_pipe(const __grid_constant__ UniParams<N> P) {
+  constexpr int PP = Pitch<N>::PP, EP = Pitch<N>::EP;
+  constexpr int N2 = N * N, N3 = N * N * N;
+  extern __shared__ double sm[];
+  double* subuf[2] = {sm, sm + TX * TY * TZ * EP};
+  double* sw = sm + 2 * TX * TY * TZ * EP;
+  const long ntiles = (long)P.ntile[0] * P.ntile[1] * P.ntile[2];
+  const long G = gridDim.x;
+  const long sx = N3, sy = (long)P.n[0] * N3, sz = (long)P.n[0] * P.n[1] * N3;
+  const double* __restrict__ X = P.x;
+  const int tid = threadIdx.x;
+  const int zi = tid % N, zj = (tid / N) % N, zex = (tid / N2) % TX, zey = tid / (N2 * TX);
+  const bool zrole = tid < N2 * TX * TY;
+  const int node = zi + N * zj;
+
+  struct Tile { int x0, y0, z0, lenx, leny, lenz; };
+  auto coords = [&](long t) {
+    Tile c;
+    const int tx = (int)(t % P.ntile[0]); t /= P.ntile[0];
+    const int ty = (int)(t % P.ntile[1]); const int tz = (int)(t / P.ntile[1]);
+    c.x0 = tx * TX; c.y0 = ty * TY; c.z0 = tz * TZ;
+    c.lenx = min(TX, P.n[0] - c.x0); c.leny = min(TY, P.n[1] - c.y0); c.lenz = min(TZ, P.n[2] - c.z0);
+    return c;
+  };
+  auto next_valid = [&](long t) {
+    if (P.part == 0) return t;
+    for (; t < ntiles; t += G) {
+      const Tile c = coords(t);
+      const bool touch = (c.x0 == 0 && P.bmode[0] == 3) || (c.x0 + c.lenx == P.n[0] && P.bmode[1] == 3) ||
+                         (c.y0 == 0 && P.bmode[2] == 3) || (c.y0 + c.leny == P.n[1] && P.bmode[3] == 3) ||
+                         (c.z0 == 0 && P.bmode[4] == 3) || (c.z0 + c.lenz == P.n[2] && P.bmode[5] == 3);
+      if ((P.part == 1) != touch) break;
+    }
+    return t;
+  };
+  auto issue_tile = [&](const Tile& c, double* sbuf) {
+    if (zrole && zex < c.lenx && zey < c.leny) {
+      const double* src = X + (long)(c.x0 + zex) * sx + (long)(c.y0 + zey) * sy + (long)c.z0 * sz + node;
+      double* dst = sbuf + (zex + TX * zey) * EP + node;
+#pragma unroll
+      for (int e = 0; e < TZ; e++)
+        if (e < c.lenz) {
+#pragma unroll
+          for (int k = 0; k < N; k++) cp_async8(dst + TX * TY * EP * e + PP * k, src + (long)e * sz + N2 * k);
+        }
+    }
+  };
+  // z-halo of a tile: raw DoF lines of the elements below / above (or the ghost trace / boundary mode)
+  auto load_zraw = [&](const Tile& c, double (&zr)[2][N], int& pm, int& nm) {
+    pm = nm = 0;
+    if (!(zrole && zex < c.lenx && zey < c.leny)) return;
+    const long ecol = (long)(c.x0 + zex) * sx + (long)(c.y0 + zey) * sy;
+    const long fe = ((long)(c.x0 + zex) + (long)P.n[0] * (c.y0 + zey)) * N2 + node;
+    if (c.z0 == 0) {
+      pm = P.bmode[4];
+      if (pm == 3) { zr[0][0] = P.ghost[4][fe * 2]; zr[0][1] = P.ghost[4][fe * 2 + 1]; pm = 4; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < N; k++) zr[0][k] = __ldg(X + ecol + (long)(c.z0 - 1) * sz + node + N2 * k);
+    }
+    if (c.z0 + c.lenz == P.n[2]) {
+      nm = P.bmode[5];
+      if (nm == 3) { zr[1][0] = P.ghost[5][fe * 2]; zr[1][1] = P.ghost[5][fe * 2 + 1]; nm = 4; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < N; k++) zr[1][k] = __ldg(X + ecol + (long)(c.z0 + c.lenz) * sz + node + N2 * k);
+    }
+  };
+  auto reduce_zraw = [&](const double (&zr)[2][N], int pm, int nm) {
+    ZTrace z; z.pd = z.pv = z.nd = z.nv = 0; z.pm = pm; z.nm = nm;
+    if (pm == 4) { z.pd = zr[0][0]; z.pv = zr[0][1]; z.pm = 0; }
+    else if (pm == 0) {
+      double d = 0;
+#pragma unroll
+      for (int k = 0; k < N; k++) d = fma(P.g[1][k], zr[0][k], d);
+      z.pd = d; z.pv = zr[0][N - 1];
+    }
+    if (nm == 4) { z.nd = zr[1][0]; z.nv = zr[1][1]; z.nm = 0; }
+    else if (nm == 0) {
+      double d = 0;
+#pragma unroll
+      for (int k = 0; k < N; k++) d = fma(P.g[0][k], zr[1][k], d);
+      z.nd = d; z.nv = zr[1][0];
+    }
+    return z;
+  };
+
+  long t = next_valid(blockIdx.x);
+  if (t >= ntiles) return;
+  Tile cur = coords(t);
+  issue_tile(cur, subuf[0]);
+  cp_async_commit();
+  ZTrace zt;
+  {
+    double zr[2][N] = {}; int pm, nm;
+    load_zraw(cur, zr, pm, nm);
+    zt = reduce_zraw(zr, pm, nm);
+  }
+  int buf = 0;
+  while (true) {
+    const long tn = next_valid(t + G);
+    const bool has_next = tn < ntiles;
+    Tile nxt = cur;
+    if (has_next) { nxt = coords(tn); issue_tile(nxt, subuf[buf ^ 1]); }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    double zr[2][N] = {}; int npm = 0, nnm = 0;
+    auto hook = [&]() { if (has_next) load_zraw(nxt, zr, npm, nnm); };
+    if (cur.lenx == TX && cur.leny == TY && cur.lenz == TZ)
+      tile_body<N, TX, TY, TZ, true, true, true>(P, subuf[buf], sw, cur.x0, cur.y0, cur.z0, TX, TY, TZ, zt, hook);
+    else
+      tile_body<N, TX, TY, TZ, false, true, true>(P, subuf[buf], sw, cur.x0, cur.y0, cur.z0, cur.lenx, cur.leny, cur.lenz, zt, hook);
+    if (!has_next) break;
+    zt = reduce_zraw(zr, npm, nnm);
+    cur = nxt; t = tn; buf ^= 1;
+  }
 }
 
 // ---- ghost trace packing (sender side of the halo exchange) -------------------------
@@ -386,7 +532,26 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
       P.bmode[f] = 3; P.ghost[f] = ctx->ghost.d_recv[f];
     } else P.bmode[f] = ctx->dirichlet ? 1 : 2;
   }
-  P.x = x; P.y = y; P.part = part;
+  P.x = x; P.y = y; P.part = part; P.dbg = ctx->variant / 100;
+  if (ctx->variant % 100 >= 10) {
+    constexpr int threads = uni_threads<N, TX, TY, TZ>();
+    constexpr size_t smem = sizeof(double) * 3 * TX * TY * TZ * Pitch<N>::EP;
+    static bool attr_set_pipe = false;
+    static int grid = 0;
+    if (!attr_set_pipe) {
+      HPDG_CUDA(cudaFuncSetAttribute(k_apply_uniform_pipe<N, TX, TY, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int nsm = 0, occ = 0;
+      HPDG_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+      HPDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_apply_uniform_pipe<N, TX, TY, TZ>, threads, smem));
+      grid = nsm * (occ > 0 ? occ : 1);
+      attr_set_pipe = true;
+    }
+    const long ntiles = (long)P.ntile[0] * P.ntile[1] * P.ntile[2];
+    k_apply_uniform_pipe<N, TX, TY, TZ><<<(unsigned)std::min<long>(grid, ntiles), threads, smem, ctx->stream>>>(P);
+    ctx->launches++;
+    HPDG_CUDA(cudaGetLastError());
+    return 0;
+  }
   constexpr int threads = uni_threads<N, TX, TY, TZ>();
   constexpr size_t smem = sizeof(double) * 2 * TX * TY * TZ * Pitch<N>::EP;
   static bool attr_set = false;
@@ -412,18 +577,26 @@ int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double 
     case 1: return launch_uni<2, 4, 4, 4, 4>(ctx, L, x, y, factor, part);
     case 2: return launch_uni<3, 4, 4, 4, 3>(ctx, L, x, y, factor, part);
     case 3:
-      switch (ctx->variant) {
+      switch (ctx->variant % 100) {
         case 1: return launch_uni<4, 4, 4, 4, 2, true>(ctx, L, x, y, factor, part);
-        case 2: return launch_uni<4, 4, 4, 4, 3, false>(ctx, L, x, y, factor, part);
         case 3: return launch_uni<4, 4, 4, 4, 2, false>(ctx, L, x, y, factor, part);
         case 4: return launch_uni<4, 4, 4, 2, 4, false>(ctx, L, x, y, factor, part);
         case 5: return launch_uni<4, 4, 4, 2, 3, false>(ctx, L, x, y, factor, part);
         case 6: return launch_uni<4, 4, 4, 2, 4, true>(ctx, L, x, y, factor, part);
         case 7: return launch_uni<4, 4, 2, 4, 4, false>(ctx, L, x, y, factor, part);
         case 8: return launch_uni<4, 2, 4, 4, 4, false>(ctx, L, x, y, factor, part);
-        default: return launch_uni<4, 4, 4, 4, 3, true>(ctx, L, x, y, factor, part);
+        case 9: return launch_uni<4, 4, 4, 4, 3, true>(ctx, L, x, y, factor, part);
+        default: return launch_uni<4, 4, 4, 4, 3, false>(ctx, L, x, y, factor, part);
       }
-    case 4: return launch_uni<5, 4, 4, 2, 2>(ctx, L, x, y, factor, part);
+    case 4:
+      switch (ctx->variant % 100) {
+        case 1: return launch_uni<5, 4, 4, 2, 1, false>(ctx, L, x, y, factor, part);
+        case 2: return launch_uni<5, 4, 4, 2, 2, false>(ctx, L, x, y, factor, part);
+        case 3: return launch_uni<5, 4, 2, 2, 2, false>(ctx, L, x, y, factor, part);
+        case 4: return launch_uni<5, 2, 2, 2, 4, false>(ctx, L, x, y, factor, part);
+        case 5: return launch_uni<5, 3, 3, 3, 2, false>(ctx, L, x, y, factor, part);
+        default: return launch_uni<5, 2, 2, 2, 3, false>(ctx, L, x, y, factor, part);
+      }
     case 5: return launch_uni<6, 2, 2, 2, 2>(ctx, L, x, y, factor, part);
     default: return -1;
   }

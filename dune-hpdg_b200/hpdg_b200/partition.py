@@ -1,0 +1,76 @@
+"""Host-side brick partition of a structured mesh over the GPUs of one node.
+
+Models the reference's element-wise owner/overlap decomposition (dune/hpdg/parallel/communicationhpdg.hh:261-263):
+every element is owned by exactly one rank; what crosses rank boundaries per operator apply is, per ghost face node,
+the pair (der, val) of the neighbour's DoF line normal to the face ("face traces") instead of whole ghost blocks
+(communicationhpdg.hh:309-326).  Pure index logic, no arithmetic on DoFs except `face_traces` (test helper layout
+contract for the pack kernel k_pack_traces).
+"""
+import numpy as np
+
+PGRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+def pgrid_for(nranks):
+    if nranks not in PGRID:
+        raise ValueError(f"unsupported rank count {nranks}; supported: {sorted(PGRID)}")
+    return PGRID[nranks]
+
+
+def coords(rank, pgrid):
+    return (rank % pgrid[0], (rank // pgrid[0]) % pgrid[1], rank // (pgrid[0] * pgrid[1]))
+
+
+def rank_of(c, pgrid):
+    return c[0] + pgrid[0] * (c[1] + pgrid[1] * c[2])
+
+
+def peers(rank, pgrid):
+    """face index f = 2*dir + side -> neighbour rank or None (domain boundary)"""
+    c = coords(rank, pgrid)
+    out = {}
+    for d in range(3):
+        for s in range(2):
+            cc = list(c)
+            cc[d] += 1 if s else -1
+            out[2 * d + s] = rank_of(cc, pgrid) if 0 <= cc[d] < pgrid[d] else None
+    return out
+
+
+def local_to_global_elements(rank, pgrid, n):
+    """global (x-fastest) element index of every local element of the rank's n[0] x n[1] x n[2] brick"""
+    c = coords(rank, pgrid)
+    N = [n[d] * pgrid[d] for d in range(3)]
+    ix = np.arange(n[0]) + c[0] * n[0]
+    iy = np.arange(n[1]) + c[1] * n[1]
+    iz = np.arange(n[2]) + c[2] * n[2]
+    g = ix[None, None, :] + N[0] * (iy[None, :, None] + N[1] * iz[:, None, None])
+    return g.reshape(-1)
+
+
+def scatter_global_vector(xg, rank, pgrid, n, ndof_per_elem):
+    """rank-local DynamicBlockVector slice (uniform block size) of a global vector"""
+    g = local_to_global_elements(rank, pgrid, n)
+    return np.ascontiguousarray(xg.reshape(-1, ndof_per_elem)[g].reshape(-1))
+
+
+def face_traces(x_local, n, p, f, g_end):
+    """(der, val) traces the rank SENDS across brick face f = 2*dir+side, in the layout the receiving kernel expects:
+    [face element (lower tangential direction fastest)][face node (lower fastest)][2].
+    g_end[s] = derivatives l_i'(s) of the 1-D basis at end point s (unit interval)."""
+    N = p + 1
+    d, s = f // 2, f % 2
+    u = x_local.reshape(n[2], n[1], n[0], N, N, N)  # [ez][ey][ex][k][j][i]
+    if d == 0:
+        blk = u[:, :, n[0] - 1 if s else 0]          # [ez][ey][k][j][i]
+        der = np.einsum("zykji,i->zykj", blk, g_end[s])
+        val = blk[..., N - 1 if s else 0]
+    elif d == 1:
+        blk = u[:, n[1] - 1 if s else 0]             # [ez][ex][k][j][i]
+        der = np.einsum("zxkji,j->zxki", blk, g_end[s])
+        val = blk[:, :, :, N - 1 if s else 0, :]
+    else:
+        blk = u[n[2] - 1 if s else 0]                # [ey][ex][k][j][i]
+        der = np.einsum("yxkji,k->yxji", blk, g_end[s])
+        val = blk[:, :, N - 1 if s else 0]
+    return np.ascontiguousarray(np.stack([der, val], axis=-1).reshape(-1))
