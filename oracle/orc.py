@@ -35,6 +35,8 @@ def lib():
     sig = {
         "orc_gl_nodes": (None, [C.c_int, _dp]),
         "orc_gauss_legendre": (None, [C.c_int, _dp, _dp]),
+        "orc_lagrange": (C.c_double, [C.c_int, _dp, C.c_int, C.c_double]),
+        "orc_lagrange_prime": (C.c_double, [C.c_int, _dp, C.c_int, C.c_double]),
         "orc_mesh_create": (vp, [C.c_int, _ip, _dp, _ip, C.c_void_p, C.c_double, C.c_int]),
         "orc_mesh_destroy": (None, [vp]),
         "orc_mesh_dimension": (C.c_long, [vp]),
@@ -89,6 +91,14 @@ def gauss_legendre(m):
     return x, w
 
 
+def lagrange(p, i, x):
+    return lib().orc_lagrange(p, gl_nodes(p), i, float(x))
+
+
+def lagrange_prime(p, i, x):
+    return lib().orc_lagrange_prime(p, gl_nodes(p), i, float(x))
+
+
 def fill_random(n, seed=1887):
     v = np.zeros(n)
     lib().orc_fill_random(v, n, seed)
@@ -109,8 +119,11 @@ class Matrix:
         self.mesh = mesh
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().orc_bcrs_destroy(self.h)
+        if getattr(self, "h", None) and _lib is not None:
+            try:
+                _lib.orc_bcrs_destroy(self.h)
+            except Exception:
+                pass
             self.h = None
 
     @property
@@ -191,8 +204,11 @@ class Mesh:
         lib().orc_mesh_offsets(self.h, self.offsets)
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().orc_mesh_destroy(self.h)
+        if getattr(self, "h", None) and _lib is not None:
+            try:
+                _lib.orc_mesh_destroy(self.h)
+            except Exception:
+                pass
             self.h = None
 
     def block_size(self, e):

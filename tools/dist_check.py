@@ -1,0 +1,60 @@
+"""Multi-rank parity check (run under torchrun, one rank per GPU): every rank owns a brick, exchanges face traces
+over NCCL inside hpdg_op_apply_device, and compares its rows with the CPU oracle applied to the GLOBAL mesh."""
+import ctypes
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "dune-hpdg_b200"))
+import numpy as np
+import torch
+import torch.distributed as dist
+import hpdg_b200 as hp
+from hpdg_b200 import partition as part
+from oracle import orc
+
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+pgrid = part.pgrid_for(world)
+ok = True
+for p, n in [(3, (8, 8, 8)), (3, (6, 5, 7)), (4, (4, 6, 4)), (1, (8, 4, 4)), (2, (5, 5, 5))]:
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        buf = ctypes.create_string_buffer(128)
+        assert hp.lib().hpdg_nccl_unique_id(buf) == 0
+        idt = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
+    dist.broadcast(idt, 0)
+    N = [n[d] * pgrid[d] for d in range(3)]
+    Lg = [float(pgrid[d]) for d in range(3)]
+    m = orc.Mesh(N, L=Lg, degree=p, sigma=2.0, dirichlet=True)
+    xg = orc.fill_random(m.ndof)
+    ref = m.apply_mf(xg, threads=orc.max_threads())
+    ne = (p + 1) ** 3
+    xl = part.scatter_global_vector(xg, rank, pgrid, n, ne)
+    rl = part.scatter_global_vector(ref, rank, pgrid, n, ne)
+    ctx = hp.Context(n, L=[1.0, 1.0, 1.0], degree=p, sigma=2.0, dirichlet=True, device=lr, pgrid=pgrid, rank=rank,
+                     nranks=world, nccl_id=bytes(idt.cpu().tolist()))
+    dx, dy = ctx.upload(xl), ctx.vec_alloc()
+    hp.Operator(ctx).apply_device(dx, dy)
+    y = ctx.download(dy)
+    err = np.linalg.norm(y - rl) / np.linalg.norm(rl)
+    # distributed dot product (Krylov allreduce)
+    dd = ctx.dot_device(dx, dx)
+    derr = abs(dd - xg @ xg) / (xg @ xg)
+    # fast-diagonalisation block Jacobi on a rank-local brick needs no communication
+    jref = part.scatter_global_vector(m.blockjacobi_apply(xg, factor=0.75), rank, pgrid, n, ne)
+    jac = hp.BlockJacobi(ctx, form=hp.JACOBI_FD, damping=0.75)
+    jac.apply_device(dx, dy)
+    jerr = np.linalg.norm(ctx.download(dy) - jref) / np.linalg.norm(jref)
+    good = err < 1e-12 and derr < 1e-12 and jerr < 1e-11
+    ok &= good
+    print(f"rank {rank}/{world} p={p} brick={n}: apply {err:.2e} dot {derr:.2e} jacobi {jerr:.2e} {'OK' if good else 'FAIL'}", flush=True)
+    ctx.close()
+t = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+dist.destroy_process_group()
+if rank == 0:
+    print("DIST_CHECK", "PASS" if t.item() == 1 else "FAIL")
+sys.exit(0 if t.item() == 1 else 1)
