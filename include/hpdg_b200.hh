@@ -1,0 +1,173 @@
+// hpdg_b200.hh -- header-only C++17 host shim over the C ABI (hpdg_b200.h).
+//
+// Mirrors the reference-side interfaces of the hot path so that code written against dune-hpdg keeps its shape:
+//   * vectors: anything exposing `double* data()` and `size_t dimension()` in the DynamicBlockVector layout
+//     (dune/hpdg/common/dynamicbvector.hh:282,328-330,366-379) -- Dune::HPDG::DynamicBlockVector itself qualifies;
+//     hpdg::BlockVector below is a minimal stand-in with the same members for builds without DUNE.
+//   * hpdg::Operator::apply(x, Ax)            <- Dune::Fufem::MatrixFree::Operator::apply (matrix-free/operator.hh:41-56)
+//     with setFactor/factor                    <- LocalOperator (matrix-free/localoperators/localoperator.hh:41-49)
+//   * hpdg::BlockJacobiStep: setProblem / preprocess / iterate
+//                                              <- Dune::Solvers::LinearIterationStep as used by DynamicBlockGS
+//                                                 (iterationsteps/dynamicblockgs.hh:87-127)
+//   * hpdg::operatorFrom / smootherFrom / restrictFrom / prolongFrom return
+//     std::function<void(Vector&, const Vector&)> <- Operator<V>, Smoother<V>, TransferOperator<V>
+//                                                 (iterationsteps/mg/multigrid.hh:13-23,83-155)
+//   * hpdg::Multigrid::apply(x, b)             <- Dune::HPDG::Multigrid<Vector>::apply (mg/multigrid_impl.hh:16-61)
+// Errors: every non-zero return of the C ABI is rethrown as hpdg::Exception (the reference throws Dune::Exception via
+// DUNE_THROW, e.g. dynamicblockgs.hh:117).  No arithmetic lives here.
+#pragma once
+#include <cstddef>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "hpdg_b200.h"
+
+namespace hpdg {
+
+struct Exception : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+// Minimal DynamicBlockVector stand-in: one contiguous array + block offsets.
+class BlockVector {
+ public:
+  BlockVector() = default;
+  explicit BlockVector(std::vector<long> offsets) : off_(std::move(offsets)), v_(off_.empty() ? 0 : off_.back(), 0.0) {}
+  double* data() { return v_.data(); }
+  const double* data() const { return v_.data(); }
+  std::size_t dimension() const { return v_.size(); }
+  std::size_t size() const { return off_.empty() ? 0 : off_.size() - 1; }          // number of blocks
+  std::size_t blockRows(std::size_t i) const { return off_[i + 1] - off_[i]; }       // dynamicbvector.hh:134-143
+  double* block(std::size_t i) { return v_.data() + off_[i]; }
+  BlockVector& operator=(double s) { for (auto& e : v_) e = s; return *this; }       // dynamicbvector.hh:185-192
+  BlockVector& operator+=(const BlockVector& o) { for (std::size_t i = 0; i < v_.size(); i++) v_[i] += o.v_[i]; return *this; }
+  BlockVector& operator-=(const BlockVector& o) { for (std::size_t i = 0; i < v_.size(); i++) v_[i] -= o.v_[i]; return *this; }
+  BlockVector& operator*=(double s) { for (auto& e : v_) e *= s; return *this; }
+  double operator*(const BlockVector& o) const { double s = 0; for (std::size_t i = 0; i < v_.size(); i++) s += v_[i] * o.v_[i]; return s; }
+  const std::vector<long>& offsets() const { return off_; }
+
+ private:
+  std::vector<long> off_;
+  std::vector<double> v_;
+};
+
+class Context {
+ public:
+  // uniform degree
+  Context(int dim, const int* n, const double* L, int degree, double sigma = 2.0, bool dirichlet = false, int device = 0) {
+    check(hpdg_create(&h_, dim, n, L, &degree, 1, sigma, dirichlet ? 1 : 0, device), nullptr);
+  }
+  // per-element degree map (DynamicDGQkGLBlockBasis(gridView, DegreeMap), dynamicdgqkglbasis.hh:54-69)
+  Context(int dim, const int* n, const double* L, const std::vector<int>& degree, double sigma = 2.0, bool dirichlet = false,
+          int device = 0) {
+    check(hpdg_create(&h_, dim, n, L, degree.data(), (long)degree.size(), sigma, dirichlet ? 1 : 0, device), nullptr);
+  }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  ~Context() { hpdg_destroy(h_); }
+
+  hpdg_ctx* handle() const { return h_; }
+  void check(int rc) const { check(rc, h_); }
+  int numLevels() const { return hpdg_num_levels(h_); }
+  long dimension(int level = HPDG_FINEST) const { return hpdg_dimension(h_, level); }
+  std::vector<long> blockOffsets(int level = HPDG_FINEST) const {
+    std::vector<long> off(hpdg_num_elements(h_) + 1);
+    check(hpdg_block_offsets(h_, level, off.data()));
+    return off;
+  }
+  BlockVector makeVector(int level = HPDG_FINEST) const { return BlockVector(blockOffsets(level)); }
+  int buildPHierarchy() { check(hpdg_build_p_hierarchy(h_)); return numLevels(); }   // solversetup.hh:71-108
+
+ private:
+  static void check(int rc, const hpdg_ctx* h) {
+    if (rc) throw Exception(hpdg_last_error(h));
+  }
+  hpdg_ctx* h_ = nullptr;
+};
+
+// Operator::apply(x, Ax): Ax = factor * A x (Ax overwritten, operator.hh:42)
+class Operator {
+ public:
+  explicit Operator(std::shared_ptr<Context> c, int level = HPDG_FINEST, double factor = 1.0)
+      : c_(std::move(c)), level_(level), factor_(factor) {}
+  double factor() const { return factor_; }
+  void setFactor(double f) { factor_ = f; }
+  template <class V>
+  void apply(const V& x, V& Ax) const { c_->check(hpdg_op_apply(c_->handle(), level_, x.data(), Ax.data(), factor_)); }
+
+ private:
+  std::shared_ptr<Context> c_;
+  int level_;
+  double factor_;
+};
+
+// LinearIterationStep-shaped damped block-Jacobi step: x += damping * D^-1 (rhs - A x)
+template <class V>
+class BlockJacobiStep {
+ public:
+  explicit BlockJacobiStep(std::shared_ptr<Context> c, int level = HPDG_FINEST, int form = HPDG_JACOBI_DENSE, double damping = 1.0)
+      : c_(std::move(c)), level_(level), form_(form), damping_(damping) {}
+  void setProblem(V& x, const V& rhs) { x_ = &x; rhs_ = &rhs; }
+  void preprocess() { c_->check(hpdg_jacobi_setup(c_->handle(), level_, form_)); ready_ = true; }
+  void iterate() {
+    if (!ready_) preprocess();
+    V r = *rhs_, t = *rhs_;
+    c_->check(hpdg_op_apply(c_->handle(), level_, x_->data(), t.data(), 1.0));
+    r -= t;
+    apply(t, r);
+    *x_ += t;
+  }
+  // Smoother<V>(c, r): correction from a zero start
+  void apply(V& c, const V& r) {
+    if (!ready_) preprocess();
+    c_->check(hpdg_jacobi_apply(c_->handle(), level_, form_, r.data(), c.data(), damping_));
+  }
+  V* x_ = nullptr;         // public members like the dune-solvers step (multigrid.hh:100-103 pokes rhs_)
+  const V* rhs_ = nullptr;
+
+ private:
+  std::shared_ptr<Context> c_;
+  int level_, form_;
+  double damping_;
+  bool ready_ = false;
+};
+
+template <class V> using Fn = std::function<void(V&, const V&)>;
+
+template <class V>
+Fn<V> operatorFrom(std::shared_ptr<Context> c, int level = HPDG_FINEST) {   // operatorFromMatrix, multigrid.hh:137-155
+  return [c, level](V& y, const V& x) { c->check(hpdg_op_apply(c->handle(), level, x.data(), y.data(), 1.0)); };
+}
+template <class V>
+Fn<V> smootherFrom(std::shared_ptr<BlockJacobiStep<V>> step) {              // smootherFromIterationStep, multigrid.hh:83-93
+  return [step](V& c, const V& r) { step->apply(c, r); };
+}
+template <class V>
+Fn<V> restrictFrom(std::shared_ptr<Context> c, int fine_level) {            // restrictFromMultigridTransfer, multigrid.hh:108-116
+  return [c, fine_level](V& coarse, const V& fine) { c->check(hpdg_restrict(c->handle(), fine_level, fine.data(), coarse.data())); };
+}
+template <class V>
+Fn<V> prolongFrom(std::shared_ptr<Context> c, int fine_level) {             // prolongFromMultigridTransfer, multigrid.hh:118-126
+  return [c, fine_level](V& fine, const V& coarse) { c->check(hpdg_prolong(c->handle(), fine_level, coarse.data(), fine.data())); };
+}
+
+// Multigrid<Vector>::apply(x, b): x += correction, b := residual
+class Multigrid {
+ public:
+  explicit Multigrid(std::shared_ptr<Context> c, int form = HPDG_JACOBI_FD, double damping = 0.75, int pre = 5, int post = 5,
+                     int coarse_its = 5)
+      : c_(std::move(c)), form_(form), damping_(damping), pre_(pre), post_(post), coarse_(coarse_its) {}
+  template <class V>
+  void apply(V& x, V& b) const { c_->check(hpdg_vcycle(c_->handle(), form_, damping_, pre_, post_, coarse_, x.data(), b.data())); }
+
+ private:
+  std::shared_ptr<Context> c_;
+  int form_;
+  double damping_;
+  int pre_, post_, coarse_;
+};
+
+}  // namespace hpdg
