@@ -97,6 +97,7 @@ void free_level(Level& L) {
   cudaFree(L.d_deg); cudaFree(L.d_pdeg); cudaFree(L.d_off); cudaFree(L.d_elist);
   cudaFree(L.jd.d_inv); cudaFree(L.jf.d_fac); cudaFree(L.jf.d_idx);
   cudaFree(L.mg_x); cudaFree(L.mg_r); cudaFree(L.mg_t1); cudaFree(L.mg_t2);
+  cudaFree(L.d_tiles_int); cudaFree(L.d_tiles_bnd);
 }
 
 int create_common(Ctx* ctx, int dim, const int* n, const double* Lx, const std::vector<int>& deg, double sigma,
@@ -110,7 +111,13 @@ int create_common(Ctx* ctx, int dim, const int* n, const double* Lx, const std::
   ctx->device = device; ctx->dim = dim; ctx->sigma = sigma; ctx->dirichlet = dirichlet;
   HPDG_CUDA(cudaSetDevice(device));
   HPDG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  HPDG_CUDA(cudaStreamCreateWithFlags(&ctx->stream_comm, cudaStreamNonBlocking));
+  {
+    // the halo stream gets the highest priority so that the NCCL kernel is scheduled as soon as any tile CTA retires
+    // instead of queueing behind the interior-tile kernel (which would serialise the exchange after it)
+    int lo = 0, hi = 0;
+    HPDG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    HPDG_CUDA(cudaStreamCreateWithPriority(&ctx->stream_comm, cudaStreamNonBlocking, hi));
+  }
   HPDG_CUDA(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
   HPDG_CUDA(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
   const HostTables& H = host_tables();
@@ -143,11 +150,14 @@ int ensure_stage(Ctx* ctx, size_t ndof) {
   return 0;
 }
 
-int halo_exchange(Ctx* ctx, Level& L, const double* d_x) {
-  // copyFromMaster analogue (parallel/communicationhpdg.hh:411-418) on face traces
-  if (launch_pack_traces(ctx, L, d_x)) return 1;
-  HPDG_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
+// Distributed apply.  Compute stream: interior tiles (need no ghost data).  Halo stream (highest priority, so its
+// kernels are scheduled as soon as any tile CTA retires): pack the brick's face traces -> grouped ncclSend/ncclRecv with the
+// <= 6 face neighbours (the copyFromMaster analogue, parallel/communicationhpdg.hh:411-418) -> rank-boundary tiles.
+// The two streams write disjoint tiles of y; the compute stream joins the halo stream at the end.
+int op_apply_distributed(Ctx* ctx, Level& L, const double* d_x, double* d_y, double factor) {
+  HPDG_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));                    // x is ready
   HPDG_CUDA(cudaStreamWaitEvent(ctx->stream_comm, ctx->ev_a, 0));
+  if (launch_pack_traces(ctx, L, d_x, ctx->stream_comm)) return 1;
   ncclComm_t comm = (ncclComm_t)ctx->nccl;
   HPDG_NCCL(g_nccl.GroupStart());
   for (int f = 0; f < 6; f++) {
@@ -156,7 +166,10 @@ int halo_exchange(Ctx* ctx, Level& L, const double* d_x) {
     HPDG_NCCL(g_nccl.Recv(ctx->ghost.d_recv[f], ctx->ghost.count[f], ncclDouble, ctx->ghost.peer[f], comm, ctx->stream_comm));
   }
   HPDG_NCCL(g_nccl.GroupEnd());
+  if (launch_apply_uniform(ctx, L, d_x, d_y, factor, 2, ctx->stream_comm)) return 1;   // rank-boundary tiles
   HPDG_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream_comm));
+  if (launch_apply_uniform(ctx, L, d_x, d_y, factor, 1, ctx->stream)) return 1;        // interior tiles, overlaps the exchange
+  HPDG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
   return 0;
 }
 
@@ -164,10 +177,7 @@ int op_apply_async(Ctx* ctx, Level& L, const double* d_x, double* d_y, double fa
   const bool finest = (&L == &ctx->levels.back());
   if (ctx->nranks > 1) {
     if (!finest || !uniform_supported(ctx, L)) { ctx->err = "distributed apply needs the uniform-degree 3-D kernel on the finest level"; return 1; }
-    if (halo_exchange(ctx, L, d_x)) return 1;
-    if (launch_apply_uniform(ctx, L, d_x, d_y, factor, 1)) return 1;   // tiles that need no ghost data: overlaps the exchange
-    HPDG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
-    return launch_apply_uniform(ctx, L, d_x, d_y, factor, 2);
+    return op_apply_distributed(ctx, L, d_x, d_y, factor);
   }
   if (uniform_supported(ctx, L)) return launch_apply_uniform(ctx, L, d_x, d_y, factor, 0);
   return launch_apply_generic(ctx, L, d_x, d_y, factor);

@@ -45,6 +45,7 @@ struct UniParams {
   double* y;
   int dbg;   // timing experiments only: 1 = skip outside-trace loads (wrong results)
   int part;  // 0 all tiles, 1 only tiles not touching a ghost face, 2 only tiles touching one
+  const int* tile_list;  // part != 0: compact list of the tile ids of that part (grid = list length)
 };
 
 template <int N> struct Pitch {
@@ -240,7 +241,7 @@ __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restr
 
   // ---------------- P2: x-pencils ----------------
   if (!EARLY) { load_xtr(); load_ytr(); }
-  if (xact) {
+  if (xact && !(P.dbg & 2)) {
     double v[TX][N];
     const int xbase = TX * (xey + TY * xez) * EP + N * xj + PP * xk;
 #pragma unroll
@@ -257,7 +258,7 @@ __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restr
   __syncthreads();
 
   // ---------------- P3: y-pencils, then M_y ----------------
-  if (yact) {
+  if (yact && !(P.dbg & 4)) {
     double v[TY][N];
     const int ybase = (yex + TX * TY * yez) * EP + yi + PP * yk;
 #pragma unroll
@@ -279,7 +280,7 @@ __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restr
   hook();
 
   // ---------------- P4: M_x ----------------
-  if (xact) {
+  if (xact && !(P.dbg & 8)) {
 #pragma unroll
     for (int e = 0; e < TX; e++)
       if (FULL || e < lenx) {
@@ -320,17 +321,11 @@ k_apply_uniform(const __grid_constant__ UniParams<N> P) {
   extern __shared__ double sm[];
   double* su = sm;
   double* sw = sm + TX * TY * TZ * EP;
-  int tb = blockIdx.x;
+  int tb = P.tile_list ? P.tile_list[blockIdx.x] : blockIdx.x;
   const int tx = tb % P.ntile[0]; tb /= P.ntile[0];
   const int ty = tb % P.ntile[1]; const int tz = tb / P.ntile[1];
   const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;
   const int lenx = min(TX, P.n[0] - x0), leny = min(TY, P.n[1] - y0), lenz = min(TZ, P.n[2] - z0);
-  if (P.part != 0) {
-    bool touch = (x0 == 0 && P.bmode[0] == 3) || (x0 + lenx == P.n[0] && P.bmode[1] == 3) ||
-                 (y0 == 0 && P.bmode[2] == 3) || (y0 + leny == P.n[1] && P.bmode[3] == 3) ||
-                 (z0 == 0 && P.bmode[4] == 3) || (z0 + lenz == P.n[2] && P.bmode[5] == 3);
-    if ((P.part == 1) == touch) return;
-  }
   if (lenx == TX && leny == TY && lenz == TZ) tile_body<N, TX, TY, TZ, true, EARLY>(P, su, sw, x0, y0, z0, TX, TY, TZ);
   else tile_body<N, TX, TY, TZ, false, EARLY>(P, su, sw, x0, y0, z0, lenx, leny, lenz);
 }
@@ -471,10 +466,14 @@ k_apply_uniform_pipe(const __grid_constant__ UniParams<N> P) {
 // ---- ghost trace packing (sender side of the halo exchange) -------------------------
 // For brick face f = (d,s): for every boundary element and face node, (der,val) of the element's
 // DoF line normal to the face at side s.  Layout matches UniParams::ghost of the receiving rank.
+struct PackParams { double* out[6]; const double* g[6]; };
 template <int N>
-__global__ void k_pack_traces(const double* __restrict__ x, double* __restrict__ out, int n0, int n1, int n2, int d,
-                              int s, const double* __restrict__ g /* g[s][0..N) */) {
+__global__ void k_pack_traces(const double* __restrict__ x, PackParams PK, int n0, int n1, int n2) {
   constexpr int N2 = N * N, N3 = N2 * N;
+  const int f = blockIdx.y, d = f / 2, s = f % 2;
+  double* __restrict__ out = PK.out[f];
+  if (!out) return;
+  const double* __restrict__ g = PK.g[f];
   const int na = d == 0 ? n1 : n0, nb = d == 2 ? n1 : n2;  // face element extents (low dim fastest)
   const long total = (long)na * nb * N2;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
@@ -499,7 +498,7 @@ __global__ void k_pack_traces(const double* __restrict__ x, double* __restrict__
 }
 
 template <int N, int TX, int TY, int TZ, int MINB, bool EARLY = true>
-static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part) {
+static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream) {
   static UniParams<N> P;  // rebuilt per call (cheap); static to keep it off the stack
   const DegTable& T = host_tables().deg[N - 1];
   const double c = ctx->sigma * (double)L.pen_uni * L.pen_uni;
@@ -533,7 +532,34 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
     } else P.bmode[f] = ctx->dirichlet ? 1 : 2;
   }
   P.x = x; P.y = y; P.part = part; P.dbg = ctx->variant / 100;
-  if (ctx->variant % 100 >= 10) {
+  P.tile_list = nullptr;
+  long nlist = 0;
+  if (part != 0) {
+    // compact tile lists of the two parts, built once per (level, tile shape)
+    const long key = ((long)TX << 16) | ((long)TY << 8) | TZ;
+    if (L.tile_key != key) {
+      std::vector<int> li, lb;
+      for (int tz = 0; tz < P.ntile[2]; tz++) for (int ty = 0; ty < P.ntile[1]; ty++) for (int tx = 0; tx < P.ntile[0]; tx++) {
+        const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;
+        const int lx = std::min(TX, L.n[0] - x0), ly = std::min(TY, L.n[1] - y0), lz = std::min(TZ, L.n[2] - z0);
+        const bool touch = (x0 == 0 && P.bmode[0] == 3) || (x0 + lx == L.n[0] && P.bmode[1] == 3) ||
+                           (y0 == 0 && P.bmode[2] == 3) || (y0 + ly == L.n[1] && P.bmode[3] == 3) ||
+                           (z0 == 0 && P.bmode[4] == 3) || (z0 + lz == L.n[2] && P.bmode[5] == 3);
+        (touch ? lb : li).push_back(tx + P.ntile[0] * (ty + P.ntile[1] * tz));
+      }
+      cudaFree(L.d_tiles_int); cudaFree(L.d_tiles_bnd);
+      L.d_tiles_int = L.d_tiles_bnd = nullptr;
+      HPDG_CUDA(cudaMalloc(&L.d_tiles_int, sizeof(int) * std::max<size_t>(li.size(), 1)));
+      HPDG_CUDA(cudaMalloc(&L.d_tiles_bnd, sizeof(int) * std::max<size_t>(lb.size(), 1)));
+      HPDG_CUDA(cudaMemcpy(L.d_tiles_int, li.data(), sizeof(int) * li.size(), cudaMemcpyHostToDevice));
+      HPDG_CUDA(cudaMemcpy(L.d_tiles_bnd, lb.data(), sizeof(int) * lb.size(), cudaMemcpyHostToDevice));
+      L.n_tiles_int = (long)li.size(); L.n_tiles_bnd = (long)lb.size(); L.tile_key = key;
+    }
+    P.tile_list = part == 1 ? L.d_tiles_int : L.d_tiles_bnd;
+    nlist = part == 1 ? L.n_tiles_int : L.n_tiles_bnd;
+    if (nlist == 0) return 0;
+  }
+  if (ctx->variant % 100 >= 10 && part == 0) {
     constexpr int threads = uni_threads<N, TX, TY, TZ>();
     constexpr size_t smem = sizeof(double) * 3 * TX * TY * TZ * Pitch<N>::EP;
     static bool attr_set_pipe = false;
@@ -559,8 +585,8 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
     HPDG_CUDA(cudaFuncSetAttribute(k_apply_uniform<N, TX, TY, TZ, MINB, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  const long ntiles = (long)P.ntile[0] * P.ntile[1] * P.ntile[2];
-  k_apply_uniform<N, TX, TY, TZ, MINB, EARLY><<<(unsigned)ntiles, threads, smem, ctx->stream>>>(P);
+  const long ntiles = part != 0 ? nlist : (long)P.ntile[0] * P.ntile[1] * P.ntile[2];
+  k_apply_uniform<N, TX, TY, TZ, MINB, EARLY><<<(unsigned)ntiles, threads, smem, stream>>>(P);
   ctx->launches++;
   HPDG_CUDA(cudaGetLastError());
   return 0;
@@ -572,60 +598,63 @@ int uniform_supported(const Ctx* ctx, const Level& L) {
   return L.p_uni >= 1 && L.p_uni <= 5;
 }
 
-int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part) {
+int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream) {
+  if (!stream) stream = ctx->stream;
   switch (L.p_uni) {
-    case 1: return launch_uni<2, 4, 4, 4, 4>(ctx, L, x, y, factor, part);
-    case 2: return launch_uni<3, 4, 4, 4, 3>(ctx, L, x, y, factor, part);
+    case 1: return launch_uni<2, 4, 4, 4, 4>(ctx, L, x, y, factor, part, stream);
+    case 2: return launch_uni<3, 4, 4, 4, 3>(ctx, L, x, y, factor, part, stream);
     case 3:
       switch (ctx->variant % 100) {
-        case 1: return launch_uni<4, 4, 4, 4, 2, true>(ctx, L, x, y, factor, part);
-        case 3: return launch_uni<4, 4, 4, 4, 2, false>(ctx, L, x, y, factor, part);
-        case 4: return launch_uni<4, 4, 4, 2, 4, false>(ctx, L, x, y, factor, part);
-        case 5: return launch_uni<4, 4, 4, 2, 3, false>(ctx, L, x, y, factor, part);
-        case 6: return launch_uni<4, 4, 4, 2, 4, true>(ctx, L, x, y, factor, part);
-        case 7: return launch_uni<4, 4, 2, 4, 4, false>(ctx, L, x, y, factor, part);
-        case 8: return launch_uni<4, 2, 4, 4, 4, false>(ctx, L, x, y, factor, part);
-        case 9: return launch_uni<4, 4, 4, 4, 3, true>(ctx, L, x, y, factor, part);
-        default: return launch_uni<4, 4, 4, 4, 3, false>(ctx, L, x, y, factor, part);
+        case 1: return launch_uni<4, 4, 4, 4, 2, true>(ctx, L, x, y, factor, part, stream);
+        case 3: return launch_uni<4, 4, 4, 4, 2, false>(ctx, L, x, y, factor, part, stream);
+        case 4: return launch_uni<4, 4, 4, 2, 4, false>(ctx, L, x, y, factor, part, stream);
+        case 5: return launch_uni<4, 4, 4, 2, 3, false>(ctx, L, x, y, factor, part, stream);
+        case 6: return launch_uni<4, 4, 4, 2, 4, true>(ctx, L, x, y, factor, part, stream);
+        case 7: return launch_uni<4, 4, 2, 4, 4, false>(ctx, L, x, y, factor, part, stream);
+        case 8: return launch_uni<4, 2, 4, 4, 4, false>(ctx, L, x, y, factor, part, stream);
+        case 9: return launch_uni<4, 4, 4, 4, 3, true>(ctx, L, x, y, factor, part, stream);
+        default: return launch_uni<4, 4, 4, 4, 3, false>(ctx, L, x, y, factor, part, stream);
       }
     case 4:
       switch (ctx->variant % 100) {
-        case 1: return launch_uni<5, 4, 4, 2, 1, false>(ctx, L, x, y, factor, part);
-        case 2: return launch_uni<5, 4, 4, 2, 2, false>(ctx, L, x, y, factor, part);
-        case 3: return launch_uni<5, 4, 2, 2, 2, false>(ctx, L, x, y, factor, part);
-        case 4: return launch_uni<5, 2, 2, 2, 4, false>(ctx, L, x, y, factor, part);
-        case 5: return launch_uni<5, 3, 3, 3, 2, false>(ctx, L, x, y, factor, part);
-        default: return launch_uni<5, 2, 2, 2, 3, false>(ctx, L, x, y, factor, part);
+        case 1: return launch_uni<5, 4, 4, 2, 1, false>(ctx, L, x, y, factor, part, stream);
+        case 2: return launch_uni<5, 4, 4, 2, 2, false>(ctx, L, x, y, factor, part, stream);
+        case 3: return launch_uni<5, 4, 2, 2, 2, false>(ctx, L, x, y, factor, part, stream);
+        case 4: return launch_uni<5, 2, 2, 2, 4, false>(ctx, L, x, y, factor, part, stream);
+        case 5: return launch_uni<5, 3, 3, 3, 2, false>(ctx, L, x, y, factor, part, stream);
+        default: return launch_uni<5, 2, 2, 2, 3, false>(ctx, L, x, y, factor, part, stream);
       }
-    case 5: return launch_uni<6, 2, 2, 2, 2>(ctx, L, x, y, factor, part);
+    case 5: return launch_uni<6, 2, 2, 2, 2>(ctx, L, x, y, factor, part, stream);
     default: return -1;
   }
 }
 
 template <int N>
-static int pack_n(Ctx* ctx, Level& L, const double* x) {
+static int pack_n(Ctx* ctx, Level& L, const double* x, cudaStream_t stream) {
   const DegTable* dt = ctx->d_tab + (N - 1);
+  PackParams PK;
+  long maxtotal = 0;
   for (int f = 0; f < 6; f++) {
-    if (!ctx->ghost.active[f]) continue;
-    const int d = f / 2, s = f % 2;
-    const long total = (long)ctx->ghost.count[f] / 2;
-    const int threads = 256;
-    const int blocks = (int)((total + threads - 1) / threads);
-    k_pack_traces<N><<<blocks, threads, 0, ctx->stream>>>(x, ctx->ghost.d_send[f], L.n[0], L.n[1], L.n[2], d, s,
-                                                         &dt->g[s][0]);
-    ctx->launches++;
-    HPDG_CUDA(cudaGetLastError());
+    PK.out[f] = ctx->ghost.active[f] ? ctx->ghost.d_send[f] : nullptr;
+    PK.g[f] = &dt->g[f % 2][0];
+    if (ctx->ghost.active[f]) maxtotal = std::max<long>(maxtotal, (long)ctx->ghost.count[f] / 2);
   }
+  if (maxtotal == 0) return 0;
+  const int threads = 256;
+  dim3 grid((unsigned)std::min<long>((maxtotal + threads - 1) / threads, 2048), 6);
+  k_pack_traces<N><<<grid, threads, 0, stream>>>(x, PK, L.n[0], L.n[1], L.n[2]);
+  ctx->launches++;
+  HPDG_CUDA(cudaGetLastError());
   return 0;
 }
 
-int launch_pack_traces(Ctx* ctx, Level& L, const double* x) {
+int launch_pack_traces(Ctx* ctx, Level& L, const double* x, cudaStream_t stream) {
   switch (L.p_uni) {
-    case 1: return pack_n<2>(ctx, L, x);
-    case 2: return pack_n<3>(ctx, L, x);
-    case 3: return pack_n<4>(ctx, L, x);
-    case 4: return pack_n<5>(ctx, L, x);
-    case 5: return pack_n<6>(ctx, L, x);
+    case 1: return pack_n<2>(ctx, L, x, stream);
+    case 2: return pack_n<3>(ctx, L, x, stream);
+    case 3: return pack_n<4>(ctx, L, x, stream);
+    case 4: return pack_n<5>(ctx, L, x, stream);
+    case 5: return pack_n<6>(ctx, L, x, stream);
     default: ctx->err = "pack_traces: unsupported degree"; return 1;
   }
 }

@@ -59,6 +59,9 @@ struct Level {
   int maxp = 0;
   JacobiDense jd;
   JacobiFD jf;
+  // compact tile lists (interior / rank-boundary tiles) of the distributed apply, per tile shape
+  int *d_tiles_int = nullptr, *d_tiles_bnd = nullptr;
+  long n_tiles_int = 0, n_tiles_bnd = 0, tile_key = -1;
   // scratch vectors for the V-cycle (device, ndof each)
   double *mg_x = nullptr, *mg_r = nullptr, *mg_t1 = nullptr, *mg_t2 = nullptr;
 };
@@ -104,9 +107,9 @@ struct Ctx {
 // ---- kernel launchers (defined in the .cu files) -----------------------------------------------
 int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double factor);
 // returns -1 if (dim, degree) has no specialised kernel
-int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part);
+int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream = nullptr);
 int uniform_supported(const Ctx* ctx, const Level& L);
-int launch_pack_traces(Ctx* ctx, Level& L, const double* x);
+int launch_pack_traces(Ctx* ctx, Level& L, const double* x, cudaStream_t stream);
 
 int jacobi_setup_dense(Ctx* ctx, Level& L);
 int jacobi_apply_dense(Ctx* ctx, Level& L, const double* r, double* c, double damping);
