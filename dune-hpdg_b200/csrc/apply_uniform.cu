@@ -622,7 +622,9 @@ int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double 
         case 3: return launch_uni<5, 4, 2, 2, 2, false>(ctx, L, x, y, factor, part, stream);
         case 4: return launch_uni<5, 2, 2, 2, 4, false>(ctx, L, x, y, factor, part, stream);
         case 5: return launch_uni<5, 3, 3, 3, 2, false>(ctx, L, x, y, factor, part, stream);
-        default: return launch_uni<5, 2, 2, 2, 3, false>(ctx, L, x, y, factor, part, stream);
+        case 7: return launch_uni<5, 4, 4, 1, 2, false>(ctx, L, x, y, factor, part, stream);
+        case 8: return launch_uni<5, 2, 2, 2, 3, false>(ctx, L, x, y, factor, part, stream);
+        default: return launch_uni<5, 3, 3, 3, 3, false>(ctx, L, x, y, factor, part, stream);
       }
     case 5: return launch_uni<6, 2, 2, 2, 2>(ctx, L, x, y, factor, part, stream);
     default: return -1;

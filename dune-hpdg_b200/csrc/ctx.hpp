@@ -115,6 +115,7 @@ int jacobi_setup_dense(Ctx* ctx, Level& L);
 int jacobi_apply_dense(Ctx* ctx, Level& L, const double* r, double* c, double damping);
 int jacobi_setup_fd(Ctx* ctx, Level& L);
 int jacobi_apply_fd(Ctx* ctx, Level& L, const double* r, double* c, double damping);
+int jacobi_apply_fd_uniform(Ctx* ctx, Level& L, const double* r, double* c, double damping);  // -1: no specialised kernel
 int diag_block_device(Ctx* ctx, Level& L, long e, double* d_out);
 
 int launch_restrict(Ctx* ctx, Level& fine, Level& coarse, const double* xf, double* xc);

@@ -303,8 +303,18 @@ __global__ void k_jacobi_fd(FDParams P) {
   }
 }
 
+static int jacobi_build_fd_generic(Ctx* ctx, Level& L);
+
 int jacobi_setup_fd(Ctx* ctx, Level& L) {
   if (L.jf.ready) return 0;
+  // uniform-degree 3-D levels use the tiled kernel (jacobi_uniform.cu) whose 1-D factors live in its parameter block
+  if (!uniform_supported(ctx, L)) { if (jacobi_build_fd_generic(ctx, L)) return 1; }
+  L.jf.ready = true;
+  return 0;
+}
+
+static int jacobi_build_fd_generic(Ctx* ctx, Level& L) {
+  if (L.jf.d_fac) return 0;
   const HostTables& H = host_tables();
   typedef std::tuple<int, int, long long, long long, int, int> Key;  // dir-kappa id, p, c0, c1 (bits), w0, w1 (x2)
   std::map<Key, int> seen;
@@ -362,12 +372,16 @@ int jacobi_setup_fd(Ctx* ctx, Level& L) {
   HPDG_CUDA(cudaMemcpy(L.jf.d_fac, fac.data(), fac.size() * sizeof(double), cudaMemcpyHostToDevice));
   HPDG_CUDA(cudaMalloc(&L.jf.d_idx, idx.size() * sizeof(int)));
   HPDG_CUDA(cudaMemcpy(L.jf.d_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
-  L.jf.ready = true;
   return 0;
 }
 
 int jacobi_apply_fd(Ctx* ctx, Level& L, const double* r, double* c, double damping) {
   if (!L.jf.ready) { ctx->err = "hpdg_jacobi_setup(fd) has not been called for this level"; return 1; }
+  {
+    const int rc = jacobi_apply_fd_uniform(ctx, L, r, c, damping);
+    if (rc >= 0) return rc;
+  }
+  if (jacobi_build_fd_generic(ctx, L)) return 1;
   FDParams P;
   P.dim = L.dim; P.deg = L.d_deg; P.off = L.d_off; P.elist = L.d_elist; P.fac = L.jf.d_fac; P.idx = L.jf.d_idx;
   P.r = r; P.c = c; P.damping = damping;
