@@ -341,6 +341,7 @@ void hpdg_destroy(hpdg_ctx* ctx) {
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->stream_comm) cudaStreamDestroy(ctx->stream_comm);
+  if (ctx->stream_h2d) { cudaStreamDestroy(ctx->stream_h2d); cudaStreamDestroy(ctx->stream_d2h); for (int k = 0; k < 3; k++) for (int c = 0; c < 32; c++) cudaEventDestroy(ctx->ev_chunk[k][c]); }
   delete ctx;
 }
 
@@ -429,9 +430,52 @@ int hpdg_op_apply_device(hpdg_ctx* ctx, int level, const double* d_x, double* d_
   HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
+// Host-pointer apply as a 3-stage pipeline over z-slabs: H2D of slab c+1, tile kernel on slab c and D2H of slab c-1 run on
+// three streams, so the PCIe copies in both directions overlap each other and the compute (the kernel on slab c needs slabs
+// c-1..c+1 resident because of the z-neighbour traces).
+static int op_apply_host_chunked(hpdg_ctx* ctx, Level& L, const double* h_x, double* h_y, double factor) {
+  const int th = uniform_tile_height(L);
+  const int layers = L.n[2];
+  int nchunk = std::min(16, layers / th);
+  const int per = ((layers + nchunk - 1) / nchunk + th - 1) / th * th;   // layers per chunk, multiple of the tile height
+  nchunk = (layers + per - 1) / per;
+  if (!ctx->stream_h2d) {
+    HPDG_CUDA(cudaStreamCreateWithFlags(&ctx->stream_h2d, cudaStreamNonBlocking));
+    HPDG_CUDA(cudaStreamCreateWithFlags(&ctx->stream_d2h, cudaStreamNonBlocking));
+    for (int k = 0; k < 3; k++) for (int c = 0; c < 32; c++) HPDG_CUDA(cudaEventCreateWithFlags(&ctx->ev_chunk[k][c], cudaEventDisableTiming));
+  }
+  const size_t layer_dofs = (size_t)L.ndof / layers;
+  HPDG_CUDA(cudaEventRecord(ctx->ev_chunk[2][0], ctx->stream));            // earlier work on the context stream is done
+  HPDG_CUDA(cudaStreamWaitEvent(ctx->stream_h2d, ctx->ev_chunk[2][0], 0));
+  HPDG_CUDA(cudaStreamWaitEvent(ctx->stream_d2h, ctx->ev_chunk[2][0], 0));
+  for (int c = 0; c < nchunk; c++) {
+    const size_t z0 = (size_t)c * per, nz = std::min<size_t>(per, layers - z0);
+    HPDG_CUDA(cudaMemcpyAsync(ctx->d_in + z0 * layer_dofs, h_x + z0 * layer_dofs, nz * layer_dofs * sizeof(double),
+                              cudaMemcpyHostToDevice, ctx->stream_h2d));
+    HPDG_CUDA(cudaEventRecord(ctx->ev_chunk[0][c], ctx->stream_h2d));
+  }
+  for (int c = 0; c < nchunk; c++) {
+    const int z0 = c * per, nz = std::min(per, layers - z0);
+    HPDG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[0][std::min(c + 1, nchunk - 1)], 0));
+    ctx->slab_z0 = z0; ctx->slab_nz = nz;
+    const int rc = launch_apply_uniform(ctx, L, ctx->d_in, ctx->d_out, factor, 0);
+    ctx->slab_z0 = ctx->slab_nz = 0;
+    if (rc) return 1;
+    HPDG_CUDA(cudaEventRecord(ctx->ev_chunk[1][c], ctx->stream));
+    HPDG_CUDA(cudaStreamWaitEvent(ctx->stream_d2h, ctx->ev_chunk[1][c], 0));
+    HPDG_CUDA(cudaMemcpyAsync(h_y + (size_t)z0 * layer_dofs, ctx->d_out + (size_t)z0 * layer_dofs, (size_t)nz * layer_dofs * sizeof(double),
+                              cudaMemcpyDeviceToHost, ctx->stream_d2h));
+  }
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream_d2h));
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 int hpdg_op_apply(hpdg_ctx* ctx, int level, const double* h_x, double* h_y, double factor) {
   Level* L = get_level(ctx, level); if (!L) return 1;
   if (ensure_stage(ctx, L->ndof)) return 1;
+  if (ctx->nranks == 1 && uniform_supported(ctx, *L) && L->n[2] >= 4 * uniform_tile_height(*L) && L->ndof >= (1 << 20))
+    return op_apply_host_chunked(ctx, *L, h_x, h_y, factor);
   HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_x, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
   if (op_apply_async(ctx, *L, ctx->d_in, ctx->d_out, factor)) return 1;
   HPDG_CUDA(cudaMemcpyAsync(h_y, ctx->d_out, sizeof(double) * L->ndof, cudaMemcpyDeviceToHost, ctx->stream));

@@ -46,6 +46,7 @@ struct UniParams {
   int dbg;   // timing experiments only: 1 = skip outside-trace loads (wrong results)
   int part;  // 0 all tiles, 1 only tiles not touching a ghost face, 2 only tiles touching one
   const int* tile_list;  // part != 0: compact list of the tile ids of that part (grid = list length)
+  int tile_offset;       // first tile of this launch (z-slab launches of the chunked host-pointer apply)
 };
 
 template <int N> struct Pitch {
@@ -321,7 +322,7 @@ k_apply_uniform(const __grid_constant__ UniParams<N> P) {
   extern __shared__ double sm[];
   double* su = sm;
   double* sw = sm + TX * TY * TZ * EP;
-  int tb = P.tile_list ? P.tile_list[blockIdx.x] : blockIdx.x;
+  int tb = P.tile_list ? P.tile_list[blockIdx.x] : blockIdx.x + P.tile_offset;
   const int tx = tb % P.ntile[0]; tb /= P.ntile[0];
   const int ty = tb % P.ntile[1]; const int tz = tb / P.ntile[1];
   const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;
@@ -532,7 +533,7 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
     } else P.bmode[f] = ctx->dirichlet ? 1 : 2;
   }
   P.x = x; P.y = y; P.part = part; P.dbg = ctx->variant / 100;
-  P.tile_list = nullptr;
+  P.tile_list = nullptr; P.tile_offset = 0;
   long nlist = 0;
   if (part != 0) {
     // compact tile lists of the two parts, built once per (level, tile shape)
@@ -559,7 +560,7 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
     nlist = part == 1 ? L.n_tiles_int : L.n_tiles_bnd;
     if (nlist == 0) return 0;
   }
-  if (ctx->variant % 100 >= 10 && part == 0) {
+  if (ctx->variant % 100 >= 10 && part == 0 && ctx->slab_nz == 0) {
     constexpr int threads = uni_threads<N, TX, TY, TZ>();
     constexpr size_t smem = sizeof(double) * 3 * TX * TY * TZ * Pitch<N>::EP;
     static bool attr_set_pipe = false;
@@ -585,11 +586,20 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
     HPDG_CUDA(cudaFuncSetAttribute(k_apply_uniform<N, TX, TY, TZ, MINB, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  const long ntiles = part != 0 ? nlist : (long)P.ntile[0] * P.ntile[1] * P.ntile[2];
+  long ntiles = part != 0 ? nlist : (long)P.ntile[0] * P.ntile[1] * P.ntile[2];
+  if (part == 0 && ctx->slab_nz > 0) {  // element layers [slab_z0, slab_z0 + slab_nz): must be multiples of TZ
+    if (ctx->slab_z0 % TZ != 0) { ctx->err = "slab not aligned to the tile height"; return 1; }
+    P.tile_offset = (ctx->slab_z0 / TZ) * P.ntile[0] * P.ntile[1];
+    ntiles = (long)((ctx->slab_nz + TZ - 1) / TZ) * P.ntile[0] * P.ntile[1];
+  }
   k_apply_uniform<N, TX, TY, TZ, MINB, EARLY><<<(unsigned)ntiles, threads, smem, stream>>>(P);
   ctx->launches++;
   HPDG_CUDA(cudaGetLastError());
   return 0;
+}
+
+int uniform_tile_height(const Level& L) {
+  switch (L.p_uni) { case 4: return 3; case 5: return 2; default: return 4; }
 }
 
 int uniform_supported(const Ctx* ctx, const Level& L) {

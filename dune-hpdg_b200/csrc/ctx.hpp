@@ -92,6 +92,9 @@ struct Ctx {
   size_t pin_cap = 0;
   int force_generic = 0;
   int variant = 0;  // kernel variant selector for tuning experiments
+  int slab_z0 = 0, slab_nz = 0;  // restrict the next uniform launch to element layers [z0, z0+nz) (chunked host apply)
+  cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;
+  cudaEvent_t ev_chunk[3][32] = {};
   long launches = 0;  // kernels launched by this context (bench.py's gpu_launches)
 };
 
@@ -109,6 +112,7 @@ int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double 
 // returns -1 if (dim, degree) has no specialised kernel
 int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream = nullptr);
 int uniform_supported(const Ctx* ctx, const Level& L);
+int uniform_tile_height(const Level& L);
 int launch_pack_traces(Ctx* ctx, Level& L, const double* x, cudaStream_t stream);
 
 int jacobi_setup_dense(Ctx* ctx, Level& L);

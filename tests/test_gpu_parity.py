@@ -101,6 +101,20 @@ def test_cfg2_full_size(orc, hp):
     assert rel(op.apply(2.0 * x - 3.0 * z), 2.0 * y - 3.0 * Az) < TOL
 
 
+@pytest.mark.parametrize("n,p", [((32, 32, 18), 3), ((24, 20, 26), 4), ((40, 40, 37), 2)])
+def test_host_pointer_apply_pipelined_slabs(orc, hp, n, p):
+    # hpdg_op_apply with host pointers streams z-slabs (H2D / kernel / D2H overlapped); ragged slab heights
+    m = orc.Mesh(n, degree=p)
+    assert m.ndof >= 1 << 20
+    x = orc.fill_random(m.ndof)
+    ctx = hp.Context(n, degree=p)
+    hx, px = ctx.host_alloc(m.ndof)
+    hy, py = ctx.host_alloc(m.ndof)
+    hx[:] = x
+    hp.Operator(ctx, factor=-2.0).apply(px, py)
+    assert rel(hy, -2.0 * m.apply_mf(x, threads=orc.max_threads())) < TOL
+
+
 def test_device_resident_api(orc, hp):
     n = (6, 6, 6)
     m = orc.Mesh(n, degree=3)
