@@ -98,6 +98,8 @@ void free_level(Level& L) {
   cudaFree(L.jd.d_inv); cudaFree(L.jf.d_fac); cudaFree(L.jf.d_idx);
   cudaFree(L.mg_x); cudaFree(L.mg_r); cudaFree(L.mg_t1); cudaFree(L.mg_t2);
   cudaFree(L.d_tiles_int); cudaFree(L.d_tiles_bnd);
+  cudaFree(L.bcrs.d_rowptr); cudaFree(L.bcrs.d_col); cudaFree(L.bcrs.d_brow); cudaFree(L.bcrs.d_boff); cudaFree(L.bcrs.d_val);
+  cudaFree(L.bcrs.d_wave); cudaFree(L.bcrs.d_res);
 }
 
 int create_common(Ctx* ctx, int dim, const int* n, const double* Lx, const std::vector<int>& deg, double sigma,
@@ -336,7 +338,7 @@ void hpdg_destroy(hpdg_ctx* ctx) {
   if (ctx->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl);
   for (auto& L : ctx->levels) free_level(L);
   for (int f = 0; f < 6; f++) { cudaFree(ctx->ghost.d_send[f]); cudaFree(ctx->ghost.d_recv[f]); }
-  cudaFree(ctx->d_tab); cudaFree(ctx->d_P); cudaFree(ctx->d_T); cudaFree(ctx->d_in); cudaFree(ctx->d_out);
+  cudaFree(ctx->d_tab); cudaFree(ctx->d_P); cudaFree(ctx->d_T); cudaFree(ctx->d_Mab); cudaFree(ctx->d_in); cudaFree(ctx->d_out);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -519,6 +521,69 @@ int hpdg_diag_block(hpdg_ctx* ctx, int level, long element, double* h_out) {
   if (!rc) { cudaError_t e = cudaMemcpy(h_out, d, sizeof(double) * ne * ne, cudaMemcpyDeviceToHost); if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = 1; } }
   cudaFree(d);
   return rc;
+}
+
+int hpdg_bcrs_sizes(hpdg_ctx* ctx, int level, long* nblocks, long* nentries) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  long nb = 0, ne = 0;
+  const long stride[3] = {1, L->n[0], (long)L->n[0] * L->n[1]};
+  for (long e = 0; e < L->nelem; e++) {
+    long r = e; int ijk[3];
+    ijk[0] = (int)(r % L->n[0]); r /= L->n[0]; ijk[1] = (int)(r % L->n[1]); r /= L->n[1]; ijk[2] = (int)r;
+    const long re = L->off[e + 1] - L->off[e];
+    nb++; ne += re * re;
+    for (int d = 0; d < L->dim; d++) for (int s = 0; s < 2; s++) {
+      const int cc = ijk[d] + (s ? 1 : -1);
+      if (cc < 0 || cc >= L->n[d]) continue;
+      const long o = e + (s ? stride[d] : -stride[d]);
+      nb++; ne += re * (L->off[o + 1] - L->off[o]);
+    }
+  }
+  if (nblocks) *nblocks = nb;
+  if (nentries) *nentries = ne;
+  return 0;
+}
+int hpdg_assemble_bcrs(hpdg_ctx* ctx, int level, long* h_rowptr, int* h_col, long* h_boff, double* h_entries) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  if (ctx->nranks > 1) { ctx->err = "assembled export is single-rank"; return 1; }
+  if (bcrs_build(ctx, *L)) return 1;
+  Bcrs& A = L->bcrs;
+  if (h_rowptr) memcpy(h_rowptr, A.rowptr.data(), sizeof(long) * A.rowptr.size());
+  if (h_col) memcpy(h_col, A.col.data(), sizeof(int) * A.col.size());
+  if (h_boff) memcpy(h_boff, A.boff.data(), sizeof(long) * A.boff.size());
+  if (h_entries) HPDG_CUDA(cudaMemcpy(h_entries, A.d_val, sizeof(double) * (size_t)A.boff.back(), cudaMemcpyDeviceToHost));
+  return 0;
+}
+int hpdg_bcrs_mv_device(hpdg_ctx* ctx, int level, const double* d_x, double* d_y) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  if (bcrs_mv(ctx, *L, d_x, d_y)) return 1;
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int hpdg_bcrs_mv(hpdg_ctx* ctx, int level, const double* h_x, double* h_y) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  if (ensure_stage(ctx, L->ndof)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_x, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
+  if (bcrs_mv(ctx, *L, ctx->d_in, ctx->d_out)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(h_y, ctx->d_out, sizeof(double) * L->ndof, cudaMemcpyDeviceToHost, ctx->stream));
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int hpdg_blockgs_iterate_device(hpdg_ctx* ctx, int level, const double* d_b, double* d_x) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  if (blockgs_iterate(ctx, *L, d_b, d_x)) return 1;
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int hpdg_blockgs_iterate(hpdg_ctx* ctx, int level, const double* h_b, double* h_x) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  if (ensure_stage(ctx, L->ndof)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_b, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
+  HPDG_CUDA(cudaMemcpyAsync(ctx->d_out, h_x, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
+  if (blockgs_iterate(ctx, *L, ctx->d_in, ctx->d_out)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(h_x, ctx->d_out, sizeof(double) * L->ndof, cudaMemcpyDeviceToHost, ctx->stream));
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
 }
 
 static int xfer_host(hpdg_ctx* ctx, int fine_level, const double* h_in, double* h_out, bool restrict_) {

@@ -40,6 +40,15 @@ struct JacobiFD {
   int nfac = 0;
 };
 
+// Assembled matrix in DynamicBCRSMatrix layout (common/dynamicbcrs.hh:178-199) + hyperplane lists for block-GS
+struct Bcrs {
+  bool ready = false;
+  std::vector<long> rowptr, boff, wave_begin;
+  std::vector<int> col;
+  long* d_rowptr = nullptr; int* d_col = nullptr; int* d_brow = nullptr; long* d_boff = nullptr;
+  double* d_val = nullptr; int* d_wave = nullptr; double* d_res = nullptr;
+};
+
 struct Level {
   int dim = 0;
   int n[3] = {1, 1, 1};
@@ -59,6 +68,7 @@ struct Level {
   int maxp = 0;
   JacobiDense jd;
   JacobiFD jf;
+  Bcrs bcrs;
   // compact tile lists (interior / rank-boundary tiles) of the distributed apply, per tile shape
   int *d_tiles_int = nullptr, *d_tiles_bnd = nullptr;
   long n_tiles_int = 0, n_tiles_bnd = 0, tile_key = -1;
@@ -76,6 +86,7 @@ struct Ctx {
   DegTable* d_tab = nullptr;
   double* d_P = nullptr;
   double* d_T = nullptr;
+  double* d_Mab = nullptr;
   std::vector<Level> levels;  // [0] coarsest ... back() finest (reference: multigrid_impl.hh:19-20)
   std::string err;
   // distributed brick
@@ -121,6 +132,10 @@ int jacobi_setup_fd(Ctx* ctx, Level& L);
 int jacobi_apply_fd(Ctx* ctx, Level& L, const double* r, double* c, double damping);
 int jacobi_apply_fd_uniform(Ctx* ctx, Level& L, const double* r, double* c, double damping);  // -1: no specialised kernel
 int diag_block_device(Ctx* ctx, Level& L, long e, double* d_out);
+
+int bcrs_build(Ctx* ctx, Level& L);
+int bcrs_mv(Ctx* ctx, Level& L, const double* x, double* y);
+int blockgs_iterate(Ctx* ctx, Level& L, const double* b, double* x);
 
 int launch_restrict(Ctx* ctx, Level& fine, Level& coarse, const double* xf, double* xc);
 int launch_prolong(Ctx* ctx, Level& fine, Level& coarse, const double* xc, double* xf);

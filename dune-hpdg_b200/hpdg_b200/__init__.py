@@ -56,6 +56,12 @@ SIGNATURES = {
     "hpdg_jacobi_apply_device": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_double]),
     "hpdg_jacobi_bytes": (C.c_size_t, [_vp, C.c_int, C.c_int]),
     "hpdg_diag_block": (C.c_int, [_vp, C.c_int, C.c_long, _dp]),
+    "hpdg_bcrs_sizes": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_long), C.POINTER(C.c_long)]),
+    "hpdg_assemble_bcrs": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "hpdg_bcrs_mv": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "hpdg_bcrs_mv_device": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "hpdg_blockgs_iterate": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "hpdg_blockgs_iterate_device": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "hpdg_restrict": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "hpdg_prolong": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "hpdg_restrict_device": (C.c_int, [_vp, C.c_int, _vp, _vp]),
@@ -276,6 +282,46 @@ class BlockJacobi:
         out = np.zeros((n, n))
         self.ctx._ck(lib().hpdg_diag_block(self.ctx._h, self.level, e, out))
         return out
+
+
+class AssembledMatrix:
+    """The SIPG matrix in DynamicBCRSMatrix layout (common/dynamicbcrs.hh:178-199), assembled on the device:
+    the drop-in for `BuildingBlocks::laplace` (buildingblocks/matrices.hh:29-89) + `mv` (matrixwindow.hh:196-209)."""
+
+    def __init__(self, ctx, level=FINEST):
+        self.ctx, self.level = ctx, level
+        nb, ne = C.c_long(), C.c_long()
+        ctx._ck(lib().hpdg_bcrs_sizes(ctx._h, level, C.byref(nb), C.byref(ne)))
+        self.block_row_ptr = np.zeros(ctx.num_elements + 1, dtype=np.int64)
+        self.block_col = np.zeros(nb.value, dtype=np.int32)
+        self.block_off = np.zeros(nb.value + 1, dtype=np.int64)
+        self.entries = np.zeros(ne.value)
+        ctx._ck(lib().hpdg_assemble_bcrs(ctx._h, level, self.block_row_ptr.ctypes.data, self.block_col.ctypes.data,
+                                         self.block_off.ctypes.data, self.entries.ctypes.data))
+
+    def mv(self, x, y=None):
+        if y is None:
+            y = np.zeros(self.ctx.dimension(self.level))
+        self.ctx._ck(lib().hpdg_bcrs_mv(self.ctx._h, self.level, _hptr(x), _hptr(y)))
+        return y
+
+
+class DynamicBlockGS:
+    """`LinearIterationStep` face of the reference's default smoother (iterationsteps/dynamicblockgs.hh:87-127)."""
+
+    def __init__(self, matrix):
+        self.mat_ = matrix
+        self.x_ = self.rhs_ = None
+
+    def setProblem(self, x, rhs):
+        self.x_, self.rhs_ = x, rhs
+
+    def preprocess(self):
+        pass
+
+    def iterate(self):
+        c = self.mat_.ctx
+        c._ck(lib().hpdg_blockgs_iterate(c._h, self.mat_.level, _hptr(self.rhs_), _hptr(self.x_)))
 
 
 class OrderTransfer:

@@ -92,6 +92,23 @@ size_t hpdg_jacobi_bytes(const hpdg_ctx* ctx, int level, int form);
  * slowipdgdiag.hh:32-218): the diagonal block A_ee, n_e x n_e row-major, to host memory. */
 int hpdg_diag_block(hpdg_ctx* ctx, int level, long element, double* h_out);
 
+/* -- assembled matrix in the reference's DynamicBCRSMatrix layout (common/dynamicbcrs.hh:178-199: one contiguous array,
+ * blocks in (block row, ascending block column) order, each dense row-major rowMap[i] x colMap[j]) -- replaces
+ * BuildingBlocks::laplace / dynamicStiffnessMatrix (buildingblocks/matrices.hh:29-89, test/testobjects.hh:20-81).
+ * Intended for small/medium meshes (3-D Q3 costs 229 KB per element).  hpdg_bcrs_sizes gives the array lengths;
+ * hpdg_assemble_bcrs builds the matrix on the device (it stays resident for hpdg_bcrs_mv / hpdg_blockgs_iterate) and copies
+ * pattern + entries to the host arrays (any of them may be NULL). */
+int hpdg_bcrs_sizes(hpdg_ctx* ctx, int level, long* nblocks, long* nentries);
+int hpdg_assemble_bcrs(hpdg_ctx* ctx, int level, long* h_block_row_ptr /* nelem+1 */, int* h_block_col /* nblocks */,
+                       long* h_block_off /* nblocks+1 */, double* h_entries /* nentries */);
+/* y = A x with the assembled matrix: BCRSMatrix<MatrixWindow>::mv (common/matrixwindow.hh:196-209) */
+int hpdg_bcrs_mv(hpdg_ctx* ctx, int level, const double* h_x, double* h_y);
+int hpdg_bcrs_mv_device(hpdg_ctx* ctx, int level, const double* d_x, double* d_y);
+/* one DynamicBlockGS::iterate() with the GSCore local solver (iterationsteps/dynamicblockgs.hh:17-40,94-126): block rows in
+ * ascending order, inner forward scalar GS sweep from zero.  x is updated in place. */
+int hpdg_blockgs_iterate(hpdg_ctx* ctx, int level, const double* h_b, double* h_x);
+int hpdg_blockgs_iterate_device(hpdg_ctx* ctx, int level, const double* d_b, double* d_x);
+
 /* -- p-transfer between level and level-1 (transferoperators/ordertransfer.hh:91-119) ------------- */
 int hpdg_restrict(hpdg_ctx* ctx, int fine_level, const double* h_fine, double* h_coarse);
 int hpdg_prolong(hpdg_ctx* ctx, int fine_level, const double* h_coarse, double* h_fine);

@@ -208,3 +208,62 @@ def test_vcycle_vs_oracle(orc, hp, form):
     assert rel(x, xr) < 1e-11 and rel(bb, rr) < 1e-10
     # the returned b is the residual of the returned x (multigrid_impl.hh:60-61)
     assert rel(bb, b - fine.apply_mf(x, threads=orc.max_threads())) < 1e-10
+
+
+def test_cfg1_assemble_matvec_blockgs(orc, hp):
+    # BASELINE config 1: 2D 16x16 Q2: assemble + matvec + 10 block-GS sweeps (test_dynamicblockgs.cc / testdg.cc)
+    m = orc.Mesh((16, 16), degree=2, sigma=2.0, dirichlet=True)
+    A = m.assemble()
+    rowptr, col, boff, val = A.export()
+    ctx = hp.Context((16, 16), degree=2, sigma=2.0, dirichlet=True)
+    G = hp.AssembledMatrix(ctx)
+    assert np.array_equal(G.block_row_ptr, rowptr) and np.array_equal(G.block_col, col) and np.array_equal(G.block_off, boff)
+    assert np.linalg.norm(G.entries - val) < 1e-12 * np.linalg.norm(val)          # test_matrices.cc: Frobenius
+    x = m.interpolate_normsq()
+    assert rel(G.mv(x), A.mv(x)) < TOL
+    b = np.ones(m.ndof)
+    xr = np.ones(m.ndof)
+    xg = np.ones(m.ndof)
+    gs = hp.DynamicBlockGS(G)
+    gs.setProblem(xg, b)
+    for _ in range(10):
+        A.blockgs_iterate(b, xr)
+        gs.iterate()
+    assert rel(xg, xr) < TOL
+
+
+@pytest.mark.parametrize("dim,n", [(2, (5, 4)), (3, (3, 4, 2)), (3, (1, 3, 1))])
+def test_assembled_hp_and_blockgs(orc, hp, dim, n):
+    rng = np.random.default_rng(11)
+    deg = rng.integers(1, 5, int(np.prod(n))).astype(np.int32)
+    for dirichlet in (True, False):
+        m = orc.Mesh(n, L=[1.0, 1.5, 0.75][:dim], degree=deg, dirichlet=dirichlet)
+        A = m.assemble()
+        rowptr, col, boff, val = A.export()
+        ctx = hp.Context(n, L=[1.0, 1.5, 0.75][:dim], degree=deg, dirichlet=dirichlet)
+        G = hp.AssembledMatrix(ctx)
+        assert np.array_equal(G.block_col, col) and np.array_equal(G.block_off, boff)
+        assert np.linalg.norm(G.entries - val) < 1e-12 * np.linalg.norm(val)
+        x = orc.fill_random(m.ndof)
+        assert rel(G.mv(x), A.mv(x)) < TOL
+        b = orc.fill_random(m.ndof, 5)
+        xr, xg = x.copy(), x.copy()
+        gs = hp.DynamicBlockGS(G)
+        gs.setProblem(xg, b)
+        for _ in range(3):
+            A.blockgs_iterate(b, xr)
+            gs.iterate()
+        assert rel(xg, xr) < 1e-11
+
+
+def test_dynamicblockgs_small_system_on_device(orc, hp):
+    # test/test_dynamicblockgs.cc:24-44 on the device: 2x2, k=2, sigma 1.5, b = 1, x0 = 1, 100 sweeps -> |b - Ax| < 1e-13
+    ctx = hp.Context((2, 2), degree=2, sigma=1.5, dirichlet=True)
+    G = hp.AssembledMatrix(ctx)
+    n = ctx.dimension()
+    b, x = np.ones(n), np.ones(n)
+    gs = hp.DynamicBlockGS(G)
+    gs.setProblem(x, b)
+    for _ in range(100):
+        gs.iterate()
+    assert np.linalg.norm(b - G.mv(x)) < 1e-13
