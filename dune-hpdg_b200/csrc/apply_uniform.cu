@@ -498,6 +498,30 @@ __global__ void k_pack_traces(const double* __restrict__ x, PackParams PK, int n
   }
 }
 
+// compact tile lists (tiles that touch no rank boundary / tiles that do), built once per (level, tile shape)
+int uniform_tile_lists(Ctx* ctx, Level& L, int TX, int TY, int TZ, const int* bmode) {
+  const long key = ((long)TX << 16) | ((long)TY << 8) | TZ;
+  if (L.tile_key == key) return 0;
+  const int nt[3] = {(L.n[0] + TX - 1) / TX, (L.n[1] + TY - 1) / TY, (L.n[2] + TZ - 1) / TZ};
+  std::vector<int> li, lb;
+  for (int tz = 0; tz < nt[2]; tz++) for (int ty = 0; ty < nt[1]; ty++) for (int tx = 0; tx < nt[0]; tx++) {
+    const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;
+    const int lx = std::min(TX, L.n[0] - x0), ly = std::min(TY, L.n[1] - y0), lz = std::min(TZ, L.n[2] - z0);
+    const bool touch = (x0 == 0 && bmode[0] == 3) || (x0 + lx == L.n[0] && bmode[1] == 3) ||
+                       (y0 == 0 && bmode[2] == 3) || (y0 + ly == L.n[1] && bmode[3] == 3) ||
+                       (z0 == 0 && bmode[4] == 3) || (z0 + lz == L.n[2] && bmode[5] == 3);
+    (touch ? lb : li).push_back(tx + nt[0] * (ty + nt[1] * tz));
+  }
+  cudaFree(L.d_tiles_int); cudaFree(L.d_tiles_bnd);
+  L.d_tiles_int = L.d_tiles_bnd = nullptr;
+  HPDG_CUDA(cudaMalloc(&L.d_tiles_int, sizeof(int) * std::max<size_t>(li.size(), 1)));
+  HPDG_CUDA(cudaMalloc(&L.d_tiles_bnd, sizeof(int) * std::max<size_t>(lb.size(), 1)));
+  HPDG_CUDA(cudaMemcpy(L.d_tiles_int, li.data(), sizeof(int) * li.size(), cudaMemcpyHostToDevice));
+  HPDG_CUDA(cudaMemcpy(L.d_tiles_bnd, lb.data(), sizeof(int) * lb.size(), cudaMemcpyHostToDevice));
+  L.n_tiles_int = (long)li.size(); L.n_tiles_bnd = (long)lb.size(); L.tile_key = key;
+  return 0;
+}
+
 template <int N, int TX, int TY, int TZ, int MINB, bool EARLY = true>
 static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream) {
   static UniParams<N> P;  // rebuilt per call (cheap); static to keep it off the stack
@@ -536,31 +560,12 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
   P.tile_list = nullptr; P.tile_offset = 0;
   long nlist = 0;
   if (part != 0) {
-    // compact tile lists of the two parts, built once per (level, tile shape)
-    const long key = ((long)TX << 16) | ((long)TY << 8) | TZ;
-    if (L.tile_key != key) {
-      std::vector<int> li, lb;
-      for (int tz = 0; tz < P.ntile[2]; tz++) for (int ty = 0; ty < P.ntile[1]; ty++) for (int tx = 0; tx < P.ntile[0]; tx++) {
-        const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;
-        const int lx = std::min(TX, L.n[0] - x0), ly = std::min(TY, L.n[1] - y0), lz = std::min(TZ, L.n[2] - z0);
-        const bool touch = (x0 == 0 && P.bmode[0] == 3) || (x0 + lx == L.n[0] && P.bmode[1] == 3) ||
-                           (y0 == 0 && P.bmode[2] == 3) || (y0 + ly == L.n[1] && P.bmode[3] == 3) ||
-                           (z0 == 0 && P.bmode[4] == 3) || (z0 + lz == L.n[2] && P.bmode[5] == 3);
-        (touch ? lb : li).push_back(tx + P.ntile[0] * (ty + P.ntile[1] * tz));
-      }
-      cudaFree(L.d_tiles_int); cudaFree(L.d_tiles_bnd);
-      L.d_tiles_int = L.d_tiles_bnd = nullptr;
-      HPDG_CUDA(cudaMalloc(&L.d_tiles_int, sizeof(int) * std::max<size_t>(li.size(), 1)));
-      HPDG_CUDA(cudaMalloc(&L.d_tiles_bnd, sizeof(int) * std::max<size_t>(lb.size(), 1)));
-      HPDG_CUDA(cudaMemcpy(L.d_tiles_int, li.data(), sizeof(int) * li.size(), cudaMemcpyHostToDevice));
-      HPDG_CUDA(cudaMemcpy(L.d_tiles_bnd, lb.data(), sizeof(int) * lb.size(), cudaMemcpyHostToDevice));
-      L.n_tiles_int = (long)li.size(); L.n_tiles_bnd = (long)lb.size(); L.tile_key = key;
-    }
+    if (uniform_tile_lists(ctx, L, TX, TY, TZ, P.bmode)) return 1;
     P.tile_list = part == 1 ? L.d_tiles_int : L.d_tiles_bnd;
     nlist = part == 1 ? L.n_tiles_int : L.n_tiles_bnd;
     if (nlist == 0) return 0;
   }
-  if (ctx->variant % 100 >= 10 && part == 0 && ctx->slab_nz == 0) {
+  if (ctx->variant % 100 >= 10 && ctx->variant % 100 < 20 && part == 0 && ctx->slab_nz == 0) {
     constexpr int threads = uni_threads<N, TX, TY, TZ>();
     constexpr size_t smem = sizeof(double) * 3 * TX * TY * TZ * Pitch<N>::EP;
     static bool attr_set_pipe = false;
@@ -623,6 +628,7 @@ int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double 
         case 7: return launch_uni<4, 4, 2, 4, 4, false>(ctx, L, x, y, factor, part, stream);
         case 8: return launch_uni<4, 2, 4, 4, 4, false>(ctx, L, x, y, factor, part, stream);
         case 9: return launch_uni<4, 4, 4, 4, 3, true>(ctx, L, x, y, factor, part, stream);
+        case 21: case 22: return launch_apply_uniform3(ctx, L, x, y, factor, part, stream);  // experimental 3-pass kernel
         default: return launch_uni<4, 4, 4, 4, 3, false>(ctx, L, x, y, factor, part, stream);
       }
     case 4:

@@ -124,6 +124,8 @@ int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double 
 int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream = nullptr);
 int uniform_supported(const Ctx* ctx, const Level& L);
 int uniform_tile_height(const Level& L);
+int uniform_tile_lists(Ctx* ctx, Level& L, int TX, int TY, int TZ, const int* bmode);
+int launch_apply_uniform3(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream);
 int launch_pack_traces(Ctx* ctx, Level& L, const double* x, cudaStream_t stream);
 
 int jacobi_setup_dense(Ctx* ctx, Level& L);
