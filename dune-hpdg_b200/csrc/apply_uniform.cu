@@ -34,6 +34,7 @@ struct UniParams {
   double Dp[3][N * N];
   double A0[3][N], B0[3][N], A1[3][N], B1[3][N];
   double M[N * N];
+  double Mf[N * N];  // factor * M: the last (z) mass sweep carries the operator's factor
   double g[2][N];
   double cohk[3];  // cpen / (kappa_d / 2)
   double factor;
@@ -108,14 +109,14 @@ __device__ __forceinline__ void pencil_apply(const UniParams<N>& P, const double
   }
 }
 
-template <int N>
+template <int N, bool SCALED = false>
 __device__ __forceinline__ void mass_line(const UniParams<N>& P, double (&a)[N]) {
   double o[N];
 #pragma unroll
   for (int i = 0; i < N; i++) {
     double s = 0;
 #pragma unroll
-    for (int m = 0; m < N; m++) s = fma(P.M[i * N + m], a[m], s);
+    for (int m = 0; m < N; m++) s = fma(SCALED ? P.Mf[i * N + m] : P.M[i * N + m], a[m], s);
     o[i] = s;
   }
 #pragma unroll
@@ -127,6 +128,13 @@ template <int N>
 __device__ __forceinline__ void outside_trace(const UniParams<N>& P, const double* __restrict__ line, long stride,
                                               int side /* near side of that element */, double& der, double& val) {
   if (P.dbg & 1) { der = 0; val = 0; return; }
+  if (N == 4 && stride == 1) {  // an x line is 32 contiguous, 32-byte aligned bytes: two 128-bit loads
+    const double2 lo = __ldg(reinterpret_cast<const double2*>(line));
+    const double2 hi = __ldg(reinterpret_cast<const double2*>(line) + 1);
+    der = fma(P.g[side][0], lo.x, fma(P.g[side][1], lo.y, fma(P.g[side][2], hi.x, P.g[side][3] * hi.y)));
+    val = side ? hi.y : lo.x;
+    return;
+  }
   double d = 0, last = 0, first = 0;
 #pragma unroll
   for (int m = 0; m < N; m++) {
@@ -307,10 +315,12 @@ __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restr
         double a[N];
 #pragma unroll
         for (int k = 0; k < N; k++) a[k] = sw[base + PP * k];
-        mass_line<N>(P, a);
+        mass_line<N, true>(P, a);
         double* yo = P.y + ecol + (long)(z0 + e) * sz + node;
 #pragma unroll
-        for (int k = 0; k < N; k++) yo[N2 * k] = P.factor * a[k];
+        for (int k = 0; k < N; k++) {
+          if (P.dbg & 16) __stcs(yo + N2 * k, a[k]); else yo[N2 * k] = a[k];
+        }
       }
   }
 }
@@ -543,7 +553,7 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
       P.B1[d][i] = -c * T.mt[1][i] + hk * T.mg[1][i];
     }
   }
-  for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) P.M[i * N + j] = T.M[i * kMaxN + j];
+  for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) { P.M[i * N + j] = T.M[i * kMaxN + j]; P.Mf[i * N + j] = factor * T.M[i * kMaxN + j]; }
   for (int s = 0; s < 2; s++) for (int i = 0; i < N; i++) P.g[s][i] = T.g[s][i];
   P.factor = factor;
   const int tdim[3] = {TX, TY, TZ};
