@@ -197,10 +197,16 @@ struct VC { int form; double damping; int pre, post, coarse_its; };
 int mg_smooth(Ctx* ctx, int l, const VC& v, int steps, double* x, double* r) {
   Level& L = ctx->levels[l];
   for (int i = 0; i < steps; i++) {                                   // multigrid_impl.hh:76-81
-    if (jacobi_async(ctx, L, v.form, r, L.mg_t1, v.damping)) return 1;  // smoother(tmp1, r)
-    if (launch_axpy(ctx, L.ndof, 1.0, L.mg_t1, x)) return 1;            // x += tmp1
-    if (op_apply_async(ctx, L, L.mg_t1, L.mg_t2, 1.0)) return 1;        // tmp2 = A tmp1
-    if (launch_axpy(ctx, L.ndof, -1.0, L.mg_t2, r)) return 1;           // r -= tmp2
+    // smoother(tmp1, r); x += tmp1 -- fused into the Jacobi kernel (one pass instead of a kernel + an axpy)
+    ctx->fuse_xacc = x;
+    int rc = jacobi_async(ctx, L, v.form, r, L.mg_t1, v.damping);
+    ctx->fuse_xacc = nullptr;
+    if (rc) return 1;
+    // tmp2 = A tmp1; r -= tmp2 -- fused: r = r + (-1) * A tmp1 in the operator kernel's store
+    ctx->fuse_accum = 1;
+    rc = op_apply_async(ctx, L, L.mg_t1, r, -1.0);
+    ctx->fuse_accum = 0;
+    if (rc) return 1;
   }
   return 0;
 }
@@ -224,8 +230,10 @@ int mg_level(Ctx* ctx, int l, const VC& v) {
   if (mg_level(ctx, l - 1, v)) return 1;                                // mu_ = 1
   if (launch_prolong(ctx, L, C, C.mg_x, L.mg_t1)) return 1;             // :108
   if (launch_axpy(ctx, L.ndof, 1.0, L.mg_t1, x)) return 1;
-  if (op_apply_async(ctx, L, L.mg_t1, L.mg_t2, 1.0)) return 1;
-  if (launch_axpy(ctx, L.ndof, -1.0, L.mg_t2, r)) return 1;
+  ctx->fuse_accum = 1;                                                  // r -= A tmp1 (:110-112), fused
+  const int rcc = op_apply_async(ctx, L, L.mg_t1, r, -1.0);
+  ctx->fuse_accum = 0;
+  if (rcc) return 1;
   return mg_smooth(ctx, l, v, v.post, x, r);                            // :116
 }
 

@@ -34,6 +34,7 @@ struct GenericParams {
   const double* x;
   double* y;
   double factor;
+  int accum;
 };
 
 __device__ __forceinline__ int ipow_d(int b, int e) { int r = 1; for (int i = 0; i < e; i++) r *= b; return r; }
@@ -250,7 +251,7 @@ __global__ void k_apply_generic(GenericParams P, int maxno1, long cnt, int smem_
       double s = 0;
 #pragma unroll
       for (int k = 0; k < n1; k++) s += T.M[ad * kMaxN + k] * src[base + k * sd];
-      if (last) P.y[P.off[e] + idx] = P.factor * s; else dst[idx] = s;
+      if (last) P.y[P.off[e] + idx] = P.accum ? P.y[P.off[e] + idx] + P.factor * s : P.factor * s; else dst[idx] = s;
     }
     gsync();
     double* t = src; src = dst; dst = t;
@@ -264,7 +265,7 @@ int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double 
   for (int d = 0; d < 3; d++) { P.n[d] = L.n[d]; P.h[d] = L.h[d]; }
   P.sigma = ctx->sigma; P.dirichlet = ctx->dirichlet;
   P.deg = L.d_deg; P.pdeg = L.d_pdeg; P.off = L.d_off; P.elist = L.d_elist;
-  P.tab = ctx->d_tab; P.P = ctx->d_P; P.x = x; P.y = y; P.factor = factor;
+  P.tab = ctx->d_tab; P.P = ctx->d_P; P.x = x; P.y = y; P.factor = factor; P.accum = ctx->fuse_accum;
   for (size_t b = 0; b < L.bucket_p.size(); b++) {
     long cnt = L.bucket_begin[b + 1] - L.bucket_begin[b];
     if (cnt == 0) continue;

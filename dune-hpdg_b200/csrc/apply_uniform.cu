@@ -44,6 +44,7 @@ struct UniParams {
   const double* ghost[6];  // [face elem][node][2] = (der, val) of the remote element at its near side
   const double* x;
   double* y;
+  int accum; // y = y_old + factor * A x
   int dbg;   // timing experiments only: 1 = skip outside-trace loads (wrong results)
   int part;  // 0 all tiles, 1 only tiles not touching a ghost face, 2 only tiles touching one
   const int* tile_list;  // part != 0: compact list of the tile ids of that part (grid = list length)
@@ -319,7 +320,7 @@ __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restr
         double* yo = P.y + ecol + (long)(z0 + e) * sz + node;
 #pragma unroll
         for (int k = 0; k < N; k++) {
-          if (P.dbg & 16) __stcs(yo + N2 * k, a[k]); else yo[N2 * k] = a[k];
+          yo[N2 * k] = P.accum ? yo[N2 * k] + a[k] : a[k];
         }
       }
   }
@@ -566,7 +567,7 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
       P.bmode[f] = 3; P.ghost[f] = ctx->ghost.d_recv[f];
     } else P.bmode[f] = ctx->dirichlet ? 1 : 2;
   }
-  P.x = x; P.y = y; P.part = part; P.dbg = ctx->variant / 100;
+  P.x = x; P.y = y; P.part = part; P.dbg = ctx->variant / 100; P.accum = ctx->fuse_accum;
   P.tile_list = nullptr; P.tile_offset = 0;
   long nlist = 0;
   if (part != 0) {
@@ -575,7 +576,7 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
     nlist = part == 1 ? L.n_tiles_int : L.n_tiles_bnd;
     if (nlist == 0) return 0;
   }
-  if (ctx->variant % 100 >= 10 && ctx->variant % 100 < 20 && part == 0 && ctx->slab_nz == 0) {
+  if (ctx->variant % 100 >= 10 && ctx->variant % 100 < 20 && part == 0 && ctx->slab_nz == 0 && !ctx->fuse_accum) {
     constexpr int threads = uni_threads<N, TX, TY, TZ>();
     constexpr size_t smem = sizeof(double) * 3 * TX * TY * TZ * Pitch<N>::EP;
     static bool attr_set_pipe = false;
@@ -638,7 +639,7 @@ int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double 
         case 7: return launch_uni<4, 4, 2, 4, 4, false>(ctx, L, x, y, factor, part, stream);
         case 8: return launch_uni<4, 2, 4, 4, 4, false>(ctx, L, x, y, factor, part, stream);
         case 9: return launch_uni<4, 4, 4, 4, 3, true>(ctx, L, x, y, factor, part, stream);
-        case 21: case 22: return launch_apply_uniform3(ctx, L, x, y, factor, part, stream);  // experimental 3-pass kernel
+        case 21: case 22: if (ctx->fuse_accum) { ctx->err = "accumulate mode is not implemented in the experimental kernel"; return 1; } return launch_apply_uniform3(ctx, L, x, y, factor, part, stream);  // experimental 3-pass kernel
         default: return launch_uni<4, 4, 4, 4, 3, false>(ctx, L, x, y, factor, part, stream);
       }
     case 4:

@@ -106,6 +106,9 @@ struct Ctx {
   int slab_z0 = 0, slab_nz = 0;  // restrict the next uniform launch to element layers [z0, z0+nz) (chunked host apply)
   cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;
   cudaEvent_t ev_chunk[3][32] = {};
+  // fusion requests of the V-cycle driver, consumed by the next launch:
+  int fuse_accum = 0;          // apply: y = y_old + factor * A x   (r -= A c without a separate axpy)
+  double* fuse_xacc = nullptr; // block Jacobi: additionally x += c
   long launches = 0;  // kernels launched by this context (bench.py's gpu_launches)
 };
 

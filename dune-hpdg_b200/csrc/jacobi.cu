@@ -123,7 +123,7 @@ __global__ void k_invert_blocks(double* A_all, int n) {
 // symmetric inverse (coalesced over i).
 __global__ void k_jacobi_dense(const double* __restrict__ inv, const int* __restrict__ elist, long ebegin, long cnt,
                                const long* __restrict__ off, int ne, int eper, const double* __restrict__ r,
-                               double* __restrict__ c, double damping) {
+                               double* __restrict__ c, double damping, double* __restrict__ xacc) {
   extern __shared__ double sr[];  // eper * ne
   const int slot = threadIdx.x / ne, i = threadIdx.x % ne;
   const long b = (long)blockIdx.x * eper + slot;
@@ -143,7 +143,9 @@ __global__ void k_jacobi_dense(const double* __restrict__ inv, const int* __rest
     a3 = fma(__ldcs(A + (size_t)(j + 3) * ne + i), rr[j + 3], a3);
   }
   for (; j < ne; j++) a0 = fma(__ldcs(A + (size_t)j * ne + i), rr[j], a0);
-  c[off[e] + i] = damping * ((a0 + a1) + (a2 + a3));
+  const double cv = damping * ((a0 + a1) + (a2 + a3));
+  c[off[e] + i] = cv;
+  if (xacc) xacc[off[e] + i] += cv;
 }
 
 static BlkParams make_blk(Ctx* ctx, Level& L) {
@@ -215,7 +217,7 @@ int jacobi_apply_dense(Ctx* ctx, Level& L, const double* r, double* c, double da
     threads = (threads + 31) / 32 * 32;
     long blocks = (cnt + eper - 1) / eper;
     k_jacobi_dense<<<(unsigned)blocks, threads, (size_t)eper * ne * sizeof(double), ctx->stream>>>(
-        L.jd.d_inv + L.jd.bucket_off[b], L.d_elist, L.bucket_begin[b], cnt, L.d_off, ne, eper, r, c, damping);
+        L.jd.d_inv + L.jd.bucket_off[b], L.d_elist, L.bucket_begin[b], cnt, L.d_off, ne, eper, r, c, damping, ctx->fuse_xacc);
     ctx->launches++;
     HPDG_CUDA(cudaGetLastError());
   }
@@ -254,6 +256,7 @@ struct FDParams {
   const double* r;
   double* c;
   double damping;
+  double* xacc;
 };
 constexpr int kFacStride = kMaxN * kMaxN + kMaxN;
 
@@ -296,7 +299,7 @@ __global__ void k_jacobi_fd(FDParams P) {
       const int ad = (idx / sd) % n1, base = idx - ad * sd;
       double s = 0;
       for (int k = 0; k < n1; k++) s += V[ad * n1 + k] * src[base + k * sd];
-      if (last) P.c[P.off[e] + idx] = P.damping * s; else dst[idx] = s;
+      if (last) { const double cv = P.damping * s; P.c[P.off[e] + idx] = cv; if (P.xacc) P.xacc[P.off[e] + idx] += cv; } else dst[idx] = s;
     }
     __syncthreads();
     double* t = src; src = dst; dst = t; sd *= n1;
@@ -384,7 +387,7 @@ int jacobi_apply_fd(Ctx* ctx, Level& L, const double* r, double* c, double dampi
   if (jacobi_build_fd_generic(ctx, L)) return 1;
   FDParams P;
   P.dim = L.dim; P.deg = L.d_deg; P.off = L.d_off; P.elist = L.d_elist; P.fac = L.jf.d_fac; P.idx = L.jf.d_idx;
-  P.r = r; P.c = c; P.damping = damping;
+  P.r = r; P.c = c; P.damping = damping; P.xacc = ctx->fuse_xacc;
   for (size_t b = 0; b < L.bucket_p.size(); b++) {
     long cnt = L.bucket_begin[b + 1] - L.bucket_begin[b];
     if (!cnt) continue;

@@ -27,6 +27,7 @@ struct FDUniParams {
   int bnd[6];  // 1 if brick face f is a domain boundary (as opposed to a rank boundary)
   const double* r;
   double* c;
+  double* xacc;  // optional: x += c
 };
 
 template <int N> struct PitchJ {
@@ -163,7 +164,11 @@ k_jacobi_fd_uniform(const __grid_constant__ FDUniParams<N> P) {
         fd_line_v<N, 2, false>(P, variant(2, z0 + e), a);
         double* co = P.c + zcol + (long)(z0 + e) * sz;
 #pragma unroll
-        for (int k = 0; k < N; k++) co[N2 * k] = P.damping * a[k];
+        for (int k = 0; k < N; k++) {
+          const double cv = P.damping * a[k];
+          co[N2 * k] = cv;
+          if (P.xacc) { double* xo = P.xacc + zcol + (long)(z0 + e) * sz; xo[N2 * k] += cv; }
+        }
       }
   }
 }
@@ -202,7 +207,7 @@ static int launch_fdu(Ctx* ctx, Level& L, const double* r, double* c, double dam
   }
   const int tdim[3] = {TX, TY, TZ};
   for (int d = 0; d < 3; d++) { P.n[d] = L.n[d]; P.ntile[d] = (L.n[d] + tdim[d] - 1) / tdim[d]; }
-  P.damping = damping; P.r = r; P.c = c;
+  P.damping = damping; P.r = r; P.c = c; P.xacc = ctx->fuse_xacc;
   constexpr int threads = fdu_threads<N, TX, TY, TZ>();
   constexpr size_t smem = sizeof(double) * TX * TY * TZ * PitchJ<N>::EP;
   static bool attr_set = false;
