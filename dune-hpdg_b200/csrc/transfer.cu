@@ -71,6 +71,64 @@ __global__ void k_transfer(XferParams P) {
   }
 }
 
+// Uniform level -> uniform level in 3-D: a warp per element, all extents compile-time, 4 elements per CTA.
+template <int NF, int NC, bool RESTRICT>
+__global__ void __launch_bounds__(128) k_transfer_uniform(const double* __restrict__ T /* [i fine][j coarse], stride kMaxN */,
+                                                          const double* __restrict__ in, double* __restrict__ out, long nelem) {
+  constexpr int NIN = RESTRICT ? NF : NC, NOUT = RESTRICT ? NC : NF;
+  constexpr int F3 = NF * NF * NF;
+  __shared__ double sT[NF * NC];
+  __shared__ double buf[4][2][F3];
+  for (int t = threadIdx.x; t < NF * NC; t += blockDim.x) sT[t] = T[(t / NC) * kMaxN + (t % NC)];
+  __syncthreads();
+  const int w = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const long e = (long)blockIdx.x * 4 + w;
+  if (e >= nelem) return;
+  constexpr int TIN = NIN * NIN * NIN, TOUT = NOUT * NOUT * NOUT;
+  const double* ein = in + e * TIN;
+  double* eout = out + e * TOUT;
+  double* a = buf[w][0]; double* b = buf[w][1];
+  for (int i = lane; i < TIN; i += 32) a[i] = ein[i];
+  __syncwarp();
+  // x: (NIN, NIN, NIN) -> (NOUT, NIN, NIN)
+  for (int idx = lane; idx < NOUT * NIN * NIN; idx += 32) {
+    const int o = idx % NOUT, r = idx / NOUT;
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < NIN; k++) s = fma(RESTRICT ? sT[k * NC + o] : sT[o * NC + k], a[k + NIN * r], s);
+    b[idx] = s;
+  }
+  __syncwarp();
+  // y: (NOUT, NIN, NIN) -> (NOUT, NOUT, NIN)
+  for (int idx = lane; idx < NOUT * NOUT * NIN; idx += 32) {
+    const int i0 = idx % NOUT, o = (idx / NOUT) % NOUT, i2 = idx / (NOUT * NOUT);
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < NIN; k++) s = fma(RESTRICT ? sT[k * NC + o] : sT[o * NC + k], b[i0 + NOUT * (k + NIN * i2)], s);
+    a[idx] = s;
+  }
+  __syncwarp();
+  // z: (NOUT, NOUT, NIN) -> (NOUT, NOUT, NOUT)
+  for (int idx = lane; idx < TOUT; idx += 32) {
+    const int r = idx % (NOUT * NOUT), o = idx / (NOUT * NOUT);
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < NIN; k++) s = fma(RESTRICT ? sT[k * NC + o] : sT[o * NC + k], a[r + NOUT * NOUT * k], s);
+    eout[idx] = s;
+  }
+}
+
+template <int NF, int NC>
+static int xfer_uniform(Ctx* ctx, long nelem, const double* in, double* out, bool restrict_) {
+  const double* T = ctx->d_T + ((size_t)(NC - 1) * (kMaxP + 1) + (NF - 1)) * kMaxN * kMaxN;
+  const unsigned grid = (unsigned)((nelem + 3) / 4);
+  if (restrict_) k_transfer_uniform<NF, NC, true><<<grid, 128, 0, ctx->stream>>>(T, in, out, nelem);
+  else k_transfer_uniform<NF, NC, false><<<grid, 128, 0, ctx->stream>>>(T, in, out, nelem);
+  ctx->launches++;
+  HPDG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static XferParams make_x(Ctx* ctx, Level& fine, Level& coarse, const double* in, double* out) {
   XferParams P;
   P.dim = fine.dim; P.degf = fine.d_deg; P.degc = coarse.d_deg; P.offf = fine.d_off; P.offc = coarse.d_off;
@@ -79,6 +137,17 @@ static XferParams make_x(Ctx* ctx, Level& fine, Level& coarse, const double* in,
 }
 
 static int xfer_launch(Ctx* ctx, Level& fine, Level& coarse, const double* in, double* out, bool restrict_) {
+  if (fine.dim == 3 && fine.uniform && coarse.uniform && !ctx->force_generic) {
+    const int key = (fine.p_uni + 1) * 16 + (coarse.p_uni + 1);
+    switch (key) {
+      case 3 * 16 + 2: return xfer_uniform<3, 2>(ctx, fine.nelem, in, out, restrict_);
+      case 4 * 16 + 2: return xfer_uniform<4, 2>(ctx, fine.nelem, in, out, restrict_);
+      case 5 * 16 + 3: return xfer_uniform<5, 3>(ctx, fine.nelem, in, out, restrict_);
+      case 6 * 16 + 3: return xfer_uniform<6, 3>(ctx, fine.nelem, in, out, restrict_);
+      case 7 * 16 + 4: return xfer_uniform<7, 4>(ctx, fine.nelem, in, out, restrict_);
+      default: break;
+    }
+  }
   XferParams P = make_x(ctx, fine, coarse, in, out);
   int n1 = fine.maxp + 1, mx = 1;
   for (int d = 0; d < fine.dim; d++) mx *= n1;

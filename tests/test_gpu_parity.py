@@ -172,6 +172,25 @@ def test_transfer_vs_oracle(orc, hp):
         assert rel(t1.prolong(xcc), l1.prolong(l0, xcc)) < TOL
 
 
+@pytest.mark.parametrize("p", [2, 3, 4, 5, 6])
+def test_transfer_uniform_levels(orc, hp, p):
+    # uniform p-hierarchy (e.g. 4 -> 2 -> 1, the BASELINE config 4 transfer): specialised warp-per-element kernels
+    n = (5, 3, 4)
+    fine = orc.Mesh(n, degree=p)
+    ctx = hp.Context(n, degree=p)
+    nl = ctx.build_p_hierarchy()
+    levels = [fine]
+    for l in range(nl - 2, -1, -1):
+        levels.insert(0, levels[0].coarsen(int(ctx.level_degrees(l)[0])))
+    for l in range(nl - 1, 0, -1):
+        f, c = levels[l], levels[l - 1]
+        xf = orc.fill_random(f.ndof, seed=l)
+        t = hp.OrderTransfer(ctx, l)
+        xc = t.restrict(xf)
+        assert rel(xc, f.restrict(c, xf)) < TOL
+        assert rel(t.prolong(xc), f.prolong(c, xc)) < TOL
+
+
 def test_coarse_level_operator_is_galerkin_product(orc, hp):
     # level operators below the finest are T^T A T (ordertransfer.hh:124-144)
     n = (3, 3, 2)
