@@ -182,6 +182,8 @@ def main():
                          nranks=world, nccl_id=bytes(idt.cpu().tolist()))
     else:
         ctx = hp.Context(n, L=L, degree=degree, sigma=2.0, dirichlet=True, device=local_rank)
+    from hpdg_b200 import partition as part
+    p2p = part.enable_p2p_halo(ctx, dist, torch, world) if world > 1 else False
     ndof = ctx.dimension()
     op = hp.Operator(ctx)
     assert ctx.uses_uniform_kernel()
@@ -258,7 +260,9 @@ def main():
             "config": {"workload": desc, "elements_per_gpu": list(n), "degree": degree, "dof_per_gpu": ndof,
                        "pgrid": list(pgrid), "sigma": 2.0, "dirichlet": True,
                        "l2": f"{NBUF} rotating (x,y) pairs of {ndof * 8 / 1e6:.0f} MB each: inputs larger than the 126 MB L2",
-                       "halo": "NCCL send/recv of face traces overlapped with interior tiles" if world > 1 else "none"},
+                       "halo": ("none" if world == 1 else "NVLink peer-memory stores of face traces from the pack kernel + step flags; rank-boundary "
+                                "tiles of the one tile kernel wait on them" if p2p else
+                                "NCCL send/recv of face traces overlapped with interior tiles")},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "DoF/s", "h2d_bytes_per_step": ndof * 8, "d2h_bytes_per_step": ndof * 8,
                     "steps": e2e_steps, "api": "hpdg_op_apply (host pointers, pinned)", "checksum": checksum},

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/hpdg_b200.h"
@@ -157,10 +158,27 @@ int ensure_stage(Ctx* ctx, size_t ndof) {
 // <= 6 face neighbours (the copyFromMaster analogue, parallel/communicationhpdg.hh:411-418) -> rank-boundary tiles.
 // The two streams write disjoint tiles of y; the compute stream joins the halo stream at the end.
 int op_apply_distributed(Ctx* ctx, Level& L, const double* d_x, double* d_y, double factor) {
+  if (ctx->ghost.p2p) {
+    // NVLink peer-memory halo, no NCCL call in the loop.  Halo stream (highest priority): pack kernel storing this rank's face
+    // traces straight into the neighbours' arenas -> flag kernel.  Compute stream, concurrently: ONE tile kernel over all tiles,
+    // interior tiles first; its rank-boundary tiles wait on the flags the NEIGHBOURS raise (the local pack is not a dependency
+    // of the local apply).  The compute stream joins the halo stream at the end so that x may be overwritten afterwards.
+    ctx->ghost.step++;
+    HPDG_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));                  // x is ready
+    HPDG_CUDA(cudaStreamWaitEvent(ctx->stream_comm, ctx->ev_a, 0));
+    if (launch_pack_traces(ctx, L, d_x, ctx->stream_comm)) return 1;
+    if (launch_halo_flags(ctx, ctx->stream_comm)) return 1;
+    HPDG_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream_comm));
+    if (launch_apply_uniform(ctx, L, d_x, d_y, factor, 3, ctx->stream)) return 1;
+    HPDG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
+    return 0;
+  }
+  static const int dbg = getenv("HPDG_DEBUG_HALO") ? atoi(getenv("HPDG_DEBUG_HALO")) : 0;  // timing experiments only
   HPDG_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));                    // x is ready
   HPDG_CUDA(cudaStreamWaitEvent(ctx->stream_comm, ctx->ev_a, 0));
-  if (launch_pack_traces(ctx, L, d_x, ctx->stream_comm)) return 1;
+  if (!(dbg & 2)) if (launch_pack_traces(ctx, L, d_x, ctx->stream_comm)) return 1;
   ncclComm_t comm = (ncclComm_t)ctx->nccl;
+  if (!(dbg & 1)) {
   HPDG_NCCL(g_nccl.GroupStart());
   for (int f = 0; f < 6; f++) {
     if (!ctx->ghost.active[f]) continue;
@@ -168,6 +186,7 @@ int op_apply_distributed(Ctx* ctx, Level& L, const double* d_x, double* d_y, dou
     HPDG_NCCL(g_nccl.Recv(ctx->ghost.d_recv[f], ctx->ghost.count[f], ncclDouble, ctx->ghost.peer[f], comm, ctx->stream_comm));
   }
   HPDG_NCCL(g_nccl.GroupEnd());
+  }
   if (launch_apply_uniform(ctx, L, d_x, d_y, factor, 2, ctx->stream_comm)) return 1;   // rank-boundary tiles
   HPDG_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream_comm));
   if (launch_apply_uniform(ctx, L, d_x, d_y, factor, 1, ctx->stream)) return 1;        // interior tiles, overlaps the exchange
@@ -333,6 +352,16 @@ int hpdg_create_distributed(hpdg_ctx** out, int dim, const int* n, const double*
           cudaMalloc(&ctx->ghost.d_recv[f], ctx->ghost.count[f] * sizeof(double)) != cudaSuccess)
         return fail("cudaMalloc of halo buffers failed");
     }
+    // arena for the peer-to-peer mode: identical layout on every rank (all six faces, sized from the brick shape)
+    size_t offb = 0;
+    for (int f = 0; f < 6; f++) {
+      const size_t bytes = ((size_t)nelem / n[f / 2]) * N2 * 2 * sizeof(double);
+      for (int par = 0; par < 2; par++) { ctx->ghost.recv_off[f][par] = offb; offb += (bytes + 255) / 256 * 256; }
+    }
+    ctx->ghost.flag_off = offb; offb += 256;
+    ctx->ghost.arena_bytes = offb;
+    if (cudaMalloc(&ctx->ghost.arena, offb) != cudaSuccess || cudaMemset(ctx->ghost.arena, 0, offb) != cudaSuccess)
+      return fail("cudaMalloc of the halo arena failed");
   }
   *out = ctx;
   return 0;
@@ -345,7 +374,8 @@ void hpdg_destroy(hpdg_ctx* ctx) {
   if (ctx->stream_comm) cudaStreamSynchronize(ctx->stream_comm);
   if (ctx->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl);
   for (auto& L : ctx->levels) free_level(L);
-  for (int f = 0; f < 6; f++) { cudaFree(ctx->ghost.d_send[f]); cudaFree(ctx->ghost.d_recv[f]); }
+  for (int f = 0; f < 6; f++) { cudaFree(ctx->ghost.d_send[f]); cudaFree(ctx->ghost.d_recv[f]); if (ctx->ghost.peer_arena[f]) cudaIpcCloseMemHandle(ctx->ghost.peer_arena[f]); }
+  cudaFree(ctx->ghost.arena);
   cudaFree(ctx->d_tab); cudaFree(ctx->d_P); cudaFree(ctx->d_T); cudaFree(ctx->d_Mab); cudaFree(ctx->d_in); cudaFree(ctx->d_out);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
@@ -427,6 +457,33 @@ int hpdg_host_free(hpdg_ctx* ctx, void* h_ptr) { HPDG_CUDA(cudaFreeHost(h_ptr));
 int hpdg_sync(hpdg_ctx* ctx) {
   HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
   HPDG_CUDA(cudaStreamSynchronize(ctx->stream_comm));
+  if (ctx->ghost.p2p) {
+    int err = 0;
+    HPDG_CUDA(cudaMemcpy(&err, ctx->ghost.arena + ctx->ghost.flag_off + 12 * sizeof(int), sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) { ctx->err = "halo exchange timed out waiting for a neighbour rank's face traces"; return 1; }
+  }
+  return 0;
+}
+
+int hpdg_halo_ipc_handle(hpdg_ctx* ctx, void* out64) {
+  if (!ctx->ghost.arena) { ctx->err = "not a distributed context"; return 1; }
+  cudaIpcMemHandle_t h;
+  HPDG_CUDA(cudaIpcGetMemHandle(&h, ctx->ghost.arena));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t size");
+  memcpy(out64, &h, 64);
+  return 0;
+}
+int hpdg_halo_ipc_attach(hpdg_ctx* ctx, const void* handles /* nranks x 64 bytes, indexed by rank */) {
+  if (!ctx->ghost.arena) { ctx->err = "not a distributed context"; return 1; }
+  for (int f = 0; f < 6; f++) {
+    if (!ctx->ghost.active[f]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(handles) + (size_t)ctx->ghost.peer[f] * 64, 64);
+    void* p = nullptr;
+    HPDG_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->ghost.peer_arena[f] = static_cast<char*>(p);
+  }
+  ctx->ghost.p2p = true;
   return 0;
 }
 void* hpdg_stream(hpdg_ctx* ctx) { return (void*)ctx->stream; }

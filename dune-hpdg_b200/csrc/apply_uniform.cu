@@ -42,6 +42,9 @@ struct UniParams {
   int ntile[3];
   int bmode[6];            // brick face: 1 Dirichlet, 2 natural, 3 ghost traces
   const double* ghost[6];  // [face elem][node][2] = (der, val) of the remote element at its near side
+  const int* ghost_flag[6];  // p2p halo: flag the neighbour raises to ghost_step once its traces for this step have landed
+  int ghost_step;
+  int* ghost_err;
   const double* x;
   double* y;
   int accum; // y = y_old + factor * A x
@@ -49,6 +52,7 @@ struct UniParams {
   int part;  // 0 all tiles, 1 only tiles not touching a ghost face, 2 only tiles touching one
   const int* tile_list;  // part != 0: compact list of the tile ids of that part (grid = list length)
   int tile_offset;       // first tile of this launch (z-slab launches of the chunked host-pointer apply)
+  int tile_rot;          // p2p halo: natural tile order rotated by this much, so the first wave is mid-domain tiles
 };
 
 template <int N> struct Pitch {
@@ -189,11 +193,11 @@ __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restr
     const int node = xj + N * xk;
     if (x0 == 0) {
       xpm = P.bmode[0];
-      if (xpm == 3) { const double* gp = P.ghost[0] + (((long)(y0 + xey) + (long)P.n[1] * (z0 + xez)) * N2 + node) * 2; xpd = gp[0]; xpv = gp[1]; xpm = 0; }
+      if (xpm == 3) { const double* gp = P.ghost[0] + (((long)(y0 + xey) + (long)P.n[1] * (z0 + xez)) * N2 + node) * 2; xpd = __ldcg(gp); xpv = __ldcg(gp + 1); xpm = 0; }
     } else outside_trace<N>(P, X + erow + (long)(x0 - 1) * sx + N * xj + N2 * xk, 1, 1, xpd, xpv);
     if (x0 + lenx == P.n[0]) {
       xnm = P.bmode[1];
-      if (xnm == 3) { const double* gp = P.ghost[1] + (((long)(y0 + xey) + (long)P.n[1] * (z0 + xez)) * N2 + node) * 2; xnd = gp[0]; xnv = gp[1]; xnm = 0; }
+      if (xnm == 3) { const double* gp = P.ghost[1] + (((long)(y0 + xey) + (long)P.n[1] * (z0 + xez)) * N2 + node) * 2; xnd = __ldcg(gp); xnv = __ldcg(gp + 1); xnm = 0; }
     } else outside_trace<N>(P, X + erow + (long)(x0 + lenx) * sx + N * xj + N2 * xk, 1, 0, xnd, xnv);
   }
   };
@@ -204,11 +208,11 @@ __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restr
     const int node = yi + N * yk;
     if (y0 == 0) {
       ypm = P.bmode[2];
-      if (ypm == 3) { const double* gp = P.ghost[2] + (((long)(x0 + yex) + (long)P.n[0] * (z0 + yez)) * N2 + node) * 2; ypd = gp[0]; ypv = gp[1]; ypm = 0; }
+      if (ypm == 3) { const double* gp = P.ghost[2] + (((long)(x0 + yex) + (long)P.n[0] * (z0 + yez)) * N2 + node) * 2; ypd = __ldcg(gp); ypv = __ldcg(gp + 1); ypm = 0; }
     } else outside_trace<N>(P, X + ecol + (long)(y0 - 1) * sy + yi + N2 * yk, N, 1, ypd, ypv);
     if (y0 + leny == P.n[1]) {
       ynm = P.bmode[3];
-      if (ynm == 3) { const double* gp = P.ghost[3] + (((long)(x0 + yex) + (long)P.n[0] * (z0 + yez)) * N2 + node) * 2; ynd = gp[0]; ynv = gp[1]; ynm = 0; }
+      if (ynm == 3) { const double* gp = P.ghost[3] + (((long)(x0 + yex) + (long)P.n[0] * (z0 + yez)) * N2 + node) * 2; ynd = __ldcg(gp); ynv = __ldcg(gp + 1); ynm = 0; }
     } else outside_trace<N>(P, X + ecol + (long)(y0 + leny) * sy + yi + N2 * yk, N, 0, ynd, ynv);
   }
   };
@@ -232,11 +236,11 @@ __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restr
     else {
     if (z0 == 0) {
       pm = P.bmode[4];
-      if (pm == 3) { const double* gp = P.ghost[4] + (((long)(x0 + zex) + (long)P.n[0] * (y0 + zey)) * N2 + node) * 2; pd = gp[0]; pv = gp[1]; pm = 0; }
+      if (pm == 3) { const double* gp = P.ghost[4] + (((long)(x0 + zex) + (long)P.n[0] * (y0 + zey)) * N2 + node) * 2; pd = __ldcg(gp); pv = __ldcg(gp + 1); pm = 0; }
     } else outside_trace<N>(P, X + ecol + (long)(z0 - 1) * sz + node, N2, 1, pd, pv);
     if (z0 + lenz == P.n[2]) {
       nm = P.bmode[5];
-      if (nm == 3) { const double* gp = P.ghost[5] + (((long)(x0 + zex) + (long)P.n[0] * (y0 + zey)) * N2 + node) * 2; nd = gp[0]; nv = gp[1]; nm = 0; }
+      if (nm == 3) { const double* gp = P.ghost[5] + (((long)(x0 + zex) + (long)P.n[0] * (y0 + zey)) * N2 + node) * 2; nd = __ldcg(gp); nv = __ldcg(gp + 1); nm = 0; }
     } else outside_trace<N>(P, X + ecol + (long)(z0 + lenz) * sz + node, N2, 0, nd, nv);
     }
     pencil_apply<N, TZ, 2, FULL>(P, v, lenz, pd, pv, pm, nd, nv, nm,
@@ -334,10 +338,32 @@ k_apply_uniform(const __grid_constant__ UniParams<N> P) {
   double* su = sm;
   double* sw = sm + TX * TY * TZ * EP;
   int tb = P.tile_list ? P.tile_list[blockIdx.x] : blockIdx.x + P.tile_offset;
+  if (P.tile_rot) { tb += P.tile_rot; if (tb >= (int)gridDim.x) tb -= gridDim.x; }
   const int tx = tb % P.ntile[0]; tb /= P.ntile[0];
   const int ty = tb % P.ntile[1]; const int tz = tb / P.ntile[1];
   const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;
   const int lenx = min(TX, P.n[0] - x0), leny = min(TY, P.n[1] - y0), lenz = min(TZ, P.n[2] - z0);
+  if (P.ghost_step > 0) {  // p2p halo: tiles on a rank boundary wait until the neighbour's traces for this step have arrived
+    const bool t0 = x0 == 0 && P.bmode[0] == 3, t1 = x0 + lenx == P.n[0] && P.bmode[1] == 3;
+    const bool t2 = y0 == 0 && P.bmode[2] == 3, t3 = y0 + leny == P.n[1] && P.bmode[3] == 3;
+    const bool t4 = z0 == 0 && P.bmode[4] == 3, t5 = z0 + lenz == P.n[2] && P.bmode[5] == 3;
+    if (t0 || t1 || t2 || t3 || t4 || t5) {
+      if (threadIdx.x == 0) {
+        const bool touch[6] = {t0, t1, t2, t3, t4, t5};
+        const long long tstart = clock64();
+        for (int f = 0; f < 6; f++) {
+          if (!touch[f]) continue;
+          const volatile int* fl = P.ghost_flag[f];
+          while (*fl < P.ghost_step) {
+            __nanosleep(200);
+            if (clock64() - tstart > 4000000000LL) { atomicExch(P.ghost_err, 1); break; }  // ~2 s: give up, never hang the GPU
+          }
+        }
+        __threadfence();
+      }
+      __syncthreads();
+    }
+  }
   if (lenx == TX && leny == TY && lenz == TZ) tile_body<N, TX, TY, TZ, true, EARLY>(P, su, sw, x0, y0, z0, TX, TY, TZ);
   else tile_body<N, TX, TY, TZ, false, EARLY>(P, su, sw, x0, y0, z0, lenx, leny, lenz);
 }
@@ -411,14 +437,14 @@ k_apply_uniform_pipe(const __grid_constant__ UniParams<N> P) {
     const long fe = ((long)(c.x0 + zex) + (long)P.n[0] * (c.y0 + zey)) * N2 + node;
     if (c.z0 == 0) {
       pm = P.bmode[4];
-      if (pm == 3) { zr[0][0] = P.ghost[4][fe * 2]; zr[0][1] = P.ghost[4][fe * 2 + 1]; pm = 4; }
+      if (pm == 3) { zr[0][0] = __ldcg(P.ghost[4] + fe * 2); zr[0][1] = __ldcg(P.ghost[4] + fe * 2 + 1); pm = 4; }
     } else {
 #pragma unroll
       for (int k = 0; k < N; k++) zr[0][k] = __ldg(X + ecol + (long)(c.z0 - 1) * sz + node + N2 * k);
     }
     if (c.z0 + c.lenz == P.n[2]) {
       nm = P.bmode[5];
-      if (nm == 3) { zr[1][0] = P.ghost[5][fe * 2]; zr[1][1] = P.ghost[5][fe * 2 + 1]; nm = 4; }
+      if (nm == 3) { zr[1][0] = __ldcg(P.ghost[5] + fe * 2); zr[1][1] = __ldcg(P.ghost[5] + fe * 2 + 1); nm = 4; }
     } else {
 #pragma unroll
       for (int k = 0; k < N; k++) zr[1][k] = __ldg(X + ecol + (long)(c.z0 + c.lenz) * sz + node + N2 * k);
@@ -523,8 +549,14 @@ int uniform_tile_lists(Ctx* ctx, Level& L, int TX, int TY, int TZ, const int* bm
                        (z0 == 0 && bmode[4] == 3) || (z0 + lz == L.n[2] && bmode[5] == 3);
     (touch ? lb : li).push_back(tx + nt[0] * (ty + nt[1] * tz));
   }
-  cudaFree(L.d_tiles_int); cudaFree(L.d_tiles_bnd);
-  L.d_tiles_int = L.d_tiles_bnd = nullptr;
+  cudaFree(L.d_tiles_int); cudaFree(L.d_tiles_bnd); cudaFree(L.d_tiles_all);
+  L.d_tiles_int = L.d_tiles_bnd = L.d_tiles_all = nullptr;
+  {
+    std::vector<int> all(li);
+    all.insert(all.end(), lb.begin(), lb.end());
+    HPDG_CUDA(cudaMalloc(&L.d_tiles_all, sizeof(int) * std::max<size_t>(all.size(), 1)));
+    HPDG_CUDA(cudaMemcpy(L.d_tiles_all, all.data(), sizeof(int) * all.size(), cudaMemcpyHostToDevice));
+  }
   HPDG_CUDA(cudaMalloc(&L.d_tiles_int, sizeof(int) * std::max<size_t>(li.size(), 1)));
   HPDG_CUDA(cudaMalloc(&L.d_tiles_bnd, sizeof(int) * std::max<size_t>(lb.size(), 1)));
   HPDG_CUDA(cudaMemcpy(L.d_tiles_int, li.data(), sizeof(int) * li.size(), cudaMemcpyHostToDevice));
@@ -564,16 +596,25 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
     P.ghost[f] = nullptr;
     if (ctx->bnd_is_rank[f]) {
       if (!finest) { ctx->err = "distributed apply is implemented on the finest level only"; return 1; }
-      P.bmode[f] = 3; P.ghost[f] = ctx->ghost.d_recv[f];
-    } else P.bmode[f] = ctx->dirichlet ? 1 : 2;
+      P.bmode[f] = 3;
+      if (ctx->ghost.p2p) {
+        const int par = ctx->ghost.step & 1;
+        P.ghost[f] = reinterpret_cast<const double*>(ctx->ghost.arena + ctx->ghost.recv_off[f][par]);
+        P.ghost_flag[f] = reinterpret_cast<const int*>(ctx->ghost.arena + ctx->ghost.flag_off) + f * 2 + par;
+      } else { P.ghost[f] = ctx->ghost.d_recv[f]; P.ghost_flag[f] = nullptr; }
+    } else { P.bmode[f] = ctx->dirichlet ? 1 : 2; P.ghost_flag[f] = nullptr; }
   }
+  P.ghost_step = (ctx->ghost.p2p && part == 3) ? ctx->ghost.step : 0;
+  P.ghost_err = ctx->ghost.p2p ? reinterpret_cast<int*>(ctx->ghost.arena + ctx->ghost.flag_off) + 12 : nullptr;
   P.x = x; P.y = y; P.part = part; P.dbg = ctx->variant / 100; P.accum = ctx->fuse_accum;
-  P.tile_list = nullptr; P.tile_offset = 0;
+  P.tile_list = nullptr; P.tile_offset = 0; P.tile_rot = 0;
   long nlist = 0;
-  if (part != 0) {
+  if (part == 3) {
+    P.tile_rot = (int)(((long)P.ntile[0] * P.ntile[1] * P.ntile[2]) / 2);
+  } else if (part != 0) {
     if (uniform_tile_lists(ctx, L, TX, TY, TZ, P.bmode)) return 1;
-    P.tile_list = part == 1 ? L.d_tiles_int : L.d_tiles_bnd;
-    nlist = part == 1 ? L.n_tiles_int : L.n_tiles_bnd;
+    P.tile_list = part == 1 ? L.d_tiles_int : part == 2 ? L.d_tiles_bnd : L.d_tiles_all;
+    nlist = part == 1 ? L.n_tiles_int : part == 2 ? L.n_tiles_bnd : L.n_tiles_int + L.n_tiles_bnd;
     if (nlist == 0) return 0;
   }
   if (ctx->variant % 100 >= 10 && ctx->variant % 100 < 20 && part == 0 && ctx->slab_nz == 0 && !ctx->fuse_accum) {
@@ -602,7 +643,7 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
     HPDG_CUDA(cudaFuncSetAttribute(k_apply_uniform<N, TX, TY, TZ, MINB, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  long ntiles = part != 0 ? nlist : (long)P.ntile[0] * P.ntile[1] * P.ntile[2];
+  long ntiles = (part == 1 || part == 2) ? nlist : (long)P.ntile[0] * P.ntile[1] * P.ntile[2];
   if (part == 0 && ctx->slab_nz > 0) {  // element layers [slab_z0, slab_z0 + slab_nz): must be multiples of TZ
     if (ctx->slab_z0 % TZ != 0) { ctx->err = "slab not aligned to the tile height"; return 1; }
     P.tile_offset = (ctx->slab_z0 / TZ) * P.ntile[0] * P.ntile[1];
@@ -664,7 +705,9 @@ static int pack_n(Ctx* ctx, Level& L, const double* x, cudaStream_t stream) {
   PackParams PK;
   long maxtotal = 0;
   for (int f = 0; f < 6; f++) {
-    PK.out[f] = ctx->ghost.active[f] ? ctx->ghost.d_send[f] : nullptr;
+    PK.out[f] = !ctx->ghost.active[f] ? nullptr
+              : ctx->ghost.p2p ? reinterpret_cast<double*>(ctx->ghost.peer_arena[f] + ctx->ghost.recv_off[f ^ 1][ctx->ghost.step & 1])
+                               : ctx->ghost.d_send[f];
     PK.g[f] = &dt->g[f % 2][0];
     if (ctx->ghost.active[f]) maxtotal = std::max<long>(maxtotal, (long)ctx->ghost.count[f] / 2);
   }
@@ -672,6 +715,27 @@ static int pack_n(Ctx* ctx, Level& L, const double* x, cudaStream_t stream) {
   const int threads = 256;
   dim3 grid((unsigned)std::min<long>((maxtotal + threads - 1) / threads, 2048), 6);
   k_pack_traces<N><<<grid, threads, 0, stream>>>(x, PK, L.n[0], L.n[1], L.n[2]);
+  ctx->launches++;
+  HPDG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// after the pack kernel (stream order): make its peer stores visible system-wide, then raise the neighbours' flags
+struct FlagParams { int* flag[6]; int step; };
+__global__ void k_halo_flags(FlagParams F) {
+  const int f = threadIdx.x;
+  if (f < 6 && F.flag[f]) {
+    __threadfence_system();
+    *reinterpret_cast<volatile int*>(F.flag[f]) = F.step;
+    __threadfence_system();
+  }
+}
+int launch_halo_flags(Ctx* ctx, cudaStream_t stream) {
+  FlagParams F;
+  F.step = ctx->ghost.step;
+  for (int f = 0; f < 6; f++)
+    F.flag[f] = ctx->ghost.active[f] ? reinterpret_cast<int*>(ctx->ghost.peer_arena[f] + ctx->ghost.flag_off) + (f ^ 1) * 2 + (ctx->ghost.step & 1) : nullptr;
+  k_halo_flags<<<1, 32, 0, stream>>>(F);
   ctx->launches++;
   HPDG_CUDA(cudaGetLastError());
   return 0;

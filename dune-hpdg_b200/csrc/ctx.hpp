@@ -22,6 +22,15 @@ struct Ghost {
   double* d_send[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t count[6] = {0, 0, 0, 0, 0, 0};  // doubles per face buffer
   int peer[6] = {-1, -1, -1, -1, -1, -1};
+  // peer-to-peer mode: the pack kernel stores the traces straight into the neighbour's arena over NVLink and
+  // publishes a per-face step flag; the tile kernel's rank-boundary tiles wait on the local flags.
+  bool p2p = false;
+  char* arena = nullptr;            // local: recv[f][parity] buffers, then int flags[6][2], then int err
+  size_t arena_bytes = 0;
+  size_t recv_off[6][2] = {};       // byte offsets into the arena (identical on every rank: same brick shape)
+  size_t flag_off = 0;
+  char* peer_arena[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int step = 0;
 };
 
 struct JacobiDense {
@@ -70,7 +79,7 @@ struct Level {
   JacobiFD jf;
   Bcrs bcrs;
   // compact tile lists (interior / rank-boundary tiles) of the distributed apply, per tile shape
-  int *d_tiles_int = nullptr, *d_tiles_bnd = nullptr;
+  int *d_tiles_int = nullptr, *d_tiles_bnd = nullptr, *d_tiles_all = nullptr;  // all = interior first, boundary last
   long n_tiles_int = 0, n_tiles_bnd = 0, tile_key = -1;
   // scratch vectors for the V-cycle (device, ndof each)
   double *mg_x = nullptr, *mg_r = nullptr, *mg_t1 = nullptr, *mg_t2 = nullptr;
@@ -130,6 +139,7 @@ int uniform_tile_height(const Level& L);
 int uniform_tile_lists(Ctx* ctx, Level& L, int TX, int TY, int TZ, const int* bmode);
 int launch_apply_uniform3(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream);
 int launch_pack_traces(Ctx* ctx, Level& L, const double* x, cudaStream_t stream);
+int launch_halo_flags(Ctx* ctx, cudaStream_t stream);
 
 int jacobi_setup_dense(Ctx* ctx, Level& L);
 int jacobi_apply_dense(Ctx* ctx, Level& L, const double* r, double* c, double damping);

@@ -31,6 +31,8 @@ SIGNATURES = {
     "hpdg_create_distributed": (C.c_int, [C.POINTER(_vp), C.c_int, _ip, _dp, C.c_int, C.c_double, C.c_int, C.c_int,
                                           _ip, C.c_int, C.c_int, C.c_void_p]),
     "hpdg_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "hpdg_halo_ipc_handle": (C.c_int, [_vp, C.c_void_p]),
+    "hpdg_halo_ipc_attach": (C.c_int, [_vp, C.c_void_p]),
     "hpdg_destroy": (None, [_vp]),
     "hpdg_last_error": (C.c_char_p, [_vp]),
     "hpdg_set_option": (C.c_int, [_vp, C.c_char_p, C.c_long]),
@@ -126,6 +128,15 @@ class Context:
             self._h = None
             raise HpdgError(msg)
         self.n = n
+
+    def halo_ipc_handle(self):
+        buf = C.create_string_buffer(64)
+        self._ck(lib().hpdg_halo_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def halo_ipc_attach(self, handles_by_rank):
+        blob = b"".join(handles_by_rank)
+        self._ck(lib().hpdg_halo_ipc_attach(self._h, C.c_char_p(blob)))
 
     def _ck(self, rc):
         if rc:

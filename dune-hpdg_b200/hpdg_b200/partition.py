@@ -74,3 +74,16 @@ def face_traces(x_local, n, p, f, g_end):
         der = np.einsum("yxkji,k->yxji", blk, g_end[s])
         val = blk[:, :, N - 1 if s else 0]
     return np.ascontiguousarray(np.stack([der, val], axis=-1).reshape(-1))
+
+
+def enable_p2p_halo(ctx, dist, torch, world):
+    """all-gather the ranks' halo-arena IPC handles and attach (NVLink peer-memory halo); HPDG_HALO=nccl keeps NCCL send/recv"""
+    import os
+    if os.environ.get("HPDG_HALO", "p2p") != "p2p" or world == 1:
+        return False
+    mine = torch.tensor(list(ctx.halo_ipc_handle()), dtype=torch.uint8, device="cuda")
+    allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    dist.all_gather(allh, mine)
+    ctx.halo_ipc_attach([bytes(t.cpu().tolist()) for t in allh])
+    dist.barrier()
+    return True

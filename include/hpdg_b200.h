@@ -46,6 +46,12 @@ int hpdg_create_distributed(hpdg_ctx** out, int dim, const int* n, const double*
                             int dirichlet, int device, const int* pgrid, int rank, int nranks,
                             const void* nccl_id);
 int hpdg_nccl_unique_id(void* out128);
+/* Optional NVLink peer-memory halo (one process per GPU, same node): every rank exports the 64-byte cudaIpcMemHandle_t of its
+ * halo arena, the caller all-gathers them (indexed by rank) and every rank attaches.  After that the operator apply stores the
+ * face traces straight into the neighbours' memory from the pack kernel and the tile kernel waits on per-face step flags: no
+ * NCCL call in the apply loop.  NCCL stays in use for the dot-product all-reduce. */
+int hpdg_halo_ipc_handle(hpdg_ctx* ctx, void* out64);
+int hpdg_halo_ipc_attach(hpdg_ctx* ctx, const void* handles_by_rank);
 void hpdg_destroy(hpdg_ctx* ctx);
 const char* hpdg_last_error(const hpdg_ctx* ctx); /* ctx may be NULL after a failed create */
 int hpdg_set_option(hpdg_ctx* ctx, const char* name, long value); /* "force_generic" */

@@ -36,9 +36,19 @@ for p, n in [(3, (8, 8, 8)), (3, (6, 5, 7)), (4, (4, 6, 4)), (1, (8, 4, 4)), (2,
     rl = part.scatter_global_vector(ref, rank, pgrid, n, ne)
     ctx = hp.Context(n, L=[1.0, 1.0, 1.0], degree=p, sigma=2.0, dirichlet=True, device=lr, pgrid=pgrid, rank=rank,
                      nranks=world, nccl_id=bytes(idt.cpu().tolist()))
+    p2p = part.enable_p2p_halo(ctx, dist, torch, world)
     dx, dy = ctx.upload(xl), ctx.vec_alloc()
-    hp.Operator(ctx).apply_device(dx, dy)
+    op = hp.Operator(ctx)
+    op.apply_device(dx, dy)
     y = ctx.download(dy)
+    # repeated applies exercise the double-buffered halo arena / step flags: y2 = A (A x) against the oracle
+    op.apply_device(dy, dx)
+    op.apply_device(dy, dx)
+    ctx.sync()
+    y2 = ctx.download(dx)
+    ref2 = part.scatter_global_vector(m.apply_mf(ref, threads=orc.max_threads()), rank, pgrid, n, ne)
+    err2 = np.linalg.norm(y2 - ref2) / np.linalg.norm(ref2)
+    ctx.upload(xl, dx)
     err = np.linalg.norm(y - rl) / np.linalg.norm(rl)
     # distributed dot product (Krylov allreduce)
     dd = ctx.dot_device(dx, dx)
@@ -48,9 +58,9 @@ for p, n in [(3, (8, 8, 8)), (3, (6, 5, 7)), (4, (4, 6, 4)), (1, (8, 4, 4)), (2,
     jac = hp.BlockJacobi(ctx, form=hp.JACOBI_FD, damping=0.75)
     jac.apply_device(dx, dy)
     jerr = np.linalg.norm(ctx.download(dy) - jref) / np.linalg.norm(jref)
-    good = err < 1e-12 and derr < 1e-12 and jerr < 1e-11
+    good = err < 1e-12 and err2 < 1e-12 and derr < 1e-12 and jerr < 1e-11
     ok &= good
-    print(f"rank {rank}/{world} p={p} brick={n}: apply {err:.2e} dot {derr:.2e} jacobi {jerr:.2e} {'OK' if good else 'FAIL'}", flush=True)
+    print(f"rank {rank}/{world} p={p} brick={n}: halo={'p2p' if p2p else 'nccl'} apply {err:.2e} twice {err2:.2e} dot {derr:.2e} jacobi {jerr:.2e} {'OK' if good else 'FAIL'}", flush=True)
     ctx.close()
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
