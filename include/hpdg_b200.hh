@@ -135,6 +135,40 @@ class BlockJacobiStep {
   bool ready_ = false;
 };
 
+// DynamicBCRSMatrix-layout matrix assembled on the device (buildingblocks/matrices.hh:29-89, common/dynamicbcrs.hh:178-199).
+// blockRowPtr/blockCol/blockOff/entries are exactly the arrays a DynamicBCRSMatrix holds; mv() is BCRSMatrix::mv.
+class AssembledMatrix {
+ public:
+  explicit AssembledMatrix(std::shared_ptr<Context> c, int level = HPDG_FINEST) : c_(std::move(c)), level_(level) {
+    long nb = 0, ne = 0;
+    c_->check(hpdg_bcrs_sizes(c_->handle(), level_, &nb, &ne));
+    blockRowPtr.resize(hpdg_num_elements(c_->handle()) + 1); blockCol.resize(nb); blockOff.resize(nb + 1); entries.resize(ne);
+    c_->check(hpdg_assemble_bcrs(c_->handle(), level_, blockRowPtr.data(), blockCol.data(), blockOff.data(), entries.data()));
+  }
+  template <class V> void mv(const V& x, V& y) const { c_->check(hpdg_bcrs_mv(c_->handle(), level_, x.data(), y.data())); }
+  std::vector<long> blockRowPtr, blockOff;
+  std::vector<int> blockCol;
+  std::vector<double> entries;
+  std::shared_ptr<Context> context() const { return c_; }
+  int level() const { return level_; }
+
+ private:
+  std::shared_ptr<Context> c_;
+  int level_;
+};
+
+// Dune::HPDG::DynamicBlockGS<Matrix, Vector> (iterationsteps/dynamicblockgs.hh:87-127): setProblem(mat, x, rhs); iterate()
+template <class V>
+class DynamicBlockGS {
+ public:
+  void setProblem(const AssembledMatrix& m, V& x, const V& rhs) { mat_ = &m; x_ = &x; rhs_ = &rhs; }
+  void preprocess() {}
+  void iterate() { mat_->context()->check(hpdg_blockgs_iterate(mat_->context()->handle(), mat_->level(), rhs_->data(), x_->data())); }
+  const AssembledMatrix* mat_ = nullptr;
+  V* x_ = nullptr;
+  const V* rhs_ = nullptr;
+};
+
 template <class V> using Fn = std::function<void(V&, const V&)>;
 
 template <class V>

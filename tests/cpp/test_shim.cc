@@ -77,6 +77,19 @@ int main() {
       Pm(xf, xc); R(yc, yf);
       CHECK(std::fabs(xf * yf - xc * yc) < 1e-10 * std::fabs(xf * yf), "restrict is the transpose of prolong");
     }
+    {  // (4) test/test_dynamicblockgs.cc:24-44: 2x2, k=2, penalty 1.5 k^dim (sigma 1.5), b = 1, x0 = 1, 100 sweeps
+      int n[2] = {2, 2}; double L[2] = {1, 1};
+      auto ctx = std::make_shared<hpdg::Context>(2, n, L, 2, 1.5, true);
+      hpdg::AssembledMatrix A(ctx);
+      V b = ctx->makeVector(), x = ctx->makeVector(), Ax = ctx->makeVector();
+      b = 1.0; x = 1.0;
+      hpdg::DynamicBlockGS<V> gs;
+      gs.setProblem(A, x, b);
+      for (int it = 0; it < 100; it++) gs.iterate();
+      A.mv(x, Ax); Ax -= b;
+      CHECK(std::sqrt(Ax * Ax) < 1e-13, "100 DynamicBlockGS sweeps solve the small system (|b - Ax| < 1e-13)");
+      CHECK(A.blockCol.size() == 12 && A.entries.size() == 12u * 81u, "DynamicBCRSMatrix pattern: 4 rows x (self + 2 neighbours), 9x9 blocks");
+    }
     {  // error behaviour: exceptions, not aborts
       bool threw = false;
       try { int n[1] = {4}; double L[1] = {1}; hpdg::Context bad(1, n, L, 1); } catch (const hpdg::Exception&) { threw = true; }
