@@ -1,0 +1,55 @@
+"""Generates tests/golden/oracle_golden.npz from the CPU oracle (oracle/hpdg_oracle.c).
+
+The reference itself cannot be built in this image and ships no golden vectors, so these fixtures freeze the
+ORACLE's outputs (which are pinned by the reference's differential tests, tests/test_oracle_pins.py) on small seeded cases:
+they guard the oracle against regressions (CPU test) and give the CUDA path a fixed target that travels to the GPU box
+(GPU test).  Inputs follow the reference's fixtures: x = interp(|x|^2) (matrix-free/test/testdg.cc:97) or
+mt19937(1887) + normal_distribution (test/randomvector.hh:11-21).  Run:  python tests/golden/gen_oracle_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import orc
+
+out = {}
+# cfg1: 2-D 16x16 Q2, sigma 2, Dirichlet: apply on |x|^2, then 10 block-GS sweeps with b = 1, x0 = 1
+m = orc.Mesh((16, 16), degree=2, sigma=2.0, dirichlet=True)
+A = m.assemble()
+x = m.interpolate_normsq()
+out["cfg1_x"] = x
+out["cfg1_Ax"] = m.apply_mf(x)
+b, xg = np.ones(m.ndof), np.ones(m.ndof)
+for _ in range(10):
+    A.blockgs_iterate(b, xg)
+out["cfg1_gs10"] = xg
+# 3-D uniform Q3 on a ragged anisotropic brick, both boundary types
+for tag, dirichlet in (("d", True), ("n", False)):
+    m = orc.Mesh((5, 6, 3), L=[1.0, 1.5, 0.5], degree=3, sigma=2.0, dirichlet=dirichlet)
+    x = orc.fill_random(m.ndof)
+    out[f"q3_{tag}_Ax"] = m.apply_mf(x)
+    out[f"q3_{tag}_jac"] = m.blockjacobi_apply(x, factor=0.75)
+# 3-D hp, degrees 1..6 from numpy's default_rng(1887)
+rng = np.random.default_rng(1887)
+deg = rng.integers(1, 7, 4 * 3 * 5).astype(np.int32)
+m = orc.Mesh((4, 3, 5), degree=deg, sigma=2.0, dirichlet=True)
+x = orc.fill_random(m.ndof)
+out["hp_deg"] = deg
+out["hp_Ax"] = m.apply_mf(x)
+out["hp_jac"] = m.blockjacobi_apply(x, factor=1.0)
+# p-multigrid pieces on 4^3 Q4: restrict / prolong / one V-cycle with damped exact block Jacobi
+fine = orc.Mesh((4, 4, 4), degree=4)
+l1 = fine.coarsen(2)
+l0 = l1.coarsen(1)
+xf = orc.fill_random(fine.ndof)
+out["mg_restrict"] = fine.restrict(l1, xf)
+out["mg_prolong"] = fine.prolong(l1, out["mg_restrict"])
+bvec = orc.fill_random(fine.ndof, seed=5)
+xv, rv = orc.vcycle([l0, l1, fine], None, np.zeros(fine.ndof), bvec, smoother=1, damping=0.75)
+out["mg_vcycle_x"] = xv
+out["mg_vcycle_r"] = rv
+np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_golden.npz"), **out)
+print({k: v.shape for k, v in out.items()})
