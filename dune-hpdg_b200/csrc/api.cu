@@ -215,6 +215,22 @@ struct VC { int form; double damping; int pre, post, coarse_its; };
 
 int mg_smooth(Ctx* ctx, int l, const VC& v, int steps, double* x, double* r) {
   Level& L = ctx->levels[l];
+  if (v.form == HPDG_SMOOTHER_BLOCKGS) {
+    // the reference's default: smootherFromIterationStep2 around DynamicBlockGS on the level's assembled (Galerkin) matrix
+    // (solversetup.hh:139-145, multigrid.hh:96-107).  tmp1 is zeroed once per applySmoother (multigrid_impl.hh:73) and NOT between
+    // steps: iterate() continues from the previous tmp1, exactly as the reference does.
+    HPDG_CUDA(cudaMemsetAsync(L.mg_t1, 0, sizeof(double) * L.ndof, ctx->stream));
+    for (int i = 0; i < steps; i++) {
+      if (blockgs_iterate(ctx, L, r, L.mg_t1)) return 1;
+      if (v.damping != 1.0) { if (launch_axpy(ctx, L.ndof, v.damping - 1.0, L.mg_t1, L.mg_t1)) return 1; }
+      if (launch_axpy(ctx, L.ndof, 1.0, L.mg_t1, x)) return 1;
+      ctx->fuse_accum = 1;
+      const int rc = op_apply_async(ctx, L, L.mg_t1, r, -1.0);
+      ctx->fuse_accum = 0;
+      if (rc) return 1;
+    }
+    return 0;
+  }
   for (int i = 0; i < steps; i++) {                                   // multigrid_impl.hh:76-81
     // smoother(tmp1, r); x += tmp1 -- fused into the Jacobi kernel (one pass instead of a kernel + an axpy)
     ctx->fuse_xacc = x;
@@ -233,6 +249,10 @@ int mg_smooth(Ctx* ctx, int l, const VC& v, int steps, double* x, double* r) {
 int mg_level(Ctx* ctx, int l, const VC& v) {
   Level& L = ctx->levels[l];
   double* x = L.mg_x; double* r = L.mg_r;
+  if (l == 0 && v.form == HPDG_SMOOTHER_BLOCKGS) {  // coarse solver of the reference: coarse_its block-GS iterations (solversetup.hh:198-215)
+    for (int i = 0; i < v.coarse_its; i++) if (blockgs_iterate(ctx, L, r, x)) return 1;
+    return 0;
+  }
   if (l == 0) {  // coarse solver: coarse_its damped block-Jacobi iterations from x = 0 (cf. solversetup.hh:198-215)
     for (int i = 0; i < v.coarse_its; i++) {
       if (op_apply_async(ctx, L, x, L.mg_t1, 1.0)) return 1;
@@ -267,7 +287,8 @@ int vcycle_device(Ctx* ctx, const VC& v, double* d_x, double* d_b) {
       HPDG_CUDA(cudaMalloc(&L.mg_t1, sizeof(double) * L.ndof));
       HPDG_CUDA(cudaMalloc(&L.mg_t2, sizeof(double) * L.ndof));
     }
-    if (v.form == HPDG_JACOBI_DENSE ? !L.jd.ready : !L.jf.ready) {
+    if (v.form == HPDG_SMOOTHER_BLOCKGS) { if (bcrs_build(ctx, L)) return 1; }
+    else if (v.form == HPDG_JACOBI_DENSE ? !L.jd.ready : !L.jf.ready) {
       if (v.form == HPDG_JACOBI_DENSE ? jacobi_setup_dense(ctx, L) : jacobi_setup_fd(ctx, L)) return 1;
     }
   }

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libhpdg_b200.so")
 FINEST = -1
 JACOBI_DENSE = 0
 JACOBI_FD = 1
+SMOOTHER_BLOCKGS = 2
 
 _lib = None
 _vp = C.c_void_p

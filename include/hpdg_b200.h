@@ -28,6 +28,7 @@ typedef struct hpdg_ctx hpdg_ctx;
 #define HPDG_FINEST (-1)          /* level argument: finest level */
 #define HPDG_JACOBI_DENSE 0       /* precomputed dense per-element inverses, batched by block size */
 #define HPDG_JACOBI_FD 1          /* same inverse in Kronecker (fast diagonalisation) form */
+#define HPDG_SMOOTHER_BLOCKGS 2    /* hpdg_vcycle only: the reference's DynamicBlockGS on assembled level matrices */
 
 /* -- problem description -------------------------------------------------------------------------
  * Replaces: DynamicDGQkGLBlockBasis(gridView, k | degree map) (functionspacebases/dynamicdgqkglbasis.hh:54-69),
@@ -122,8 +123,9 @@ int hpdg_restrict_device(hpdg_ctx* ctx, int fine_level, const double* d_fine, do
 int hpdg_prolong_device(hpdg_ctx* ctx, int fine_level, const double* d_coarse, double* d_fine);
 
 /* -- one multigrid cycle: Multigrid<Vector>::apply(x, b) (iterationsteps/mg/multigrid_impl.hh:16-117) with the
- * block-Jacobi smoother on every level and `coarse_its` damped Jacobi iterations as coarse solver
- * (the reference default is 5 block-GS iterations, solversetup.hh:198-215).  On return x += correction and
+ * block-Jacobi smoother on every level and `coarse_its` damped Jacobi iterations as coarse solver, or -- with form =
+ * HPDG_SMOOTHER_BLOCKGS -- the reference's own configuration: DynamicBlockGS on the assembled Galerkin level matrices as
+ * smoother and `coarse_its` block-GS iterations as coarse solver (solversetup.hh:139-145,198-215; small/medium meshes).  On return x += correction and
  * b holds the residual (multigrid_impl.hh:60-61). */
 int hpdg_vcycle(hpdg_ctx* ctx, int form, double damping, int pre, int post, int coarse_its, double* h_x, double* h_b);
 int hpdg_vcycle_device(hpdg_ctx* ctx, int form, double damping, int pre, int post, int coarse_its, double* d_x,

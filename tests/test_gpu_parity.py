@@ -286,3 +286,24 @@ def test_dynamicblockgs_small_system_on_device(orc, hp):
     for _ in range(100):
         gs.iterate()
     assert np.linalg.norm(b - G.mv(x)) < 1e-13
+
+
+def test_vcycle_with_reference_default_smoother(orc, hp):
+    # the reference's own p-MG configuration (solversetup.hh:139-145,198-215): DynamicBlockGS on the Galerkin level matrices
+    n = (3, 3, 3)
+    fine = orc.Mesh(n, degree=4)
+    l1 = fine.coarsen(2)
+    l0 = l1.coarsen(1)
+    Af = fine.assemble()
+    A1 = fine.galerkin_restrict(l1, Af)
+    A0 = l1.galerkin_restrict(l0, A1)
+    b = orc.fill_random(fine.ndof)
+    x0 = orc.fill_random(fine.ndof, seed=3) * 0.1
+    xr, rr = orc.vcycle([l0, l1, fine], [A0, A1, Af], x0, b, smoother=0, damping=1.0)
+    ctx = hp.Context(n, degree=4)
+    ctx.build_p_hierarchy()
+    x, bb = x0.copy(), b.copy()
+    hp.Multigrid(ctx, form=hp.SMOOTHER_BLOCKGS, damping=1.0).apply(x, bb)
+    assert rel(x, xr) < 1e-11 and rel(bb, rr) < 1e-10
+    # and it contracts much faster than damped block Jacobi
+    assert np.linalg.norm(bb) < 0.2 * np.linalg.norm(b - Af.mv(x0))
