@@ -411,6 +411,10 @@ const char* hpdg_last_error(const hpdg_ctx* ctx) { return ctx ? ctx->err.c_str()
 int hpdg_set_option(hpdg_ctx* ctx, const char* name, long value) {
   if (!strcmp(name, "force_generic")) { ctx->force_generic = (int)value; return 0; }
   if (!strcmp(name, "variant")) { ctx->variant = (int)value; return 0; }
+  if (!strcmp(name, "halo_p2p")) {  // switch between the NVLink peer-memory halo and NCCL send/recv (attach must have succeeded for 1)
+    if (value && !ctx->ghost.peer_attached) { ctx->err = "halo_p2p: hpdg_halo_ipc_attach has not succeeded on this context"; return 1; }
+    ctx->ghost.p2p = value != 0; return 0;
+  }
   ctx->err = std::string("unknown option ") + name; return 1;
 }
 
@@ -504,6 +508,7 @@ int hpdg_halo_ipc_attach(hpdg_ctx* ctx, const void* handles /* nranks x 64 bytes
     HPDG_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     ctx->ghost.peer_arena[f] = static_cast<char*>(p);
   }
+  ctx->ghost.peer_attached = true;
   ctx->ghost.p2p = true;
   return 0;
 }

@@ -25,6 +25,7 @@ struct Ghost {
   // peer-to-peer mode: the pack kernel stores the traces straight into the neighbour's arena over NVLink and
   // publishes a per-face step flag; the tile kernel's rank-boundary tiles wait on the local flags.
   bool p2p = false;
+  bool peer_attached = false;
   char* arena = nullptr;            // local: recv[f][parity] buffers, then int flags[6][2], then int err
   size_t arena_bytes = 0;
   size_t recv_off[6][2] = {};       // byte offsets into the arena (identical on every rank: same brick shape)

@@ -55,7 +55,7 @@ int hpdg_halo_ipc_handle(hpdg_ctx* ctx, void* out64);
 int hpdg_halo_ipc_attach(hpdg_ctx* ctx, const void* handles_by_rank);
 void hpdg_destroy(hpdg_ctx* ctx);
 const char* hpdg_last_error(const hpdg_ctx* ctx); /* ctx may be NULL after a failed create */
-int hpdg_set_option(hpdg_ctx* ctx, const char* name, long value); /* "force_generic" */
+int hpdg_set_option(hpdg_ctx* ctx, const char* name, long value); /* "force_generic", "halo_p2p", "variant" (tuning) */
 
 /* -- sizes (DynamicBlockVector::dimension(), blockRows(i): dynamicbvector.hh:134-143,282) ---------- */
 int hpdg_num_levels(const hpdg_ctx* ctx);
