@@ -173,12 +173,10 @@ int op_apply_distributed(Ctx* ctx, Level& L, const double* d_x, double* d_y, dou
     HPDG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
     return 0;
   }
-  static const int dbg = getenv("HPDG_DEBUG_HALO") ? atoi(getenv("HPDG_DEBUG_HALO")) : 0;  // timing experiments only
   HPDG_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));                    // x is ready
   HPDG_CUDA(cudaStreamWaitEvent(ctx->stream_comm, ctx->ev_a, 0));
-  if (!(dbg & 2)) if (launch_pack_traces(ctx, L, d_x, ctx->stream_comm)) return 1;
+  if (launch_pack_traces(ctx, L, d_x, ctx->stream_comm)) return 1;
   ncclComm_t comm = (ncclComm_t)ctx->nccl;
-  if (!(dbg & 1)) {
   HPDG_NCCL(g_nccl.GroupStart());
   for (int f = 0; f < 6; f++) {
     if (!ctx->ghost.active[f]) continue;
@@ -186,7 +184,6 @@ int op_apply_distributed(Ctx* ctx, Level& L, const double* d_x, double* d_y, dou
     HPDG_NCCL(g_nccl.Recv(ctx->ghost.d_recv[f], ctx->ghost.count[f], ncclDouble, ctx->ghost.peer[f], comm, ctx->stream_comm));
   }
   HPDG_NCCL(g_nccl.GroupEnd());
-  }
   if (launch_apply_uniform(ctx, L, d_x, d_y, factor, 2, ctx->stream_comm)) return 1;   // rank-boundary tiles
   HPDG_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream_comm));
   if (launch_apply_uniform(ctx, L, d_x, d_y, factor, 1, ctx->stream)) return 1;        // interior tiles, overlaps the exchange

@@ -48,7 +48,6 @@ struct UniParams {
   const double* x;
   double* y;
   int accum; // y = y_old + factor * A x
-  int dbg;   // timing experiments only: 1 = skip outside-trace loads (wrong results)
   int part;  // 0 all tiles, 1 only tiles not touching a ghost face, 2 only tiles touching one
   const int* tile_list;  // part != 0: compact list of the tile ids of that part (grid = list length)
   int tile_offset;       // first tile of this launch (z-slab launches of the chunked host-pointer apply)
@@ -132,7 +131,6 @@ __device__ __forceinline__ void mass_line(const UniParams<N>& P, double (&a)[N])
 template <int N>
 __device__ __forceinline__ void outside_trace(const UniParams<N>& P, const double* __restrict__ line, long stride,
                                               int side /* near side of that element */, double& der, double& val) {
-  if (P.dbg & 1) { der = 0; val = 0; return; }
   if (N == 4 && stride == 1) {  // an x line is 32 contiguous, 32-byte aligned bytes: two 128-bit loads
     const double2 lo = __ldg(reinterpret_cast<const double2*>(line));
     const double2 hi = __ldg(reinterpret_cast<const double2*>(line) + 1);
@@ -255,7 +253,7 @@ __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restr
 
   // ---------------- P2: x-pencils ----------------
   if (!EARLY) { load_xtr(); load_ytr(); }
-  if (xact && !(P.dbg & 2)) {
+  if (xact) {
     double v[TX][N];
     const int xbase = TX * (xey + TY * xez) * EP + N * xj + PP * xk;
 #pragma unroll
@@ -272,7 +270,7 @@ __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restr
   __syncthreads();
 
   // ---------------- P3: y-pencils, then M_y ----------------
-  if (yact && !(P.dbg & 4)) {
+  if (yact) {
     double v[TY][N];
     const int ybase = (yex + TX * TY * yez) * EP + yi + PP * yk;
 #pragma unroll
@@ -294,7 +292,7 @@ __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restr
   hook();
 
   // ---------------- P4: M_x ----------------
-  if (xact && !(P.dbg & 8)) {
+  if (xact) {
 #pragma unroll
     for (int e = 0; e < TX; e++)
       if (FULL || e < lenx) {
@@ -606,7 +604,7 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
   }
   P.ghost_step = (ctx->ghost.p2p && part == 3) ? ctx->ghost.step : 0;
   P.ghost_err = ctx->ghost.p2p ? reinterpret_cast<int*>(ctx->ghost.arena + ctx->ghost.flag_off) + 12 : nullptr;
-  P.x = x; P.y = y; P.part = part; P.dbg = ctx->variant / 100; P.accum = ctx->fuse_accum;
+  P.x = x; P.y = y; P.part = part; P.accum = ctx->fuse_accum;
   P.tile_list = nullptr; P.tile_offset = 0; P.tile_rot = 0;
   long nlist = 0;
   if (part == 3) {
@@ -617,7 +615,7 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
     nlist = part == 1 ? L.n_tiles_int : part == 2 ? L.n_tiles_bnd : L.n_tiles_int + L.n_tiles_bnd;
     if (nlist == 0) return 0;
   }
-  if (ctx->variant % 100 >= 10 && ctx->variant % 100 < 20 && part == 0 && ctx->slab_nz == 0 && !ctx->fuse_accum) {
+  if (ctx->variant >= 10 && ctx->variant < 20 && part == 0 && ctx->slab_nz == 0 && !ctx->fuse_accum) {
     constexpr int threads = uni_threads<N, TX, TY, TZ>();
     constexpr size_t smem = sizeof(double) * 3 * TX * TY * TZ * Pitch<N>::EP;
     static bool attr_set_pipe = false;
@@ -671,7 +669,7 @@ int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double 
     case 1: return launch_uni<2, 4, 4, 4, 4>(ctx, L, x, y, factor, part, stream);
     case 2: return launch_uni<3, 4, 4, 4, 3>(ctx, L, x, y, factor, part, stream);
     case 3:
-      switch (ctx->variant % 100) {
+      switch (ctx->variant) {
         case 1: return launch_uni<4, 4, 4, 4, 2, true>(ctx, L, x, y, factor, part, stream);
         case 3: return launch_uni<4, 4, 4, 4, 2, false>(ctx, L, x, y, factor, part, stream);
         case 4: return launch_uni<4, 4, 4, 2, 4, false>(ctx, L, x, y, factor, part, stream);
@@ -684,7 +682,7 @@ int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double 
         default: return launch_uni<4, 4, 4, 4, 3, false>(ctx, L, x, y, factor, part, stream);
       }
     case 4:
-      switch (ctx->variant % 100) {
+      switch (ctx->variant) {
         case 1: return launch_uni<5, 4, 4, 2, 1, false>(ctx, L, x, y, factor, part, stream);
         case 2: return launch_uni<5, 4, 4, 2, 2, false>(ctx, L, x, y, factor, part, stream);
         case 3: return launch_uni<5, 4, 2, 2, 2, false>(ctx, L, x, y, factor, part, stream);

@@ -23,8 +23,6 @@
 
 namespace hpdg {
 
-constexpr int N3K = 4;  // this file is specialised for N = 4
-
 struct Uni3Params {
   double Dp[3][16];      // kappa_d S + own face terms (interior faces on both sides); [2] pre-scaled by factor
   double B0[3][4], B1[3][4];
@@ -349,7 +347,7 @@ int launch_apply_uniform3(Ctx* ctx, Level& L, const double* x, double* y, double
   }
   if (!stream) stream = ctx->stream;
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) { ctx->err = "device vectors must be 16-byte aligned"; return 1; }
-  if (ctx->variant % 100 == 22) k_apply_uniform3<2><<<(unsigned)ntiles, 256, smem, stream>>>(P);
+  if (ctx->variant == 22) k_apply_uniform3<2><<<(unsigned)ntiles, 256, smem, stream>>>(P);
   else k_apply_uniform3<3><<<(unsigned)ntiles, 256, smem, stream>>>(P);
   ctx->launches++;
   HPDG_CUDA(cudaGetLastError());

@@ -105,12 +105,9 @@ struct Ctx {
   bool bnd_is_rank[6] = {false, false, false, false, false, false};
   Ghost ghost;           // finest level only
   void* nccl = nullptr;  // ncclComm_t
-  void* nccl_lib = nullptr;
-  // pinned staging for the host-pointer entry points
+  // device staging for the host-pointer entry points
   double *d_in = nullptr, *d_out = nullptr;
   size_t stage_cap = 0;
-  double *h_pin_in = nullptr, *h_pin_out = nullptr;
-  size_t pin_cap = 0;
   int force_generic = 0;
   int variant = 0;  // kernel variant selector for tuning experiments
   int slab_z0 = 0, slab_nz = 0;  // restrict the next uniform launch to element layers [z0, z0+nz) (chunked host apply)

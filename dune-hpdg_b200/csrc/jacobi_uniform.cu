@@ -230,7 +230,7 @@ int jacobi_apply_fd_uniform(Ctx* ctx, Level& L, const double* r, double* c, doub
     case 2: return launch_fdu<3, 4, 4, 4, 4>(ctx, L, r, c, damping);
     case 3: return launch_fdu<4, 4, 4, 4, 4>(ctx, L, r, c, damping);
     case 4:
-      switch (ctx->variant % 100) {
+      switch (ctx->variant) {
         case 1: return launch_fdu<5, 3, 3, 3, 3>(ctx, L, r, c, damping);
         case 2: return launch_fdu<5, 2, 2, 2, 4>(ctx, L, r, c, damping);
         case 3: return launch_fdu<5, 4, 4, 2, 3>(ctx, L, r, c, damping);
