@@ -101,6 +101,7 @@ void free_level(Level& L) {
   cudaFree(L.d_tiles_int); cudaFree(L.d_tiles_bnd);
   cudaFree(L.bcrs.d_rowptr); cudaFree(L.bcrs.d_col); cudaFree(L.bcrs.d_brow); cudaFree(L.bcrs.d_boff); cudaFree(L.bcrs.d_val);
   cudaFree(L.bcrs.d_wave); cudaFree(L.bcrs.d_res);
+  for (int f = 0; f < 6; f++) { cudaFree(L.cg.d_send[f]); cudaFree(L.cg.d_recv[f]); }
 }
 
 int create_common(Ctx* ctx, int dim, const int* n, const double* Lx, const std::vector<int>& deg, double sigma,
@@ -158,7 +159,11 @@ int ensure_stage(Ctx* ctx, size_t ndof) {
 // <= 6 face neighbours (the copyFromMaster analogue, parallel/communicationhpdg.hh:411-418) -> rank-boundary tiles.
 // The two streams write disjoint tiles of y; the compute stream joins the halo stream at the end.
 int op_apply_distributed(Ctx* ctx, Level& L, const double* d_x, double* d_y, double factor) {
-  if (ctx->ghost.p2p) {
+  const bool finest = (&L == &ctx->levels.back());
+  Ghost* Gp = nullptr;
+  if (level_ghost(ctx, L, &Gp)) return 1;
+  Ghost& G = *Gp;
+  if (finest && ctx->ghost.p2p) {
     // NVLink peer-memory halo, no NCCL call in the loop.  Halo stream (highest priority): pack kernel storing this rank's face
     // traces straight into the neighbours' arenas -> flag kernel.  Compute stream, concurrently: ONE tile kernel over all tiles,
     // interior tiles first; its rank-boundary tiles wait on the flags the NEIGHBOURS raise (the local pack is not a dependency
@@ -179,9 +184,9 @@ int op_apply_distributed(Ctx* ctx, Level& L, const double* d_x, double* d_y, dou
   ncclComm_t comm = (ncclComm_t)ctx->nccl;
   HPDG_NCCL(g_nccl.GroupStart());
   for (int f = 0; f < 6; f++) {
-    if (!ctx->ghost.active[f]) continue;
-    HPDG_NCCL(g_nccl.Send(ctx->ghost.d_send[f], ctx->ghost.count[f], ncclDouble, ctx->ghost.peer[f], comm, ctx->stream_comm));
-    HPDG_NCCL(g_nccl.Recv(ctx->ghost.d_recv[f], ctx->ghost.count[f], ncclDouble, ctx->ghost.peer[f], comm, ctx->stream_comm));
+    if (!G.active[f]) continue;
+    HPDG_NCCL(g_nccl.Send(G.d_send[f], G.count[f], ncclDouble, G.peer[f], comm, ctx->stream_comm));
+    HPDG_NCCL(g_nccl.Recv(G.d_recv[f], G.count[f], ncclDouble, G.peer[f], comm, ctx->stream_comm));
   }
   HPDG_NCCL(g_nccl.GroupEnd());
   if (launch_apply_uniform(ctx, L, d_x, d_y, factor, 2, ctx->stream_comm)) return 1;   // rank-boundary tiles
@@ -192,9 +197,8 @@ int op_apply_distributed(Ctx* ctx, Level& L, const double* d_x, double* d_y, dou
 }
 
 int op_apply_async(Ctx* ctx, Level& L, const double* d_x, double* d_y, double factor) {
-  const bool finest = (&L == &ctx->levels.back());
   if (ctx->nranks > 1) {
-    if (!finest || !uniform_supported(ctx, L)) { ctx->err = "distributed apply needs the uniform-degree 3-D kernel on the finest level"; return 1; }
+    if (!uniform_supported(ctx, L)) { ctx->err = "distributed apply needs a level with a uniform-degree 3-D kernel"; return 1; }
     return op_apply_distributed(ctx, L, d_x, d_y, factor);
   }
   if (uniform_supported(ctx, L)) return launch_apply_uniform(ctx, L, d_x, d_y, factor, 0);
@@ -274,7 +278,7 @@ int mg_level(Ctx* ctx, int l, const VC& v) {
 }
 
 int vcycle_device(Ctx* ctx, const VC& v, double* d_x, double* d_b) {
-  if (ctx->nranks > 1) { ctx->err = "V-cycle is single-rank in this round"; return 1; }
+  if (ctx->nranks > 1 && v.form != HPDG_JACOBI_FD) { ctx->err = "the distributed V-cycle supports the fd block-Jacobi smoother only"; return 1; }
   const int nl = (int)ctx->levels.size();
   for (int l = 0; l < nl; l++) {
     Level& L = ctx->levels[l];

@@ -590,19 +590,20 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
   const int tdim[3] = {TX, TY, TZ};
   for (int d = 0; d < 3; d++) { P.n[d] = L.n[d]; P.ntile[d] = (L.n[d] + tdim[d] - 1) / tdim[d]; }
   const bool finest = (&L == &ctx->levels.back());
+  Ghost* Gp = nullptr;
+  if (ctx->nranks > 1 && level_ghost(ctx, L, &Gp)) return 1;
   for (int f = 0; f < 6; f++) {
     P.ghost[f] = nullptr;
     if (ctx->bnd_is_rank[f]) {
-      if (!finest) { ctx->err = "distributed apply is implemented on the finest level only"; return 1; }
       P.bmode[f] = 3;
-      if (ctx->ghost.p2p) {
+      if (finest && ctx->ghost.p2p) {
         const int par = ctx->ghost.step & 1;
         P.ghost[f] = reinterpret_cast<const double*>(ctx->ghost.arena + ctx->ghost.recv_off[f][par]);
         P.ghost_flag[f] = reinterpret_cast<const int*>(ctx->ghost.arena + ctx->ghost.flag_off) + f * 2 + par;
-      } else { P.ghost[f] = ctx->ghost.d_recv[f]; P.ghost_flag[f] = nullptr; }
+      } else { P.ghost[f] = Gp->d_recv[f]; P.ghost_flag[f] = nullptr; }
     } else { P.bmode[f] = ctx->dirichlet ? 1 : 2; P.ghost_flag[f] = nullptr; }
   }
-  P.ghost_step = (ctx->ghost.p2p && part == 3) ? ctx->ghost.step : 0;
+  P.ghost_step = (finest && ctx->ghost.p2p && part == 3) ? ctx->ghost.step : 0;
   P.ghost_err = ctx->ghost.p2p ? reinterpret_cast<int*>(ctx->ghost.arena + ctx->ghost.flag_off) + 12 : nullptr;
   P.x = x; P.y = y; P.part = part; P.accum = ctx->fuse_accum;
   P.tile_list = nullptr; P.tile_offset = 0; P.tile_rot = 0;
@@ -697,17 +698,38 @@ int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double 
   }
 }
 
+// halo buffers of a level: the context's for the finest level, lazily allocated per-level buffers (NCCL transport) otherwise
+int level_ghost(Ctx* ctx, Level& L, Ghost** out) {
+  if (&L == &ctx->levels.back()) { *out = &ctx->ghost; return 0; }
+  Ghost& G = L.cg;
+  if (!G.d_recv[0] && !G.d_recv[1] && !G.d_recv[2] && !G.d_recv[3] && !G.d_recv[4] && !G.d_recv[5]) {
+    const int N2 = (L.p_uni + 1) * (L.p_uni + 1);
+    for (int f = 0; f < 6; f++) {
+      G.active[f] = ctx->ghost.active[f]; G.peer[f] = ctx->ghost.peer[f];
+      if (!G.active[f]) continue;
+      G.count[f] = ((size_t)L.nelem / L.n[f / 2]) * N2 * 2;
+      HPDG_CUDA(cudaMalloc(&G.d_send[f], G.count[f] * sizeof(double)));
+      HPDG_CUDA(cudaMalloc(&G.d_recv[f], G.count[f] * sizeof(double)));
+    }
+  }
+  *out = &G;
+  return 0;
+}
+
 template <int N>
 static int pack_n(Ctx* ctx, Level& L, const double* x, cudaStream_t stream) {
   const DegTable* dt = ctx->d_tab + (N - 1);
+  const bool finest = (&L == &ctx->levels.back());
+  Ghost* Gp = nullptr;
+  if (level_ghost(ctx, L, &Gp)) return 1;
   PackParams PK;
   long maxtotal = 0;
   for (int f = 0; f < 6; f++) {
-    PK.out[f] = !ctx->ghost.active[f] ? nullptr
-              : ctx->ghost.p2p ? reinterpret_cast<double*>(ctx->ghost.peer_arena[f] + ctx->ghost.recv_off[f ^ 1][ctx->ghost.step & 1])
-                               : ctx->ghost.d_send[f];
+    PK.out[f] = !Gp->active[f] ? nullptr
+              : (finest && ctx->ghost.p2p) ? reinterpret_cast<double*>(ctx->ghost.peer_arena[f] + ctx->ghost.recv_off[f ^ 1][ctx->ghost.step & 1])
+                                           : Gp->d_send[f];
     PK.g[f] = &dt->g[f % 2][0];
-    if (ctx->ghost.active[f]) maxtotal = std::max<long>(maxtotal, (long)ctx->ghost.count[f] / 2);
+    if (Gp->active[f]) maxtotal = std::max<long>(maxtotal, (long)Gp->count[f] / 2);
   }
   if (maxtotal == 0) return 0;
   const int threads = 256;

@@ -322,7 +322,7 @@ int launch_apply_uniform3(Ctx* ctx, Level& L, const double* x, double* y, double
   for (int f = 0; f < 6; f++) {
     P.ghost[f] = nullptr;
     if (ctx->bnd_is_rank[f]) {
-      if (!finest) { ctx->err = "distributed apply is implemented on the finest level only"; return 1; }
+      if (!finest || ctx->ghost.p2p) { ctx->err = "the experimental kernel supports the NCCL halo on the finest level only"; return 1; }
       P.bmode[f] = 3; P.ghost[f] = ctx->ghost.d_recv[f];
     } else P.bmode[f] = ctx->dirichlet ? 1 : 2;
   }

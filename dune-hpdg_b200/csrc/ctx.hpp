@@ -79,6 +79,7 @@ struct Level {
   JacobiDense jd;
   JacobiFD jf;
   Bcrs bcrs;
+  Ghost cg;   // halo buffers of a coarse level (NCCL transport); the finest level uses Ctx::ghost
   // compact tile lists (interior / rank-boundary tiles) of the distributed apply, per tile shape
   int *d_tiles_int = nullptr, *d_tiles_bnd = nullptr, *d_tiles_all = nullptr;  // all = interior first, boundary last
   long n_tiles_int = 0, n_tiles_bnd = 0, tile_key = -1;
@@ -137,6 +138,7 @@ int uniform_tile_height(const Level& L);
 int uniform_tile_lists(Ctx* ctx, Level& L, int TX, int TY, int TZ, const int* bmode);
 int launch_apply_uniform3(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream);
 int launch_pack_traces(Ctx* ctx, Level& L, const double* x, cudaStream_t stream);
+int level_ghost(Ctx* ctx, Level& L, Ghost** out);  // halo buffers of this level (allocated on first use for coarse levels)
 int launch_halo_flags(Ctx* ctx, cudaStream_t stream);
 
 int jacobi_setup_dense(Ctx* ctx, Level& L);

@@ -323,7 +323,6 @@ static int jacobi_build_fd_generic(Ctx* ctx, Level& L) {
   std::map<Key, int> seen;
   std::vector<double> fac;
   std::vector<int> idx((size_t)L.nelem * 3, 0);
-  const bool finest = (&L == &ctx->levels.back());
   for (long e = 0; e < L.nelem; e++) {
     long r = e; int ijk[3];
     ijk[0] = (int)(r % L.n[0]); r /= L.n[0]; ijk[1] = (int)(r % L.n[1]); r /= L.n[1]; ijk[2] = (int)r;
@@ -339,7 +338,7 @@ static int jacobi_build_fd_generic(Ctx* ctx, Level& L) {
           long o = e + (s ? stride : -stride);
           int pm = std::max(L.pdeg[e], L.pdeg[o]);
           w[s] = 0.5; c[s] = ctx->sigma * (double)pm * pm;
-        } else if (finest && ctx->bnd_is_rank[2 * d + s]) { w[s] = 0.5; c[s] = ctx->sigma * (double)L.pdeg[e] * L.pdeg[e]; }
+        } else if (ctx->bnd_is_rank[2 * d + s]) { w[s] = 0.5; c[s] = ctx->sigma * (double)L.pdeg[e] * L.pdeg[e]; }
         else if (ctx->dirichlet) { w[s] = 1.0; c[s] = ctx->sigma * (double)L.pdeg[e] * L.pdeg[e]; }
         else { w[s] = 0.0; c[s] = 0.0; }
       }

@@ -177,12 +177,11 @@ template <int N, int TX, int TY, int TZ, int MINB>
 static int launch_fdu(Ctx* ctx, Level& L, const double* r, double* c, double damping) {
   static FDUniParams<N> P;
   const DegTable& T = host_tables().deg[N - 1];
-  const bool finest = (&L == &ctx->levels.back());
   const double cpen = ctx->sigma * (double)L.pen_uni * L.pen_uni;
   for (int d = 0; d < 3; d++) {
     double kappa = 1.0 / L.h[d];
     for (int dd = 0; dd < 3; dd++) if (dd != d) kappa *= L.h[dd];
-    for (int s = 0; s < 2; s++) P.bnd[2 * d + s] = (finest && ctx->bnd_is_rank[2 * d + s]) ? 0 : 1;
+    for (int s = 0; s < 2; s++) P.bnd[2 * d + s] = ctx->bnd_is_rank[2 * d + s] ? 0 : 1;
     for (int var = 0; var < 4; var++) {
       double w[2], cc[2];
       for (int s = 0; s < 2; s++) {

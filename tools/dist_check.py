@@ -58,9 +58,26 @@ for p, n in [(3, (8, 8, 8)), (3, (6, 5, 7)), (4, (4, 6, 4)), (1, (8, 4, 4)), (2,
     jac = hp.BlockJacobi(ctx, form=hp.JACOBI_FD, damping=0.75)
     jac.apply_device(dx, dy)
     jerr = np.linalg.norm(ctx.download(dy) - jref) / np.linalg.norm(jref)
-    good = err < 1e-12 and err2 < 1e-12 and derr < 1e-12 and jerr < 1e-11
+    # distributed p-multigrid cycle (fd block-Jacobi smoothing) against the oracle's cycle on the global mesh
+    verr = 0.0
+    if p >= 2:
+        lv = [m]
+        nl = int(np.floor(np.log2(p)))
+        for idx in range(nl - 1, -1, -1):
+            lv.insert(0, lv[0].coarsen(p // ((nl - idx) * 2)))
+        bg = orc.fill_random(m.ndof, seed=9)
+        xr, rr = orc.vcycle(lv, None, np.zeros(m.ndof), bg, smoother=1, damping=0.75)
+        ctx.build_p_hierarchy()
+        assert ctx.num_levels == len(lv)
+        dxv = ctx.upload(np.zeros(ctx.dimension()))
+        dbv = ctx.upload(part.scatter_global_vector(bg, rank, pgrid, n, ne))
+        hp.Multigrid(ctx, form=hp.JACOBI_FD, damping=0.75).apply_device(dxv, dbv)
+        xv = ctx.download(dxv)
+        xrl = part.scatter_global_vector(xr, rank, pgrid, n, ne)
+        verr = np.linalg.norm(xv - xrl) / np.linalg.norm(xrl)
+    good = err < 1e-12 and err2 < 1e-12 and derr < 1e-12 and jerr < 1e-11 and verr < 1e-10
     ok &= good
-    print(f"rank {rank}/{world} p={p} brick={n}: halo={'p2p' if p2p else 'nccl'} apply {err:.2e} twice {err2:.2e} dot {derr:.2e} jacobi {jerr:.2e} {'OK' if good else 'FAIL'}", flush=True)
+    print(f"rank {rank}/{world} p={p} brick={n}: halo={'p2p' if p2p else 'nccl'} apply {err:.2e} twice {err2:.2e} dot {derr:.2e} jacobi {jerr:.2e} vcycle {verr:.2e} {'OK' if good else 'FAIL'}", flush=True)
     ctx.close()
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
