@@ -354,9 +354,21 @@ int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double 
   P.sigma = ctx->sigma; P.dirichlet = ctx->dirichlet;
   P.deg = L.d_deg; P.pdeg = L.d_pdeg; P.off = L.d_off; P.elist = L.d_elist;
   P.tab = ctx->d_tab; P.P = ctx->d_P; P.x = x; P.y = y; P.factor = factor; P.accum = ctx->fuse_accum;
-  for (size_t b = 0; b < L.bucket_p.size(); b++) {
+  // the degree buckets write disjoint rows of y: launch them on side streams so that small buckets overlap the large ones
+  const size_t nb = L.bucket_p.size();
+  const bool fork = nb > 1;
+  if (fork) {
+    if (!ctx->bucket_stream[0]) {
+      for (int k = 0; k < 4; k++) HPDG_CUDA(cudaStreamCreateWithFlags(&ctx->bucket_stream[k], cudaStreamNonBlocking));
+      for (int k = 0; k < 5; k++) HPDG_CUDA(cudaEventCreateWithFlags(&ctx->bucket_ev[k], cudaEventDisableTiming));
+    }
+    HPDG_CUDA(cudaEventRecord(ctx->bucket_ev[4], ctx->stream));
+    for (int k = 0; k < 4; k++) HPDG_CUDA(cudaStreamWaitEvent(ctx->bucket_stream[k], ctx->bucket_ev[4], 0));
+  }
+  for (size_t b = 0; b < nb; b++) {
     long cnt = L.bucket_begin[b + 1] - L.bucket_begin[b];
     if (cnt == 0) continue;
+    cudaStream_t lstream = fork ? ctx->bucket_stream[b % 4] : ctx->stream;
     int p = L.bucket_p[b], n1 = p + 1;
     int ne = 1, nf = 1;
     for (int d = 0; d < L.dim; d++) ne *= n1;
@@ -385,7 +397,7 @@ int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double 
     }                                                                                                                     \
     if (smem_l + 1024 > 48 * 1024)                                                                                        \
       HPDG_CUDA(cudaFuncSetAttribute(k_apply_generic<D, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));  \
-    k_apply_generic<D, NN><<<grid, threads, smem_l, ctx->stream>>>(P, T, maxno1, cnt, epc, per_elem);                     \
+    k_apply_generic<D, NN><<<grid, threads, smem_l, lstream>>>(P, T, maxno1, cnt, epc, per_elem);                     \
   } while (0)
 #define HPDG_GEN_CASE(NN)                                                      \
   case NN:                                                                     \
@@ -400,6 +412,12 @@ int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double 
 #undef HPDG_GEN_LAUNCH
     ctx->launches++;
     HPDG_CUDA(cudaGetLastError());
+  }
+  if (fork) {
+    for (int k = 0; k < 4; k++) {
+      HPDG_CUDA(cudaEventRecord(ctx->bucket_ev[k], ctx->bucket_stream[k]));
+      HPDG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->bucket_ev[k], 0));
+    }
   }
   return 0;
 }

@@ -113,6 +113,8 @@ struct Ctx {
   int variant = 0;  // kernel variant selector for tuning experiments
   int slab_z0 = 0, slab_nz = 0;  // restrict the next uniform launch to element layers [z0, z0+nz) (chunked host apply)
   cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;
+  cudaStream_t bucket_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // hp apply: degree buckets run concurrently
+  cudaEvent_t bucket_ev[5] = {};
   cudaEvent_t ev_chunk[3][32] = {};
   // fusion requests of the V-cycle driver, consumed by the next launch:
   int fuse_accum = 0;          // apply: y = y_old + factor * A x   (r -= A c without a separate axpy)
