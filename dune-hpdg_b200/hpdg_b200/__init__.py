@@ -164,7 +164,10 @@ class Context:
         return lib().hpdg_num_elements(self._h)
 
     def dimension(self, level=FINEST):
-        return lib().hpdg_dimension(self._h, level)
+        n = lib().hpdg_dimension(self._h, level)
+        if n < 0:
+            raise HpdgError(lib().hpdg_last_error(self._h).decode())
+        return n
 
     def block_offsets(self, level=FINEST):
         off = np.zeros(self.num_elements + 1, dtype=np.int64)

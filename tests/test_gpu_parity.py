@@ -307,3 +307,56 @@ def test_vcycle_with_reference_default_smoother(orc, hp):
     assert rel(x, xr) < 1e-11 and rel(bb, rr) < 1e-10
     # and it contracts much faster than damped block Jacobi
     assert np.linalg.norm(bb) < 0.2 * np.linalg.norm(b - Af.mv(x0))
+
+
+def test_cfg5_full_size_properties(hp):
+    # BASELINE config 5 brick: 128^3 elements, Q4 (262 144 000 DoF, 2.1 GB per vector) -- too large for the CPU oracle, so the
+    # size-independent properties of the operator are checked on the device: symmetry, linearity, positivity.
+    import torch
+    if torch.cuda.mem_get_info()[0] < 16e9:
+        pytest.skip("needs 16 GB of free HBM")
+    n = (128, 128, 128)
+    ctx = hp.Context(n, degree=4, sigma=2.0, dirichlet=True)
+    nd = ctx.dimension()
+    assert nd == 262144000 and ctx.uses_uniform_kernel()
+    rng = np.random.default_rng(5)
+    hx, px = ctx.host_alloc(nd)
+    hx[:] = rng.standard_normal(nd)
+    dx = ctx.upload(px)
+    hx[:] = rng.standard_normal(nd)
+    dz = ctx.upload(px)
+    dAx, dAz, dw = ctx.vec_alloc(), ctx.vec_alloc(), ctx.vec_alloc()
+    op = hp.Operator(ctx)
+    op.apply_device(dx, dAx)
+    op.apply_device(dz, dAz)
+    zAx, xAz, xAx = ctx.dot_device(dz, dAx), ctx.dot_device(dx, dAz), ctx.dot_device(dx, dAx)
+    assert abs(zAx - xAz) <= 1e-11 * abs(xAx)          # symmetry
+    assert xAx > 0                                        # SPD with Dirichlet faces
+    # linearity: A(2x - 3z) = 2Ax - 3Az
+    ctx.axpy_device(1.0, dx, dx)                          # x <- 2x
+    ctx.axpy_device(-3.0, dz, dx)                         # x <- 2x - 3z
+    op.apply_device(dx, dw)
+    ctx.axpy_device(-2.0, dAx, dw)
+    ctx.axpy_device(3.0, dAz, dw)
+    ctx.sync()
+    assert ctx.dot_device(dw, dw) <= (1e-12 ** 2) * (4 * ctx.dot_device(dAx, dAx) + 9 * ctx.dot_device(dAz, dAz))
+    for d in (dx, dz, dAx, dAz, dw):
+        ctx.vec_free(d)
+    ctx.host_free(px)
+    ctx.close()
+
+
+def test_error_behaviour(orc, hp):
+    # errors are reported, not aborted on (the reference throws Dune::Exception, e.g. dynamicblockgs.hh:117)
+    ctx = hp.Context((4, 4, 4), degree=3)
+    x = np.zeros(ctx.dimension())
+    with pytest.raises(hp.HpdgError, match="jacobi_setup"):
+        ctx._ck(hp.lib().hpdg_jacobi_apply(ctx._h, hp.FINEST, hp.JACOBI_DENSE, x.ctypes.data, x.ctypes.data, 1.0))
+    with pytest.raises(hp.HpdgError, match="level index"):
+        hp.Operator(ctx, level=3).apply(x)
+    with pytest.raises(hp.HpdgError, match="no coarser level"):
+        hp.OrderTransfer(ctx, 0).restrict(x)
+    with pytest.raises(hp.HpdgError, match="assemble"):
+        ctx._ck(hp.lib().hpdg_bcrs_mv(ctx._h, hp.FINEST, x.ctypes.data, x.ctypes.data))
+    with pytest.raises(hp.HpdgError, match="unknown option"):
+        ctx.set_option("nonsense", 1)
