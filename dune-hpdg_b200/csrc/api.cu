@@ -98,7 +98,7 @@ void free_level(Level& L) {
   cudaFree(L.d_deg); cudaFree(L.d_pdeg); cudaFree(L.d_off); cudaFree(L.d_elist);
   cudaFree(L.jd.d_inv); cudaFree(L.jf.d_fac); cudaFree(L.jf.d_idx);
   cudaFree(L.mg_x); cudaFree(L.mg_r); cudaFree(L.mg_t1); cudaFree(L.mg_t2);
-  cudaFree(L.d_tiles_int); cudaFree(L.d_tiles_bnd);
+  cudaFree(L.d_tiles_int); cudaFree(L.d_tiles_bnd); cudaFree(L.d_tiles_all); cudaFree(L.d_tile_desc);
   cudaFree(L.bcrs.d_rowptr); cudaFree(L.bcrs.d_col); cudaFree(L.bcrs.d_brow); cudaFree(L.bcrs.d_boff); cudaFree(L.bcrs.d_val);
   cudaFree(L.bcrs.d_wave); cudaFree(L.bcrs.d_res);
   for (int f = 0; f < 6; f++) { cudaFree(L.cg.d_send[f]); cudaFree(L.cg.d_recv[f]); }
@@ -413,6 +413,7 @@ const char* hpdg_last_error(const hpdg_ctx* ctx) { return ctx ? ctx->err.c_str()
 int hpdg_set_option(hpdg_ctx* ctx, const char* name, long value) {
   if (!strcmp(name, "force_generic")) { ctx->force_generic = (int)value; return 0; }
   if (!strcmp(name, "variant")) { ctx->variant = (int)value; return 0; }
+  if (!strcmp(name, "q3p_grid")) { ctx->q3p_grid = (int)value; return 0; }
   if (!strcmp(name, "halo_p2p")) {  // switch between the NVLink peer-memory halo and NCCL send/recv (attach must have succeeded for 1)
     if (value && !ctx->ghost.peer_attached) { ctx->err = "halo_p2p: hpdg_halo_ipc_attach has not succeeded on this context"; return 1; }
     ctx->ghost.p2p = value != 0; return 0;

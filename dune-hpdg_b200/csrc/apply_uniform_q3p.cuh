@@ -1,0 +1,393 @@
+// Persistent, prefetching Q3 (N = 4) tile kernel of the uniform-degree 3-D SIPG operator apply: the headline kernel.
+//
+// Same operator, formulation and five pencil passes as k_apply_uniform (apply_uniform.cu; reference: Operator::apply over
+// IPDGOperator, matrix-free/operator.hh:41-56, matrix-free/localoperators/ipdgoperator.hh:80-390).  What changes is how the
+// DoF blocks move:
+//  * CTAs are persistent (one per SM slot, tiles strided by the grid, x-fastest so concurrent CTAs work on neighbouring
+//    tiles and their halo reads hit L2).  The 4x4x4-element tile of u arrives in shared memory by 16 bulk async copies
+//    (cp.async.bulk, 2 KB each: the four x-contiguous elements of a row are contiguous in a DynamicBlockVector) that
+//    complete on an mbarrier.  The copies for tile t+1 are issued right after pass 3 of tile t (the last reader of the
+//    u buffer), so they are in flight during passes 4 and 5 and no thread ever waits on a global load of u.
+//  * Shared memory is unpadded (2 x 32 KB per CTA -> 3 CTAs/SM).  Pass 1 rewrites u in place into a swizzled layout:
+//    within the 128-byte row of an (element, z-plane k) the 32-byte x-line j sits at line slot j^k, rotated by 16 bytes
+//    for odd element layers.  With that, all three pencil directions are bank-conflict free: z-pencils (64-bit, a half
+//    warp = the 16 nodes of a plane), y-pencils (64-bit, half warp = 4 i x 4 k), x-pencils (128-bit, quarter warp = 4 j x
+//    2 element layers).  The in-place rewrite only permutes data among the lanes of one half warp (they own the column of
+//    elements they read), so a __syncwarp between the reads and the writes is all it needs.
+//  * Pass 5 and the next tile's pass 1 use the same thread -> column mapping, so no block barrier separates two tiles.
+// Requires brick extents that are multiples of 4 (otherwise the masked k_apply_uniform is used).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <utility>
+
+#include "uniform_common.cuh"
+
+namespace hpdg {
+
+__device__ __forceinline__ uint32_t q3p_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void q3p_mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(q3p_smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void q3p_mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(q3p_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool q3p_mbar_try_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok) : "r"(q3p_smem_u32(b)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void q3p_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(q3p_smem_u32(dst)), "l"(src), "r"(bytes), "r"(q3p_smem_u32(b)) : "memory");
+}
+
+// ---- table access ------------------------------------------------------------------------------------------------------
+// The 1-D tables live in the kernel's parameter block (constant bank).  Read through the struct, NVVM hoists all ~180
+// table loads out of the persistent tile loop; they then overflow the uniform register file and ptxas spills them to local
+// memory and moves them back with R2UR inside the passes.  Reading them with a (volatile, immediate-offset) ld.param keeps
+// the loads where they are used; ptxas still merges and schedules them like ordinary constant-bank operands.
+template <int OFF>
+__device__ __forceinline__ double q3p_c() {
+  double v;
+  asm volatile("ld.param.f64 %0, [hpdg_k_apply_q3_persist_param_0+%1];\n" : "=d"(v) : "n"(OFF));
+  return v;
+}
+#define Q3P_C(field, idx) q3p_c<(int)offsetof(UniParams<4>, field) + 8 * (idx)>()
+
+// The GL nodes are symmetric about the element centre, so with R the node reflection: M, Dp commute with R, M is symmetric,
+// g_1 = -R g_0, A1 = -R A0, B1 = R B0.  Only one representative of each group of equal entries is read (27 distinct doubles
+// for a T-sweep + mass pass instead of 57), which lets a pass's tables fit in the uniform register file.
+__host__ __device__ constexpr int q3p_dp_idx(int dir, int i, int m) { return dir * 16 + (i < 2 ? i * 4 + m : (3 - i) * 4 + (3 - m)); }
+__host__ __device__ constexpr int q3p_m_idx(int i, int m) {
+  int best = i * 4 + m;
+  const int c1 = m * 4 + i, c2 = (3 - i) * 4 + (3 - m), c3 = (3 - m) * 4 + (3 - i);
+  if (c1 < best) best = c1;
+  if (c2 < best) best = c2;
+  if (c3 < best) best = c3;
+  return best;
+}
+
+template <int... I, class F>
+__device__ __forceinline__ void q3p_for_impl(std::integer_sequence<int, I...>, F f) { (f(std::integral_constant<int, I>{}), ...); }
+template <int N, class F>
+__device__ __forceinline__ void q3p_for(F f) { q3p_for_impl(std::make_integer_sequence<int, N>{}, f); }
+
+// acc_e = accin_e + (Tt_dir v)_e for the 4 elements of a full pencil (N = 4); same arithmetic as pencil_apply
+// (uniform_common.cuh).  load(e, v) fetches the DoF line of element e, accin(e, a) fills the accumulator's initial values
+// of element e, out(e, v, a) consumes the element's line and results.  The elements are processed in the order 1, 2, 3, 0
+// so that the traces of the elements outside the pencil (global loads issued just before the call) are consumed last.
+template <int DIR, class Load, class AccIn, class Out>
+__device__ __forceinline__ void q3p_pencil(double pd, double pv, int pmode, double nd, double nv, int nmode, Load load,
+                                           AccIn accin, Out out) {
+  constexpr int N = 4, T = 4;
+  double v[T][N], d0[T], d1[T];
+#pragma unroll
+  for (int e = 0; e < T; e++) {
+    load(e, v[e]);
+    double a = 0, b = 0;
+    q3p_for<N>([&](auto mc) {
+      constexpr int m = decltype(mc)::value;
+      a = fma(Q3P_C(g, m), v[e][m], a); b = fma(-Q3P_C(g, N - 1 - m), v[e][m], b);
+    });
+    d0[e] = a; d1[e] = b;
+  }
+#pragma unroll
+  for (int ee = 0; ee < T; ee++) {
+    const int e = (ee + 1) % T;
+    double qd, qv, rd, rv;
+    if (e == 0) {
+      if (pmode == 1) { pd = fma(-Q3P_C(cohk, DIR), v[0][0], d0[0]); pv = -v[0][0]; }
+      else if (pmode == 2) { pd = -d0[0]; pv = v[0][0]; }
+      qd = pd; qv = pv;
+    } else { qd = d1[e > 0 ? e - 1 : 0]; qv = v[e > 0 ? e - 1 : 0][N - 1]; }
+    if (e == T - 1) {
+      if (nmode == 1) { nd = fma(Q3P_C(cohk, DIR), v[T - 1][N - 1], d1[T - 1]); nv = -v[T - 1][N - 1]; }
+      else if (nmode == 2) { nd = -d1[T - 1]; nv = v[T - 1][N - 1]; }
+      rd = nd; rv = nv;
+    } else { rd = d0[e < T - 1 ? e + 1 : e]; rv = v[e < T - 1 ? e + 1 : e][0]; }
+    double a[N];
+    accin(e, a);
+    q3p_for<N>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      double s = a[i];
+      q3p_for<N>([&](auto mc) {
+        constexpr int m = decltype(mc)::value;
+        s = fma(Q3P_C(Dp, q3p_dp_idx(DIR, i, m)), v[e][m], s);
+      });
+      s = fma(Q3P_C(A0, DIR * N + i), qd, s); s = fma(Q3P_C(B0, DIR * N + i), qv, s);
+      s = fma(-Q3P_C(A0, DIR * N + N - 1 - i), rd, s); s = fma(Q3P_C(B0, DIR * N + N - 1 - i), rv, s);
+      a[i] = s;
+    });
+    out(e, v[e], a);
+  }
+}
+
+template <bool SCALED>
+__device__ __forceinline__ void q3p_mass(double (&a)[4]) {
+  double o[4];
+  q3p_for<4>([&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    double s = 0;
+    q3p_for<4>([&](auto mc) {
+      constexpr int m = decltype(mc)::value;
+      s = fma(SCALED ? Q3P_C(Mf, q3p_m_idx(i, m)) : Q3P_C(M, q3p_m_idx(i, m)), a[m], s);
+    });
+    o[i] = s;
+  });
+#pragma unroll
+  for (int i = 0; i < 4; i++) a[i] = o[i];
+}
+
+constexpr int kQ3pSmemBytes = 2 * 4096 * 8 + 16;
+
+// threadIdx.x re-read as an opaque value: the role indices derived from it are recomputed where a pass needs them
+// instead of being kept alive (and spilled) across the whole tile loop
+__device__ __forceinline__ int q3p_tid() {
+  int t;
+  asm volatile("mov.u32 %0, %%tid.x;\n" : "=r"(t));
+  return t;
+}
+
+struct Q3pTrace { double pd, pv, nd, nv; int pm, nm; };
+
+// (der, val) traces of the elements before / after a pencil in direction DIR.  fl: which brick faces the tile touches;
+// prev / next: this thread's DoF line in the element before / after the pencil (stride in doubles between its nodes);
+// gidx: index of this thread's face node in the ghost trace buffers of the direction.
+template <int DIR, class GIdx>
+__device__ __forceinline__ Q3pTrace q3p_halo(const UniParams<4>& P, int fl, const double* __restrict__ prev,
+                                             const double* __restrict__ next, int stride, GIdx gidx) {
+  Q3pTrace r; r.pd = r.pv = r.nd = r.nv = 0;
+  r.pm = (fl >> (2 * DIR)) & 1 ? P.bmode[2 * DIR] : 0;
+  r.nm = (fl >> (2 * DIR + 1)) & 1 ? P.bmode[2 * DIR + 1] : 0;
+  if (r.pm == 0) outside_trace<4>(P, prev, stride, 1, r.pd, r.pv);
+  else if (r.pm == 3) { const double* gp = P.ghost[2 * DIR] + gidx() * 2; r.pd = __ldcg(gp); r.pv = __ldcg(gp + 1); r.pm = 0; }
+  if (r.nm == 0) outside_trace<4>(P, next, stride, 0, r.nd, r.nv);
+  else if (r.nm == 3) { const double* gp = P.ghost[2 * DIR + 1] + gidx() * 2; r.nd = __ldcg(gp); r.nv = __ldcg(gp + 1); r.nm = 0; }
+  return r;
+}
+
+__device__ __forceinline__ void q3p_bar_half(int half) {
+  if (half) asm volatile("bar.sync 2, 128;\n" ::: "memory");
+  else asm volatile("bar.sync 1, 128;\n" ::: "memory");
+}
+
+}  // namespace hpdg
+
+// Tile descriptors (built once per level on the host): .x = index of the tile's first element, .y = tile coordinates
+// tx | ty << 10 | tz << 20, .z = bit f set if the tile touches brick face f.
+// extern "C": the table reads name the kernel's parameter symbol (<kernel>_param_0)
+extern "C" __global__ void __launch_bounds__(256, 3)
+hpdg_k_apply_q3_persist(const __grid_constant__ hpdg::UniParams<4> P, const int4* __restrict__ tile_desc, const int ntiles,
+                        const int ntiles_total) {
+  using namespace hpdg;
+  constexpr int N = 4, N2 = 16, N3 = 64;
+  extern __shared__ __align__(128) double q3p_sm[];
+  double* __restrict__ su = q3p_sm;
+  double* __restrict__ sw = q3p_sm + 4096;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(q3p_sm + 8192);
+  const double* __restrict__ X = P.x;
+  const int n0 = P.n[0], n01 = P.n[0] * P.n[1];  // element strides (in elements) in y and z
+
+  auto descriptor = [&](int t) {
+    int tb = P.tile_list ? P.tile_list[t] : t + P.tile_offset;
+    if (P.tile_rot) { tb += P.tile_rot; if (tb >= ntiles_total) tb -= ntiles_total; }
+    return __ldg(tile_desc + tb);
+  };
+  // The two halves of the CTA (element layers ez = 0,1 / 2,3) are independent between the first and the last pass: each
+  // fetches its own half of the u tile, 8 rows of four x-contiguous elements (2 KB each)
+  auto prefetch = [&](int tid, int e0) {
+    const int l = tid & 127, half = tid >> 7;
+    if (l < 8) {
+      if (l == 0) q3p_mbar_expect_tx(mbar, 16384u);
+      const int ey = l & 3, ez = 2 * half + (l >> 2);
+      q3p_bulk_g2s(su + (4 * ey + 16 * ez) * N3, X + (long)(e0 + n0 * ey + n01 * ez) * N3, 2048u, mbar);
+    }
+  };
+
+  if (threadIdx.x == 0) {
+    q3p_mbar_init(mbar, 2);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  int t = blockIdx.x;
+  if (t >= ntiles) return;
+  int4 td = descriptor(t);
+  prefetch(threadIdx.x, td.x);
+  uint32_t phase = 0;
+
+  for (;;) {
+    const int e0 = td.x, fl = td.z;
+    const int ty4 = ((td.y >> 10) & 1023) * 4, tz4 = (td.y >> 20) * 4, tx4 = (td.y & 1023) * 4;  // only used on ghost faces
+    if (P.ghost_step > 0) {  // p2p halo: tiles on a rank boundary wait until the neighbour's traces for this step have arrived
+      bool touch[6]; bool any = false;
+#pragma unroll
+      for (int f = 0; f < 6; f++) { touch[f] = ((fl >> f) & 1) && P.bmode[f] == 3; any = any || touch[f]; }
+      if (any) {
+        if (threadIdx.x == 0) {
+          const long long tstart = clock64();
+          for (int f = 0; f < 6; f++) {
+            if (!touch[f]) continue;
+            const volatile int* fg = P.ghost_flag[f];
+            while (*fg < P.ghost_step) {
+              __nanosleep(200);
+              if (clock64() - tstart > 4000000000LL) { atomicExch(P.ghost_err, 1); break; }  // ~2 s: give up, never hang the GPU
+            }
+          }
+          __threadfence();
+        }
+        __syncthreads();
+      }
+    }
+
+    // ---------------- P1: z-pencils; u from the prefetched tile, rewritten in place (swizzled) ----------------
+    // z-role: node (i, j) of element column (ex, ey); a half warp = one column
+    {
+      const int tid = q3p_tid();
+      const int zq = tid & 15, zex = (tid >> 4) & 3, zey = tid >> 6;
+      const int zcol = (zex + 4 * zey) * N3;
+      const double* colp = X + (long)(e0 + zex + n0 * zey) * N3 + zq;  // element (x, y, z0), this node
+      const Q3pTrace h = q3p_halo<2>(P, fl, colp - (long)n01 * N3, colp + (long)n01 * (4 * N3), N2,
+                                     [&]() { return ((long)(tx4 + zex) + (long)n0 * (ty4 + zey)) * N2 + zq; });
+      while (!q3p_mbar_try_wait(mbar, phase)) {}
+      phase ^= 1;
+      // in-place swizzle: every lane of the half warp reads its raw lines before any lane overwrites the column
+      double v[4][4];
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[e][k] = su[zcol + 1024 * e + 16 * k + zq];
+      __syncwarp();
+      q3p_pencil<2>(h.pd, h.pv, h.pm, h.nd, h.nv, h.nm,
+        [&](int e, double (&l)[4]) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) l[k] = v[e][k];
+        },
+        [](int, double (&a)[4]) { a[0] = a[1] = a[2] = a[3] = 0.0; },
+        [&](int e, const double (&l)[4], const double (&a)[4]) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int o = zcol + 1024 * e + 16 * k + (((zq ^ (4 * k)) + 2 * (e & 1)) & 15);
+            su[o] = l[k]; sw[o] = a[k];
+          }
+        });
+    }
+
+    // ---------------- P2: x-pencils (128-bit shared-memory accesses) ----------------
+    // x-role: line (j, k) of element row (ey, ez); a quarter warp = 4 j x 2 element layers
+    {
+      const int tid = q3p_tid();
+      const int xj = tid & 3, xez = ((tid >> 2) & 1) | ((tid >> 6) & 2), xk = (tid >> 3) & 3, xey = (tid >> 5) & 3;
+      const int xq = 2 * (xj ^ xk) + (xez & 1);
+      const int xo0 = (4 * xey + 16 * xez) * N3 + 16 * xk + 2 * (xq & 7);        // nodes i = 0,1 of the line (+ 64 e)
+      const int xo1 = (4 * xey + 16 * xez) * N3 + 16 * xk + 2 * ((xq + 1) & 7);  // nodes i = 2,3
+      const double* rowp = X + (long)(e0 + n0 * xey + n01 * xez) * N3 + N * xj + N2 * xk;  // element (x0, y, z), this line
+      const Q3pTrace h = q3p_halo<0>(P, fl, rowp - N3, rowp + 4 * N3, 1,
+                                     [&]() { return ((long)(ty4 + xey) + (long)P.n[1] * (tz4 + xez)) * N2 + xj + N * xk; });
+      __syncthreads();
+      q3p_pencil<0>(h.pd, h.pv, h.pm, h.nd, h.nv, h.nm,
+        [&](int e, double (&l)[4]) {
+          const double2 lo = *reinterpret_cast<const double2*>(su + xo0 + 64 * e);
+          const double2 hi = *reinterpret_cast<const double2*>(su + xo1 + 64 * e);
+          l[0] = lo.x; l[1] = lo.y; l[2] = hi.x; l[3] = hi.y;
+        },
+        [&](int e, double (&a)[4]) {
+          const double2 lo = *reinterpret_cast<const double2*>(sw + xo0 + 64 * e);
+          const double2 hi = *reinterpret_cast<const double2*>(sw + xo1 + 64 * e);
+          a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
+        },
+        [&](int e, const double (&)[4], const double (&a)[4]) {
+          *reinterpret_cast<double2*>(sw + xo0 + 64 * e) = make_double2(a[0], a[1]);
+          *reinterpret_cast<double2*>(sw + xo1 + 64 * e) = make_double2(a[2], a[3]);
+        });
+    }
+
+    // ---------------- P3: y-pencils, then M_y ----------------
+    // y-role: line (i, k) of element row (ex, ez); a half warp = 4 i x 4 k
+    {
+      const int tid = q3p_tid();
+      const int yi = tid & 3, yk = (tid >> 2) & 3, yex = (tid >> 4) & 3, yez = tid >> 6;
+      const int ybase = (yex + 16 * yez) * N3 + 16 * yk;
+      const int yr = yi + 2 * (yez & 1);
+      auto yo = [&](int j) { return ybase + (((4 * j) ^ (4 * yk)) + yr & 15); };  // node j of the line (+ 256 e)
+      const double* colp = X + (long)(e0 + yex + n01 * yez) * N3 + yi + N2 * yk;  // element (x, y0, z), this line
+      const Q3pTrace h = q3p_halo<1>(P, fl, colp - (long)n0 * N3, colp + (long)n0 * (4 * N3), N,
+                                     [&]() { return ((long)(tx4 + yex) + (long)n0 * (tz4 + yez)) * N2 + yi + N * yk; });
+      q3p_bar_half(tid >> 7);
+      q3p_pencil<1>(h.pd, h.pv, h.pm, h.nd, h.nv, h.nm,
+        [&](int e, double (&l)[4]) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) l[j] = su[yo(j) + 256 * e];
+        },
+        [&](int e, double (&a)[4]) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) a[j] = sw[yo(j) + 256 * e];
+        },
+        [&](int e, const double (&)[4], const double (&a)[4]) {
+          double b[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) b[j] = a[j];
+          q3p_mass<false>(b);
+#pragma unroll
+          for (int j = 0; j < 4; j++) sw[yo(j) + 256 * e] = b[j];
+        });
+    }
+
+    // this half's u rows are free: start the next tile's copies; they land during P4 and P5
+    const int tn = t + (int)gridDim.x;
+    const bool has_next = tn < ntiles;
+    {
+      const int tid = q3p_tid();
+      if (has_next) td = descriptor(tn);
+      q3p_bar_half(tid >> 7);
+      if (has_next) {
+        if ((tid & 127) < 8) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        prefetch(tid, td.x);
+      }
+    }
+
+    // ---------------- P4: M_x ----------------
+    {
+      const int tid = q3p_tid();
+      const int xj = tid & 3, xez = ((tid >> 2) & 1) | ((tid >> 6) & 2), xk = (tid >> 3) & 3, xey = (tid >> 5) & 3;
+      const int xq = 2 * (xj ^ xk) + (xez & 1);
+      const int xo0 = (4 * xey + 16 * xez) * N3 + 16 * xk + 2 * (xq & 7);
+      const int xo1 = (4 * xey + 16 * xez) * N3 + 16 * xk + 2 * ((xq + 1) & 7);
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const double2 lo = *reinterpret_cast<const double2*>(sw + xo0 + 64 * e);
+        const double2 hi = *reinterpret_cast<const double2*>(sw + xo1 + 64 * e);
+        double a[4] = {lo.x, lo.y, hi.x, hi.y};
+        q3p_mass<false>(a);
+        *reinterpret_cast<double2*>(sw + xo0 + 64 * e) = make_double2(a[0], a[1]);
+        *reinterpret_cast<double2*>(sw + xo1 + 64 * e) = make_double2(a[2], a[3]);
+      }
+    }
+    __syncthreads();
+
+    // ---------------- P5: factor * M_z, coalesced store ----------------
+    {
+      const int tid = q3p_tid();
+      const int zq = tid & 15, zex = (tid >> 4) & 3, zey = tid >> 6;
+      const int zcol = (zex + 4 * zey) * N3;
+      double* __restrict__ yo_g = P.y + (long)(e0 + zex + n0 * zey) * N3 + zq;
+      auto tile_out = [&](auto accum) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          double a[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) a[k] = sw[zcol + 1024 * e + 16 * k + (((zq ^ (4 * k)) + 2 * (e & 1)) & 15)];
+          q3p_mass<true>(a);
+          double* yo_e = yo_g + (long)(n01 * e) * N3;
+#pragma unroll
+          for (int k = 0; k < 4; k++) yo_e[N2 * k] = decltype(accum)::value ? yo_e[N2 * k] + a[k] : a[k];
+        }
+      };
+      if (P.accum) tile_out(std::true_type{}); else tile_out(std::false_type{});
+    }
+    if (!has_next) break;
+    t = tn;
+  }
+}

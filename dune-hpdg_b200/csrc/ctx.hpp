@@ -83,6 +83,7 @@ struct Level {
   // compact tile lists (interior / rank-boundary tiles) of the distributed apply, per tile shape
   int *d_tiles_int = nullptr, *d_tiles_bnd = nullptr, *d_tiles_all = nullptr;  // all = interior first, boundary last
   long n_tiles_int = 0, n_tiles_bnd = 0, tile_key = -1;
+  void* d_tile_desc = nullptr;  // persistent Q3 kernel: int4 per 4x4x4 tile {first element, packed tile coordinates, brick-face bits, 0}
   // scratch vectors for the V-cycle (device, ndof each)
   double *mg_x = nullptr, *mg_r = nullptr, *mg_t1 = nullptr, *mg_t2 = nullptr;
 };
@@ -111,6 +112,7 @@ struct Ctx {
   size_t stage_cap = 0;
   int force_generic = 0;
   int variant = 0;  // kernel variant selector for tuning experiments
+  int q3p_grid = 0; // persistent Q3 kernel: CTA count override (0 = one per SM slot)
   int slab_z0 = 0, slab_nz = 0;  // restrict the next uniform launch to element layers [z0, z0+nz) (chunked host apply)
   cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;
   cudaStream_t bucket_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // hp apply: degree buckets run concurrently

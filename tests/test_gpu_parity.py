@@ -37,6 +37,40 @@ def test_uniform_q3_edge_meshes(orc, hp, n):
     assert rel(y, ref) < TOL
 
 
+@pytest.mark.parametrize("n,L", [((8, 4, 12), [1.0, 0.5, 2.0]), ((16, 8, 8), [1.0, 1.0, 1.0]), ((4, 4, 4), [1.0, 1.0, 1.0])])
+@pytest.mark.parametrize("dirichlet", [True, False])
+@pytest.mark.parametrize("grid", [0, 3])
+def test_q3_persistent_kernel(orc, hp, n, L, dirichlet, grid):
+    # extents that are multiples of 4 take the persistent bulk-prefetch kernel; grid=3 forces several tiles per CTA
+    # (the prefetch loop)
+    m = orc.Mesh(n, L=L, degree=3, sigma=2.0, dirichlet=dirichlet)
+    x = orc.fill_random(m.ndof)
+    ref = m.apply_mf(x, threads=orc.max_threads())
+    ctx = hp.Context(n, L=L, degree=3, sigma=2.0, dirichlet=dirichlet)
+    ctx.set_option("q3p_grid", grid)
+    op = hp.Operator(ctx, factor=-0.75)
+    y = op.apply(x)
+    assert rel(y, -0.75 * ref) < TOL
+    for variant in (40,):  # 40: the one-tile-per-CTA kernel
+        ctx.set_option("variant", variant)
+        assert rel(op.apply(x), y) < TOL
+
+
+def test_q3_persistent_many_tiles(orc, hp):
+    # 32^3: 512 tiles > one per SM slot, so CTAs loop; host-pointer entry point (z-slab launches with a tile offset)
+    n = (32, 32, 32)
+    m = orc.Mesh(n, degree=3)
+    x = orc.fill_random(m.ndof)
+    ref = m.apply_mf(x, threads=orc.max_threads())
+    ctx = hp.Context(n, degree=3)
+    assert rel(hp.Operator(ctx).apply(x), ref) < TOL
+    hx, px = ctx.host_alloc(m.ndof)
+    hy, py = ctx.host_alloc(m.ndof)
+    hx[:] = x
+    hp.Operator(ctx, factor=2.0).apply(px, py)
+    assert rel(hy, 2.0 * ref) < TOL
+
+
 def test_cfg1_2d_q2_testdg(orc, hp):
     # BASELINE config 1 / matrix-free/test/testdg.cc: 16x16 Q2, x = |x|^2, factor 0.5, energy error < 1e-14
     m = orc.Mesh((16, 16), degree=2, sigma=2.0, dirichlet=True)
