@@ -398,7 +398,7 @@ void hpdg_destroy(hpdg_ctx* ctx) {
   for (auto& L : ctx->levels) free_level(L);
   for (int f = 0; f < 6; f++) { cudaFree(ctx->ghost.d_send[f]); cudaFree(ctx->ghost.d_recv[f]); if (ctx->ghost.peer_arena[f]) cudaIpcCloseMemHandle(ctx->ghost.peer_arena[f]); }
   cudaFree(ctx->ghost.arena);
-  cudaFree(ctx->d_tab); cudaFree(ctx->d_P); cudaFree(ctx->d_T); cudaFree(ctx->d_Mab); cudaFree(ctx->d_in); cudaFree(ctx->d_out);
+  cudaFree(ctx->d_tab); cudaFree(ctx->d_sched); cudaFree(ctx->d_P); cudaFree(ctx->d_T); cudaFree(ctx->d_Mab); cudaFree(ctx->d_in); cudaFree(ctx->d_out);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -414,6 +414,7 @@ int hpdg_set_option(hpdg_ctx* ctx, const char* name, long value) {
   if (!strcmp(name, "force_generic")) { ctx->force_generic = (int)value; return 0; }
   if (!strcmp(name, "variant")) { ctx->variant = (int)value; return 0; }
   if (!strcmp(name, "q3p_grid")) { ctx->q3p_grid = (int)value; return 0; }
+  if (!strcmp(name, "q3p_tune")) { ctx->q3p_tune = (int)value; return 0; }
   if (!strcmp(name, "halo_p2p")) {  // switch between the NVLink peer-memory halo and NCCL send/recv (attach must have succeeded for 1)
     if (value && !ctx->ghost.peer_attached) { ctx->err = "halo_p2p: hpdg_halo_ipc_attach has not succeeded on this context"; return 1; }
     ctx->ghost.p2p = value != 0; return 0;

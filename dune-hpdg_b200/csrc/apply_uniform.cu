@@ -28,6 +28,7 @@
 #include "ctx.hpp"
 #include "uniform_common.cuh"
 #include "apply_uniform_q3p.cuh"
+#include "apply_uniform_q3e.cuh"
 
 namespace hpdg {
 
@@ -538,10 +539,15 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
       static int slots = 0;
       if (!slots) {
         HPDG_CUDA(cudaFuncSetAttribute(hpdg_k_apply_q3_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, kQ3pSmemBytes));
+        HPDG_CUDA(cudaFuncSetAttribute(hpdg_k_apply_q3_eo, cudaFuncAttributeMaxDynamicSharedMemorySize, kQ3pSmemBytes));
         int nsm = 0, occ = 0;
         HPDG_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
         HPDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hpdg_k_apply_q3_persist, 256, kQ3pSmemBytes));
         slots = nsm * std::max(occ, 1);
+      }
+      if (!ctx->d_sched) {  // tile counters of the dynamic scheduler: {next, done} per launch kind
+        HPDG_CUDA(cudaMalloc(&ctx->d_sched, 8 * sizeof(int)));
+        HPDG_CUDA(cudaMemset(ctx->d_sched, 0, 8 * sizeof(int)));
       }
       if (!L.d_tile_desc) {  // tile descriptors, once per level
         std::vector<int4> td((size_t)ntiles_total);
@@ -554,7 +560,31 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
         HPDG_CUDA(cudaMemcpy(L.d_tile_desc, td.data(), sizeof(int4) * td.size(), cudaMemcpyHostToDevice));
       }
       const int grid = (int)std::min<long>(ntiles, ctx->q3p_grid > 0 ? ctx->q3p_grid : slots);
-      hpdg_k_apply_q3_persist<<<grid, 256, kQ3pSmemBytes, stream>>>(P, static_cast<const int4*>(L.d_tile_desc), (int)ntiles, (int)ntiles_total);
+      if (ctx->variant != 42) {  // default: nodal arithmetic
+        hpdg_k_apply_q3_persist<<<grid, 256, kQ3pSmemBytes, stream>>>(P, static_cast<const int4*>(L.d_tile_desc), (int)ntiles, (int)ntiles_total, ctx->d_sched + 2 * (part & 3));
+      } else {  // variant 42: even/odd arithmetic (apply_uniform_q3e.cuh); fewer FP64 operations but measured slower (94.9 vs 91.7 us on cfg2)
+        static Q3eTab E;
+        for (int d = 0; d < 3; d++) {
+          for (int a = 0; a < 2; a++) {
+            for (int b = 0; b < 2; b++) {
+              E.De[d][a * 2 + b] = P.Dp[d][a * 4 + b] + P.Dp[d][a * 4 + 3 - b];
+              E.Do[d][a * 2 + b] = P.Dp[d][a * 4 + b] - P.Dp[d][a * 4 + 3 - b];
+            }
+            E.Ae[d][a] = P.A0[d][a] + P.A0[d][3 - a]; E.Ao[d][a] = P.A0[d][a] - P.A0[d][3 - a];
+            E.Be[d][a] = 0.5 * (P.B0[d][a] + P.B0[d][3 - a]); E.Bo[d][a] = 0.5 * (P.B0[d][a] - P.B0[d][3 - a]);
+          }
+          E.hc[d] = 0.5 * P.cohk[d];
+        }
+        for (int a = 0; a < 2; a++) {
+          E.ge[a] = 0.5 * (P.g[0][a] + P.g[0][3 - a]); E.go[a] = 0.5 * (P.g[0][a] - P.g[0][3 - a]);
+          for (int b = 0; b < 2; b++) {
+            E.Me[a * 2 + b] = P.M[a * 4 + b] + P.M[a * 4 + 3 - b]; E.Mo[a * 2 + b] = P.M[a * 4 + b] - P.M[a * 4 + 3 - b];
+            E.Mfe[a * 2 + b] = 0.125 * (P.Mf[a * 4 + b] + P.Mf[a * 4 + 3 - b]); E.Mfo[a * 2 + b] = 0.125 * (P.Mf[a * 4 + b] - P.Mf[a * 4 + 3 - b]);
+          }
+        }
+        for (int m = 0; m < 4; m++) E.g0[m] = P.g[0][m];
+        hpdg_k_apply_q3_eo<<<grid, 256, kQ3pSmemBytes, stream>>>(P, E, static_cast<const int4*>(L.d_tile_desc), (int)ntiles, (int)ntiles_total);
+      }
       ctx->launches++;
       HPDG_CUDA(cudaGetLastError());
       return 0;

@@ -181,13 +181,14 @@ __device__ __forceinline__ void q3p_bar_half(int half) {
 // extern "C": the table reads name the kernel's parameter symbol (<kernel>_param_0)
 extern "C" __global__ void __launch_bounds__(256, 3)
 hpdg_k_apply_q3_persist(const __grid_constant__ hpdg::UniParams<4> P, const int4* __restrict__ tile_desc, const int ntiles,
-                        const int ntiles_total) {
+                        const int ntiles_total, int* __restrict__ sched) {
   using namespace hpdg;
   constexpr int N = 4, N2 = 16, N3 = 64;
   extern __shared__ __align__(128) double q3p_sm[];
   double* __restrict__ su = q3p_sm;
   double* __restrict__ sw = q3p_sm + 4096;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(q3p_sm + 8192);
+  volatile int* s_next = reinterpret_cast<volatile int*>(q3p_sm + 8193);
   const double* __restrict__ X = P.x;
   const int n0 = P.n[0], n01 = P.n[0] * P.n[1];  // element strides (in elements) in y and z
 
@@ -219,6 +220,10 @@ hpdg_k_apply_q3_persist(const __grid_constant__ hpdg::UniParams<4> P, const int4
   uint32_t phase = 0;
 
   for (;;) {
+    // dynamic tile scheduling: the CTA's first tile is blockIdx.x, the following ones come from a global counter (sched[0],
+    // reset by the last CTA to finish), so that CTAs on less loaded SMs take more tiles and the last wave stays short.
+    // Thread 0 draws the next tile here; the others read it after pass 3 (three barriers later).
+    if (threadIdx.x == 0) *s_next = (int)gridDim.x + atomicAdd(sched, 1);
     const int e0 = td.x, fl = td.z;
     const int ty4 = ((td.y >> 10) & 1023) * 4, tz4 = (td.y >> 20) * 4, tx4 = (td.y & 1023) * 4;  // only used on ghost faces
     if (P.ghost_step > 0) {  // p2p halo: tiles on a rank boundary wait until the neighbour's traces for this step have arrived
@@ -336,7 +341,7 @@ hpdg_k_apply_q3_persist(const __grid_constant__ hpdg::UniParams<4> P, const int4
     }
 
     // this half's u rows are free: start the next tile's copies; they land during P4 and P5
-    const int tn = t + (int)gridDim.x;
+    const int tn = *s_next;
     const bool has_next = tn < ntiles;
     {
       const int tid = q3p_tid();
@@ -390,4 +395,5 @@ hpdg_k_apply_q3_persist(const __grid_constant__ hpdg::UniParams<4> P, const int4
     if (!has_next) break;
     t = tn;
   }
+  if (threadIdx.x == 0 && atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) { sched[0] = 0; sched[1] = 0; __threadfence(); }
 }

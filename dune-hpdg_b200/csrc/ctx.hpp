@@ -113,6 +113,8 @@ struct Ctx {
   int force_generic = 0;
   int variant = 0;  // kernel variant selector for tuning experiments
   int q3p_grid = 0; // persistent Q3 kernel: CTA count override (0 = one per SM slot)
+  int* d_sched = nullptr;  // persistent Q3 kernel: tile counters of its dynamic scheduler
+  int q3p_tune = 0; // persistent Q3 kernel: tuning switches (bit 0: L2 prefetch two tiles ahead)
   int slab_z0 = 0, slab_nz = 0;  // restrict the next uniform launch to element layers [z0, z0+nz) (chunked host apply)
   cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;
   cudaStream_t bucket_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // hp apply: degree buckets run concurrently

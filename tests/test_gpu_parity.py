@@ -51,7 +51,7 @@ def test_q3_persistent_kernel(orc, hp, n, L, dirichlet, grid):
     op = hp.Operator(ctx, factor=-0.75)
     y = op.apply(x)
     assert rel(y, -0.75 * ref) < TOL
-    for variant in (40,):  # 40: the one-tile-per-CTA kernel
+    for variant in (40, 42):  # 40: the one-tile-per-CTA kernel, 42: the persistent kernel with even/odd arithmetic
         ctx.set_option("variant", variant)
         assert rel(op.apply(x), y) < TOL
 
