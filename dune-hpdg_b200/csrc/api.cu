@@ -169,6 +169,11 @@ int op_apply_distributed(Ctx* ctx, Level& L, const double* d_x, double* d_y, dou
     // interior tiles first; its rank-boundary tiles wait on the flags the NEIGHBOURS raise (the local pack is not a dependency
     // of the local apply).  The compute stream joins the halo stream at the end so that x may be overwritten afterwards.
     ctx->ghost.step++;
+    if (uniform_persistent(ctx, L) && ctx->variant != 42) {
+      // persistent Q3 kernel: packing the face traces, publishing the flags and all tiles are ONE launch (its CTAs fill every
+      // SM for the whole run, so a separate pack kernel would not be scheduled next to it)
+      return launch_apply_uniform(ctx, L, d_x, d_y, factor, 3, ctx->stream);
+    }
     HPDG_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));                  // x is ready
     HPDG_CUDA(cudaStreamWaitEvent(ctx->stream_comm, ctx->ev_a, 0));
     if (launch_pack_traces(ctx, L, d_x, ctx->stream_comm)) return 1;

@@ -534,8 +534,8 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
   }
   if constexpr (N == 4 && TX == 4 && TY == 4 && TZ == 4 && MINB == 3 && !EARLY) {
     // default Q3 path: persistent CTAs with bulk-copy prefetch (apply_uniform_q3p.cuh); needs full tiles
-    if (ctx->variant != 40 && L.n[0] % 4 == 0 && L.n[1] % 4 == 0 && L.n[2] % 4 == 0 && L.n[0] <= 4092 && L.n[1] <= 4092 &&
-        L.n[2] <= 4092 && L.ndof < (1L << 31) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    // (not for the two-launch NCCL halo path: its interior launch would starve the halo stream's kernels of SM slots)
+    if (uniform_persistent(ctx, L) && part != 1 && part != 2 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
       static int slots = 0;
       if (!slots) {
         HPDG_CUDA(cudaFuncSetAttribute(hpdg_k_apply_q3_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, kQ3pSmemBytes));
@@ -546,8 +546,8 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
         slots = nsm * std::max(occ, 1);
       }
       if (!ctx->d_sched) {  // tile counters of the dynamic scheduler: {next, done} per launch kind
-        HPDG_CUDA(cudaMalloc(&ctx->d_sched, 8 * sizeof(int)));
-        HPDG_CUDA(cudaMemset(ctx->d_sched, 0, 8 * sizeof(int)));
+        HPDG_CUDA(cudaMalloc(&ctx->d_sched, 12 * sizeof(int)));
+        HPDG_CUDA(cudaMemset(ctx->d_sched, 0, 12 * sizeof(int)));
       }
       if (!L.d_tile_desc) {  // tile descriptors, once per level
         std::vector<int4> td((size_t)ntiles_total);
@@ -561,7 +561,22 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
       }
       const int grid = (int)std::min<long>(ntiles, ctx->q3p_grid > 0 ? ctx->q3p_grid : slots);
       if (ctx->variant != 42) {  // default: nodal arithmetic
-        hpdg_k_apply_q3_persist<<<grid, 256, kQ3pSmemBytes, stream>>>(P, static_cast<const int4*>(L.d_tile_desc), (int)ntiles, (int)ntiles_total, ctx->d_sched + 2 * (part & 3));
+        Q3pPack PK = {};
+        if (part == 3) {  // interior tiles first: by the time the CTAs reach the rank-boundary tiles the neighbours' traces have landed
+          if (uniform_tile_lists(ctx, L, TX, TY, TZ, P.bmode)) return 1;
+          P.tile_list = L.d_tiles_all; P.tile_rot = 0;
+        }
+        if (part == 3 && P.ghost_step > 0) {  // p2p halo: the tile kernel packs and publishes this rank's face traces itself
+          const int par = ctx->ghost.step & 1;
+          for (int f = 0; f < 6; f++) {
+            if (!ctx->ghost.active[f]) continue;
+            PK.out[f] = reinterpret_cast<double*>(ctx->ghost.peer_arena[f] + ctx->ghost.recv_off[f ^ 1][par]);
+            PK.flag[f] = reinterpret_cast<int*>(ctx->ghost.peer_arena[f] + ctx->ghost.flag_off) + (f ^ 1) * 2 + par;
+          }
+          PK.done = ctx->d_sched + 8;
+          PK.step = ctx->ghost.step;
+        }
+        hpdg_k_apply_q3_persist<<<grid, 256, kQ3pSmemBytes, stream>>>(P, static_cast<const int4*>(L.d_tile_desc), (int)ntiles, (int)ntiles_total, ctx->d_sched + 2 * (part & 3), PK);
       } else {  // variant 42: even/odd arithmetic (apply_uniform_q3e.cuh); fewer FP64 operations but measured slower (94.9 vs 91.7 us on cfg2)
         static Q3eTab E;
         for (int d = 0; d < 3; d++) {
@@ -598,6 +613,12 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
 
 int uniform_tile_height(const Level& L) {
   switch (L.p_uni) { case 4: return 3; case 5: return 2; default: return 4; }
+}
+
+int uniform_persistent(const Ctx* ctx, const Level& L) {
+  return uniform_supported(ctx, L) && L.p_uni == 3 && ctx->variant != 40 && (ctx->variant < 1 || ctx->variant > 22) &&
+         L.n[0] % 4 == 0 && L.n[1] % 4 == 0 && L.n[2] % 4 == 0 && L.n[0] <= 4092 && L.n[1] <= 4092 && L.n[2] <= 4092 &&
+         L.ndof < (1L << 31);
 }
 
 int uniform_supported(const Ctx* ctx, const Level& L) {

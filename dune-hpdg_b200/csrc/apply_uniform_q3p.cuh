@@ -169,6 +169,53 @@ __device__ __forceinline__ Q3pTrace q3p_halo(const UniParams<4>& P, int fl, cons
   return r;
 }
 
+// NVLink peer-memory halo, sender side, fused into the tile kernel (multi-GPU): before their first tile all CTAs
+// together compute the brick's boundary traces -- for brick face f = (d, s) and every boundary element and face node the
+// pair (der, val) of the element's DoF line normal to the face at side s -- and store them straight into the neighbours'
+// arenas; the last CTA to finish raises the neighbours' step flags.  No separate pack / flag kernels, no stream joins.
+struct Q3pPack {
+  double* out[6];  // receive buffer of the neighbour across face f (mapped peer memory), or null
+  int* flag[6];    // that neighbour's step flag for the face
+  int* done;       // local counter of CTAs that have finished packing
+  int step;        // 0: no packing in this launch
+};
+__device__ __forceinline__ void q3p_pack(const UniParams<4>& P, const Q3pPack& K) {
+  const double* __restrict__ x = P.x;
+  const int n0 = P.n[0], n1 = P.n[1], n2 = P.n[2];
+#pragma unroll 1
+  for (int f = 0; f < 6; f++) {
+    double* __restrict__ out = K.out[f];
+    if (!out) continue;
+    const int d = f >> 1, sd = f & 1;
+    const int na = d == 0 ? n1 : n0, nb = d == 2 ? n1 : n2;  // face element extents (low dim fastest)
+    const int total = na * nb * 16;
+    for (int t = blockIdx.x * 256 + threadIdx.x; t < total; t += gridDim.x * 256) {
+      const int node = t & 15, fe = t >> 4;
+      const int a = fe % na, b = fe / na;
+      const int pp = node & 3, q = node >> 2;
+      long e; int off, stride;
+      if (d == 0) { e = (sd ? n0 - 1 : 0) + (long)n0 * (a + (long)n1 * b); off = 4 * pp + 16 * q; stride = 1; }
+      else if (d == 1) { e = a + (long)n0 * ((sd ? n1 - 1 : 0) + (long)n1 * b); off = pp + 16 * q; stride = 4; }
+      else { e = a + (long)n0 * (b + (long)n1 * (sd ? n2 - 1 : 0)); off = pp + 4 * q; stride = 16; }
+      const double* line = x + e * 64 + off;
+      const double u0 = line[0], u1 = line[stride], u2 = line[2 * stride], u3 = line[3 * stride];
+      double der;
+      if (sd == 0) der = fma(P.g[0][0], u0, fma(P.g[0][1], u1, fma(P.g[0][2], u2, P.g[0][3] * u3)));
+      else der = fma(P.g[1][0], u0, fma(P.g[1][1], u1, fma(P.g[1][2], u2, P.g[1][3] * u3)));
+      reinterpret_cast<double2*>(out)[t] = make_double2(der, sd ? u3 : u0);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(K.done, 1) == (int)gridDim.x - 1) {
+    __threadfence_system();
+    for (int f = 0; f < 6; f++)
+      if (K.flag[f]) *reinterpret_cast<volatile int*>(K.flag[f]) = K.step;
+    __threadfence_system();
+    *K.done = 0;
+  }
+}
+
 __device__ __forceinline__ void q3p_bar_half(int half) {
   if (half) asm volatile("bar.sync 2, 128;\n" ::: "memory");
   else asm volatile("bar.sync 1, 128;\n" ::: "memory");
@@ -181,7 +228,7 @@ __device__ __forceinline__ void q3p_bar_half(int half) {
 // extern "C": the table reads name the kernel's parameter symbol (<kernel>_param_0)
 extern "C" __global__ void __launch_bounds__(256, 3)
 hpdg_k_apply_q3_persist(const __grid_constant__ hpdg::UniParams<4> P, const int4* __restrict__ tile_desc, const int ntiles,
-                        const int ntiles_total, int* __restrict__ sched) {
+                        const int ntiles_total, int* __restrict__ sched, const __grid_constant__ hpdg::Q3pPack PK) {
   using namespace hpdg;
   constexpr int N = 4, N2 = 16, N3 = 64;
   extern __shared__ __align__(128) double q3p_sm[];
@@ -215,6 +262,7 @@ hpdg_k_apply_q3_persist(const __grid_constant__ hpdg::UniParams<4> P, const int4
   __syncthreads();
   int t = blockIdx.x;
   if (t >= ntiles) return;
+  if (PK.step > 0) q3p_pack(P, PK);
   int4 td = descriptor(t);
   prefetch(threadIdx.x, td.x);
   uint32_t phase = 0;

@@ -140,6 +140,7 @@ int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double 
 // returns -1 if (dim, degree) has no specialised kernel
 int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream = nullptr);
 int uniform_supported(const Ctx* ctx, const Level& L);
+int uniform_persistent(const Ctx* ctx, const Level& L);  // the level's apply runs the persistent Q3 tile kernel
 int uniform_tile_height(const Level& L);
 int uniform_tile_lists(Ctx* ctx, Level& L, int TX, int TY, int TZ, const int* bmode);
 int launch_apply_uniform3(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream);
