@@ -260,8 +260,8 @@ def main():
             "config": {"workload": desc, "elements_per_gpu": list(n), "degree": degree, "dof_per_gpu": ndof,
                        "pgrid": list(pgrid), "sigma": 2.0, "dirichlet": True,
                        "l2": f"{NBUF} rotating (x,y) pairs of {ndof * 8 / 1e6:.0f} MB each: inputs larger than the 126 MB L2",
-                       "halo": ("none" if world == 1 else "NVLink peer-memory stores of face traces from the pack kernel + step flags; rank-boundary "
-                                "tiles of the one tile kernel wait on them" if p2p else
+                       "halo": ("none" if world == 1 else "NVLink peer-memory stores of the face traces + step flags, issued by the tile kernel itself "
+                                "before its first tile; its rank-boundary tiles (scheduled last) wait on the neighbours' flags" if p2p else
                                 "NCCL send/recv of face traces overlapped with interior tiles")},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "DoF/s", "h2d_bytes_per_step": ndof * 8, "d2h_bytes_per_step": ndof * 8,
@@ -269,7 +269,7 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
-                         "kernel": "k_apply_uniform", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": BYTES_PER_DOF * ndof},
+                         "kernel": "hpdg_k_apply_q3_persist" if degree == 3 else "k_apply_uniform", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": BYTES_PER_DOF * ndof},
         }
         if world == 1 and not args.no_cpu_baseline:
             rate, thr, sdof, reps, el = cpu_reference_rate(32, degree, 10.0)
