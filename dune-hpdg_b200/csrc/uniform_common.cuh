@@ -32,6 +32,21 @@ struct UniParams {
   int tile_rot;          // p2p halo: natural tile order rotated by this much, so the first wave is mid-domain tiles
 };
 
+// The GL nodes are symmetric about the element centre, so with R the node reflection: M and Dp commute with R, M is symmetric,
+// g_1 = -R g_0, A1 = -R A0, B1 = R B0.  The kernels read one representative of each group of equal table entries, which roughly
+// halves the number of distinct constants a pass needs (uniform-register pressure, LDCU count).
+template <int N> __host__ __device__ constexpr int sym_dp_idx(int i, int m) {
+  return (i * N + m <= (N - 1 - i) * N + (N - 1 - m)) ? i * N + m : (N - 1 - i) * N + (N - 1 - m);
+}
+template <int N> __host__ __device__ constexpr int sym_m_idx(int i, int m) {
+  int best = i * N + m;
+  const int c1 = m * N + i, c2 = (N - 1 - i) * N + (N - 1 - m), c3 = (N - 1 - m) * N + (N - 1 - i);
+  if (c1 < best) best = c1;
+  if (c2 < best) best = c2;
+  if (c3 < best) best = c3;
+  return best;
+}
+
 template <int N> struct Pitch {
   static constexpr int PP = (N % 2 == 0) ? N * N + 1 : N * N;  // z-plane pitch
   static constexpr int EP0 = N * PP;
@@ -54,7 +69,7 @@ __device__ __forceinline__ void pencil_apply(const UniParams<N>& P, const double
   for (int e = 0; e < T; e++) {
     double a = 0, b = 0;
 #pragma unroll
-    for (int m = 0; m < N; m++) { a = fma(P.g[0][m], v[e][m], a); b = fma(P.g[1][m], v[e][m], b); }
+    for (int m = 0; m < N; m++) { a = fma(P.g[0][m], v[e][m], a); b = fma(-P.g[0][N - 1 - m], v[e][m], b); }
     d0[e] = a; d1[e] = b;
   }
   if (pmode == 1) { pd = fma(-P.cohk[DIR], v[0][0], d0[0]); pv = -v[0][0]; }
@@ -81,9 +96,9 @@ __device__ __forceinline__ void pencil_apply(const UniParams<N>& P, const double
       for (int i = 0; i < N; i++) {
         double s = accin(e, i);
 #pragma unroll
-        for (int m = 0; m < N; m++) s = fma(P.Dp[DIR][i * N + m], v[e][m], s);
+        for (int m = 0; m < N; m++) s = fma(P.Dp[DIR][sym_dp_idx<N>(i, m)], v[e][m], s);
         s = fma(P.A0[DIR][i], qd, s); s = fma(P.B0[DIR][i], qv, s);
-        s = fma(P.A1[DIR][i], rd, s); s = fma(P.B1[DIR][i], rv, s);
+        s = fma(-P.A0[DIR][N - 1 - i], rd, s); s = fma(P.B0[DIR][N - 1 - i], rv, s);
         a[i] = s;
       }
       out(e, a);
@@ -98,7 +113,7 @@ __device__ __forceinline__ void mass_line(const UniParams<N>& P, double (&a)[N])
   for (int i = 0; i < N; i++) {
     double s = 0;
 #pragma unroll
-    for (int m = 0; m < N; m++) s = fma(SCALED ? P.Mf[i * N + m] : P.M[i * N + m], a[m], s);
+    for (int m = 0; m < N; m++) s = fma(SCALED ? P.Mf[sym_m_idx<N>(i, m)] : P.M[sym_m_idx<N>(i, m)], a[m], s);
     o[i] = s;
   }
 #pragma unroll
