@@ -100,7 +100,7 @@ void free_level(Level& L) {
   cudaFree(L.mg_x); cudaFree(L.mg_r); cudaFree(L.mg_t1); cudaFree(L.mg_t2);
   cudaFree(L.d_tiles_int); cudaFree(L.d_tiles_bnd); cudaFree(L.d_tiles_all); cudaFree(L.d_tile_desc);
   cudaFree(L.bcrs.d_rowptr); cudaFree(L.bcrs.d_col); cudaFree(L.bcrs.d_brow); cudaFree(L.bcrs.d_boff); cudaFree(L.bcrs.d_val);
-  cudaFree(L.bcrs.d_wave); cudaFree(L.bcrs.d_res);
+  cudaFree(L.bcrs.d_wave); cudaFree(L.bcrs.d_res); cudaFree(L.bcrs.d_l1reg);
   for (int f = 0; f < 6; f++) { cudaFree(L.cg.d_send[f]); cudaFree(L.cg.d_recv[f]); }
 }
 
@@ -681,6 +681,28 @@ int hpdg_blockgs_iterate(hpdg_ctx* ctx, int level, const double* h_b, double* h_
   HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_b, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
   HPDG_CUDA(cudaMemcpyAsync(ctx->d_out, h_x, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
   if (blockgs_iterate(ctx, *L, ctx->d_in, ctx->d_out)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(h_x, ctx->d_out, sizeof(double) * L->ndof, cudaMemcpyDeviceToHost, ctx->stream));
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int hpdg_l1_setup(hpdg_ctx* ctx, int level, const long* ghosts, long nghost) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  if (nghost > 0 && !ghosts) { ctx->err = "ghost index list is null"; return 1; }
+  return l1_setup(ctx, *L, ghosts, nghost);
+}
+int hpdg_l1_iterate_device(hpdg_ctx* ctx, int level, const double* d_b, double* d_x) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  if (blockgs_iterate(ctx, *L, d_b, d_x, 1)) return 1;
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int hpdg_l1_iterate(hpdg_ctx* ctx, int level, const double* h_b, double* h_x) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  if (ensure_stage(ctx, L->ndof)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_b, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
+  HPDG_CUDA(cudaMemcpyAsync(ctx->d_out, h_x, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
+  if (blockgs_iterate(ctx, *L, ctx->d_in, ctx->d_out, 1)) return 1;
   HPDG_CUDA(cudaMemcpyAsync(h_x, ctx->d_out, sizeof(double) * L->ndof, cudaMemcpyDeviceToHost, ctx->stream));
   HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;

@@ -140,9 +140,10 @@ __global__ void k_bcrs_mv(const long* __restrict__ rowptr, const int* __restrict
 }
 
 // GSCore on the block rows of one hyperplane: res holds r_i = b_i - sum_j A_ij x_j; x_i += (L_ii + D_ii)^-1 r_i
+// reg != nullptr: the L1Smoother's local solver (iterationsteps/l1smoother.hh:127-145): the diagonal is D_aa + reg_a
 __global__ void k_gscore_update(const long* __restrict__ rowptr, const int* __restrict__ col, const long* __restrict__ boff,
                                 const long* __restrict__ off, const double* __restrict__ val, const double* __restrict__ res,
-                                double* __restrict__ x, const int* __restrict__ rows) {
+                                double* __restrict__ x, const int* __restrict__ rows, const double* __restrict__ reg) {
   extern __shared__ double sc[];  // corr (n)
   const long i = rows[blockIdx.x];
   const int n = (int)(off[i + 1] - off[i]);
@@ -155,7 +156,8 @@ __global__ void k_gscore_update(const long* __restrict__ rowptr, const int* __re
     for (int w = 16; w > 0; w >>= 1) s += __shfl_xor_sync(0xffffffffu, s, w);
     if (lane == 0) {
       const double d = D[(size_t)a * n + a];
-      sc[a] = (fabs(d) == 0.) ? 0.0 : (res[off[i] + a] - s) / d;   // dynamicblockgs.hh:26-27,36
+      const double dr = reg ? d + reg[off[i] + a] : d;              // l1smoother.hh:144
+      sc[a] = (fabs(d) == 0.) ? 0.0 : (res[off[i] + a] - s) / dr;  // dynamicblockgs.hh:26-27,36
     }
     __syncwarp();
   }
@@ -251,9 +253,54 @@ int bcrs_mv(Ctx* ctx, Level& L, const double* x, double* y) {
   return 0;
 }
 
-int blockgs_iterate(Ctx* ctx, Level& L, const double* b, double* x) {
+// L1Smoother::preprocess (iterationsteps/l1smoother.hh:31-57): reg_r[j] = sum over the ghost block columns g != r of block row r
+// (each counted as often as it appears in the ghost list) of the l1 norm of row j of A[r][g].  One CTA per block row.
+__global__ void k_l1_regularization(const long* __restrict__ rowptr, const int* __restrict__ col, const long* __restrict__ boff,
+                                    const long* __restrict__ off, const double* __restrict__ val, const int* __restrict__ mult,
+                                    double* __restrict__ reg) {
+  const long r = blockIdx.x;
+  const int nr = (int)(off[r + 1] - off[r]);
+  for (int j = threadIdx.x; j < nr; j += blockDim.x) {
+    double s = 0;
+    for (long k = rowptr[r]; k < rowptr[r + 1]; k++) {
+      const long g = col[k];
+      if (g == r || mult[g] == 0) continue;
+      const int nc = (int)(off[g + 1] - off[g]);
+      const double* B = val + boff[k] + (size_t)j * nc;
+      double t = 0;
+      for (int c = 0; c < nc; c++) t += fabs(B[c]);
+      s += mult[g] * t;
+    }
+    reg[off[r] + j] = s;
+  }
+}
+
+int l1_setup(Ctx* ctx, Level& L, const long* ghosts, long nghost) {
   Bcrs& A = L.bcrs;
   if (!A.ready) { ctx->err = "hpdg_assemble_bcrs has not been called for this level"; return 1; }
+  std::vector<int> mult((size_t)L.nelem, 0);
+  for (long q = 0; q < nghost; q++) {
+    if (ghosts[q] < 0 || ghosts[q] >= L.nelem) { ctx->err = "ghost block index out of range"; return 1; }
+    mult[(size_t)ghosts[q]]++;
+  }
+  int* d_mult = nullptr;
+  HPDG_CUDA(cudaMalloc(&d_mult, sizeof(int) * mult.size()));
+  HPDG_CUDA(cudaMemcpy(d_mult, mult.data(), sizeof(int) * mult.size(), cudaMemcpyHostToDevice));
+  if (!A.d_l1reg) HPDG_CUDA(cudaMalloc(&A.d_l1reg, sizeof(double) * L.ndof));
+  k_l1_regularization<<<(unsigned)L.nelem, 64, 0, ctx->stream>>>(A.d_rowptr, A.d_col, A.d_boff, L.d_off, A.d_val, d_mult, A.d_l1reg);
+  ctx->launches++;
+  HPDG_CUDA(cudaGetLastError());
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_mult);
+  A.l1_ready = true;
+  return 0;
+}
+
+// l1 != 0: L1Smoother::iterate (l1smoother.hh:63-113) -- the same sweep with the regularised local solver
+int blockgs_iterate(Ctx* ctx, Level& L, const double* b, double* x, int l1) {
+  Bcrs& A = L.bcrs;
+  if (!A.ready) { ctx->err = "hpdg_assemble_bcrs has not been called for this level"; return 1; }
+  if (l1 && !A.l1_ready) { ctx->err = "hpdg_l1_setup has not been called for this level"; return 1; }
   const int ne = maxblock(L);
   const int thr = (std::min(std::max(32, (ne + 3) / 4 > 256 ? (ne + 3) / 4 : std::min(ne, 256)), 1024) + 31) / 32 * 32;
   const int nw = (int)A.wave_begin.size() - 1;
@@ -263,7 +310,7 @@ int blockgs_iterate(Ctx* ctx, Level& L, const double* b, double* x) {
     const int* rows = A.d_wave + A.wave_begin[w];
     // r_i = b_i - sum_j A_ij x_j over the whole row including the diagonal, with the current x (dynamicblockgs.hh:108-111)
     k_bcrs_mv<<<(unsigned)cnt, thr, ne * sizeof(double), ctx->stream>>>(A.d_rowptr, A.d_col, A.d_boff, L.d_off, A.d_val, x, A.d_res, rows, 1, b);
-    k_gscore_update<<<(unsigned)cnt, 32, ne * sizeof(double), ctx->stream>>>(A.d_rowptr, A.d_col, A.d_boff, L.d_off, A.d_val, A.d_res, x, rows);
+    k_gscore_update<<<(unsigned)cnt, 32, ne * sizeof(double), ctx->stream>>>(A.d_rowptr, A.d_col, A.d_boff, L.d_off, A.d_val, A.d_res, x, rows, l1 ? A.d_l1reg : nullptr);
     ctx->launches += 2;
   }
   HPDG_CUDA(cudaGetLastError());

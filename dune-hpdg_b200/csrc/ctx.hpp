@@ -57,6 +57,7 @@ struct Bcrs {
   std::vector<int> col;
   long* d_rowptr = nullptr; int* d_col = nullptr; int* d_brow = nullptr; long* d_boff = nullptr;
   double* d_val = nullptr; int* d_wave = nullptr; double* d_res = nullptr;
+  double* d_l1reg = nullptr; bool l1_ready = false;  // L1Smoother's diagonal regularisation (iterationsteps/l1smoother.hh:31-57)
 };
 
 struct Level {
@@ -157,7 +158,8 @@ int diag_block_device(Ctx* ctx, Level& L, long e, double* d_out);
 
 int bcrs_build(Ctx* ctx, Level& L);
 int bcrs_mv(Ctx* ctx, Level& L, const double* x, double* y);
-int blockgs_iterate(Ctx* ctx, Level& L, const double* b, double* x);
+int blockgs_iterate(Ctx* ctx, Level& L, const double* b, double* x, int l1 = 0);
+int l1_setup(Ctx* ctx, Level& L, const long* ghosts, long nghost);
 
 int launch_restrict(Ctx* ctx, Level& fine, Level& coarse, const double* xf, double* xc);
 int launch_prolong(Ctx* ctx, Level& fine, Level& coarse, const double* xc, double* xf);

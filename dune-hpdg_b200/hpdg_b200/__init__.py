@@ -65,6 +65,9 @@ SIGNATURES = {
     "hpdg_bcrs_mv_device": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "hpdg_blockgs_iterate": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "hpdg_blockgs_iterate_device": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "hpdg_l1_setup": (C.c_int, [_vp, C.c_int, _vp, C.c_long]),
+    "hpdg_l1_iterate": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "hpdg_l1_iterate_device": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "hpdg_restrict": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "hpdg_prolong": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "hpdg_restrict_device": (C.c_int, [_vp, C.c_int, _vp, _vp]),
@@ -337,6 +340,26 @@ class DynamicBlockGS:
     def iterate(self):
         c = self.mat_.ctx
         c._ck(lib().hpdg_blockgs_iterate(c._h, self.mat_.level, _hptr(self.rhs_), _hptr(self.x_)))
+
+
+class L1Smoother:
+    """`LinearIterationStep` face of the reference's smoother for MPI runs (iterationsteps/l1smoother.hh:20-145):
+    L1Smoother(ghosts); setProblem(mat, x, rhs); preprocess(); iterate()."""
+
+    def __init__(self, ghosts):
+        self.ghosts_ = np.ascontiguousarray(ghosts, dtype=np.int64)
+        self.mat_ = self.x_ = self.rhs_ = None
+
+    def setProblem(self, matrix, x, rhs):
+        self.mat_, self.x_, self.rhs_ = matrix, x, rhs
+
+    def preprocess(self):
+        c = self.mat_.ctx
+        c._ck(lib().hpdg_l1_setup(c._h, self.mat_.level, self.ghosts_.ctypes.data_as(C.c_void_p), len(self.ghosts_)))
+
+    def iterate(self):
+        c = self.mat_.ctx
+        c._ck(lib().hpdg_l1_iterate(c._h, self.mat_.level, _hptr(self.rhs_), _hptr(self.x_)))
 
 
 class OrderTransfer:

@@ -115,6 +115,14 @@ int hpdg_bcrs_mv_device(hpdg_ctx* ctx, int level, const double* d_x, double* d_y
  * ascending order, inner forward scalar GS sweep from zero.  x is updated in place. */
 int hpdg_blockgs_iterate(hpdg_ctx* ctx, int level, const double* h_b, double* h_x);
 int hpdg_blockgs_iterate_device(hpdg_ctx* ctx, int level, const double* d_b, double* d_x);
+/* L1Smoother (iterationsteps/l1smoother.hh:20-145), the reference's smoother for MPI runs: block Gauss-Seidel whose local solver
+ * (a forward scalar GS sweep from zero, :127-145) divides by D_aa + reg_a, where reg is the l1 norm of the rows of the blocks
+ * that couple an owned block row to a ghost block (preprocess(), :31-57).  hpdg_l1_setup = L1Smoother(ghosts) + preprocess():
+ * `ghosts` are block (element) indices, duplicates count again as in the reference; hpdg_l1_iterate = iterate() (:63-113),
+ * x updated in place.  Needs hpdg_assemble_bcrs first. */
+int hpdg_l1_setup(hpdg_ctx* ctx, int level, const long* ghosts, long nghost);
+int hpdg_l1_iterate(hpdg_ctx* ctx, int level, const double* h_b, double* h_x);
+int hpdg_l1_iterate_device(hpdg_ctx* ctx, int level, const double* d_b, double* d_x);
 
 /* -- p-transfer between level and level-1 (transferoperators/ordertransfer.hh:91-119) ------------- */
 int hpdg_restrict(hpdg_ctx* ctx, int fine_level, const double* h_fine, double* h_coarse);

@@ -169,6 +169,22 @@ class DynamicBlockGS {
   const V* rhs_ = nullptr;
 };
 
+// Dune::HPDG::L1Smoother<Matrix, Vector> (iterationsteps/l1smoother.hh:20-145): L1Smoother(ghosts); setProblem(mat, x, rhs);
+// preprocess(); iterate()
+template <class V>
+class L1Smoother {
+ public:
+  explicit L1Smoother(const std::vector<std::size_t>& ghosts) : ghosts_(ghosts.begin(), ghosts.end()) {}
+  void setProblem(const AssembledMatrix& m, V& x, const V& rhs) { mat_ = &m; x_ = &x; rhs_ = &rhs; }
+  void preprocess() { mat_->context()->check(hpdg_l1_setup(mat_->context()->handle(), mat_->level(), ghosts_.data(), (long)ghosts_.size())); }
+  void iterate() { mat_->context()->check(hpdg_l1_iterate(mat_->context()->handle(), mat_->level(), rhs_->data(), x_->data())); }
+  const AssembledMatrix* mat_ = nullptr;
+  V* x_ = nullptr;
+  const V* rhs_ = nullptr;
+ private:
+  std::vector<long> ghosts_;
+};
+
 template <class V> using Fn = std::function<void(V&, const V&)>;
 
 template <class V>

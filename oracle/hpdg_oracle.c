@@ -784,6 +784,63 @@ void orc_blockgs_iterate(const obcrs* A, const double* b, double* x) {
   free(ri);
 }
 
+/* L1Smoother::preprocess (iterationsteps/l1smoother.hh:31-57): for every ghost block index g (list order, duplicates
+ * count again) and every block row r != g in the pattern of row g, add to reg_r[j] the l1 norm of row j of block A[r][g]. */
+void orc_l1_regularization(const obcrs* A, const long* ghosts, long nghost, double* reg) {
+  long N = A->voff[A->nrows];
+  for (long i = 0; i < N; i++) reg[i] = 0.0;                                  /* :33 */
+  for (long q = 0; q < nghost; q++) {
+    long g = ghosts[q];
+    for (long k = A->rowptr[g]; k < A->rowptr[g + 1]; k++) {                  /* :41 */
+      long row = A->col[k];
+      if (row == g) continue;                                                 /* :45-46 */
+      const double* B = NULL; int c = 0;
+      for (long kk = A->rowptr[row]; kk < A->rowptr[row + 1]; kk++)           /* m[row][ghostIdx] :47 */
+        if (A->col[kk] == g) { B = A->val + A->boff[kk]; c = A->bcols[g]; }
+      if (!B) continue;
+      int r = A->brows[row];
+      for (int j = 0; j < r; j++)                                             /* :49-54 */
+        for (int e = 0; e < c; e++) reg[A->voff[row] + j] += fabs(B[j * c + e]);
+    }
+  }
+}
+
+/* L1Smoother::gs (l1smoother.hh:127-145): forward scalar GS sweep from zero on (M + diag(d)), tolerance 0 */
+static void gs_l1(const double* M, int n, const double* b, const double* d, double* x) {
+  for (int i = 0; i < n; i++) x[i] = 0;
+  for (int i = 0; i < n; i++) {
+    double mii = M[i * n + i];
+    if (fabs(mii) <= 0.0) continue;                                           /* :136-137 */
+    double xi = b[i];
+    for (int j = 0; j < n; j++) if (j != i) xi -= M[i * n + j] * x[j];
+    x[i] = xi / (mii + d[i]);                                                 /* :144 */
+  }
+}
+
+/* L1Smoother::iterate (l1smoother.hh:63-113): block rows in ascending order (ghost rows included, :71-73) */
+void orc_l1_iterate(const obcrs* A, const double* reg, const double* b, double* x) {
+  int mx = 0;
+  for (long i = 0; i < A->nrows; i++) if (A->brows[i] > mx) mx = A->brows[i];
+  double* ri = (double*)malloc(sizeof(double) * mx * 2);
+  double* corr = ri + mx;
+  for (long i = 0; i < A->nrows; i++) {
+    int r = A->brows[i];
+    memcpy(ri, b + A->voff[i], sizeof(double) * r);                           /* r = b :67 */
+    const double* diag = NULL;
+    for (long k = A->rowptr[i]; k < A->rowptr[i + 1]; k++) {                  /* :91-94 */
+      int j = A->col[k], c = A->bcols[j];
+      const double* B = A->val + A->boff[k];
+      const double* xj = x + A->voff[j];
+      if (j == i) diag = B;
+      for (int a = 0; a < r; a++)
+        for (int bb = 0; bb < c; bb++) ri[a] -= B[a * c + bb] * xj[bb];
+    }
+    gs_l1(diag, r, ri, reg + A->voff[i], corr);                               /* :105 */
+    for (int a = 0; a < r; a++) x[A->voff[i] + a] += corr[a];                 /* :107-109 */
+  }
+  free(ri);
+}
+
 /* ipdgblockjacobi.hh:58-152: the diagonal block as the matrix-free block Jacobi builds it */
 void orc_diag_block_mf(const omesh* m, long e, double* out) {
   int dim = m->dim, p = m->deg[e], n = p + 1, ne = ipow(n, dim);

@@ -60,6 +60,9 @@ void   orc_bcrs_diag_block(const obcrs* A, long e, double* out);
 /* --- smoothers ------------------------------------------------------------ */
 /* one DynamicBlockGS::iterate with GSCore inner solver (dynamicblockgs.hh:17-40,94-126) */
 void   orc_blockgs_iterate(const obcrs* A, const double* b, double* x);
+/* L1Smoother (iterationsteps/l1smoother.hh:20-145): preprocess -> reg (one double per DoF), then iterate */
+void   orc_l1_regularization(const obcrs* A, const long* ghosts, long nghost, double* reg);
+void   orc_l1_iterate(const obcrs* A, const double* reg, const double* b, double* x);
 /* matrix-free block Jacobi c = sum_e P_e^T solve(D_e, P_e r)  (ipdgblockjacobi.hh:58-178)
  * local_solver: 0 = exact (dense Cholesky), 1 = one scalar GS sweep from zero (testdgblockjacobi.cc:63-76) */
 void   orc_blockjacobi_apply(const omesh* m, const double* r, double* c, double factor, int local_solver);

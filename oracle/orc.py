@@ -54,6 +54,8 @@ def lib():
         "orc_bcrs_frobenius_diff": (C.c_double, [vp, vp]),
         "orc_bcrs_diag_block": (None, [vp, C.c_long, _dp]),
         "orc_blockgs_iterate": (None, [vp, _dp, _dp]),
+        "orc_l1_regularization": (None, [vp, _lp, C.c_long, _dp]),
+        "orc_l1_iterate": (None, [vp, _dp, _dp, _dp]),
         "orc_blockjacobi_apply": (None, [vp, _dp, _dp, C.c_double, C.c_int]),
         "orc_diag_block_mf": (None, [vp, C.c_long, _dp]),
         "orc_transfer_matrix": (None, [C.c_int, C.c_int, C.c_int, _dp]),
@@ -160,6 +162,18 @@ class Matrix:
 
     def blockgs_iterate(self, b, x):
         lib().orc_blockgs_iterate(self.h, np.ascontiguousarray(b), x)
+        return x
+
+    def l1_regularization(self, ghosts):
+        """L1Smoother::preprocess (iterationsteps/l1smoother.hh:31-57)."""
+        g = np.ascontiguousarray(ghosts, dtype=np.int64)
+        reg = np.zeros(self.mesh.ndof)
+        lib().orc_l1_regularization(self.h, g, len(g), reg)
+        return reg
+
+    def l1_iterate(self, reg, b, x):
+        """L1Smoother::iterate (iterationsteps/l1smoother.hh:63-113)."""
+        lib().orc_l1_iterate(self.h, np.ascontiguousarray(reg), np.ascontiguousarray(b), x)
         return x
 
     def frobenius_diff(self, other):

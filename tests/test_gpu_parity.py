@@ -309,6 +309,45 @@ def test_assembled_hp_and_blockgs(orc, hp, dim, n):
         assert rel(xg, xr) < 1e-11
 
 
+@pytest.mark.parametrize("dim,n", [(2, (6, 5)), (3, (3, 4, 2))])
+def test_l1_smoother(orc, hp, dim, n):
+    # iterationsteps/l1smoother.hh:20-145 on the device against the oracle: ghost list with a duplicate, hp degrees, 4 sweeps
+    rng = np.random.default_rng(7)
+    ne = int(np.prod(n))
+    deg = rng.integers(1, 4, ne).astype(np.int32)
+    m = orc.Mesh(n, degree=deg, sigma=2.0, dirichlet=True)
+    A = m.assemble()
+    ghosts = [0, n[0] - 1, n[0] - 1, ne - 1, ne // 2]
+    reg = A.l1_regularization(ghosts)
+    ctx = hp.Context(n, degree=deg, sigma=2.0, dirichlet=True)
+    G = hp.AssembledMatrix(ctx)
+    b = orc.fill_random(m.ndof)
+    x, xr = np.ones(m.ndof), np.ones(m.ndof)
+    sm = hp.L1Smoother(ghosts)
+    sm.setProblem(G, x, b)
+    sm.preprocess()
+    for _ in range(4):
+        sm.iterate()
+        A.l1_iterate(reg, b, xr)
+    assert rel(x, xr) < TOL
+    # an l1 sweep is not a plain block-GS sweep (the regularisation is active) ...
+    xg = np.ones(m.ndof)
+    for _ in range(4):
+        A.blockgs_iterate(b, xg)
+    assert rel(x, xg) > 1e-6
+    # ... and iterate() before preprocess() is an error, as is a ghost index outside the matrix
+    ctx2 = hp.Context(n, degree=deg)
+    G2 = hp.AssembledMatrix(ctx2)
+    bad = hp.L1Smoother([0])
+    bad.setProblem(G2, np.ones(m.ndof), b)
+    with pytest.raises(hp.HpdgError):
+        bad.iterate()
+    bad2 = hp.L1Smoother([ne])
+    bad2.setProblem(G2, np.ones(m.ndof), b)
+    with pytest.raises(hp.HpdgError):
+        bad2.preprocess()
+
+
 def test_dynamicblockgs_small_system_on_device(orc, hp):
     # test/test_dynamicblockgs.cc:24-44 on the device: 2x2, k=2, sigma 1.5, b = 1, x0 = 1, 100 sweeps -> |b - Ax| < 1e-13
     ctx = hp.Context((2, 2), degree=2, sigma=1.5, dirichlet=True)
