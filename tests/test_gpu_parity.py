@@ -361,6 +361,23 @@ def test_dynamicblockgs_small_system_on_device(orc, hp):
     assert np.linalg.norm(b - G.mv(x)) < 1e-13
 
 
+def test_vcycle_q3_fine_level_persistent_kernel(orc, hp):
+    # Q3 -> Q1 (solversetup.hh:77,94 for pmax = 3) on a mesh whose fine level runs the persistent Q3 kernel: covers its
+    # accumulate mode (r -= A c is fused into the operator kernel)
+    n = (8, 4, 4)
+    fine = orc.Mesh(n, degree=3)
+    l0 = fine.coarsen(1)
+    b = orc.fill_random(fine.ndof)
+    x0 = orc.fill_random(fine.ndof, seed=3) * 0.1
+    xr, rr = orc.vcycle([l0, fine], None, x0, b, smoother=1, damping=0.75)
+    ctx = hp.Context(n, degree=3)
+    ctx.build_p_hierarchy()
+    mg = hp.Multigrid(ctx, form=hp.JACOBI_FD, damping=0.75)
+    x, bb = x0.copy(), b.copy()
+    mg.apply(x, bb)
+    assert rel(x, xr) < 1e-11 and rel(bb, rr) < 1e-10
+
+
 def test_vcycle_with_reference_default_smoother(orc, hp):
     # the reference's own p-MG configuration (solversetup.hh:139-145,198-215): DynamicBlockGS on the Galerkin level matrices
     n = (3, 3, 3)
