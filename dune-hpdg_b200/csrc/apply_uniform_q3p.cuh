@@ -3,19 +3,23 @@
 // Same operator, formulation and five pencil passes as k_apply_uniform (apply_uniform.cu; reference: Operator::apply over
 // IPDGOperator, matrix-free/operator.hh:41-56, matrix-free/localoperators/ipdgoperator.hh:80-390).  What changes is how the
 // DoF blocks move:
-//  * CTAs are persistent (one per SM slot, tiles strided by the grid, x-fastest so concurrent CTAs work on neighbouring
-//    tiles and their halo reads hit L2).  The 4x4x4-element tile of u arrives in shared memory by 16 bulk async copies
-//    (cp.async.bulk, 2 KB each: the four x-contiguous elements of a row are contiguous in a DynamicBlockVector) that
-//    complete on an mbarrier.  The copies for tile t+1 are issued right after pass 3 of tile t (the last reader of the
-//    u buffer), so they are in flight during passes 4 and 5 and no thread ever waits on a global load of u.
+//  * CTAs are persistent (one per SM slot; tiles are handed out x-fastest by a global counter, so concurrent CTAs work on
+//    neighbouring tiles and their halo reads hit L2, and the last wave stays short).  The 4x4x4-element tile of u arrives
+//    in shared memory by 16 bulk async copies (cp.async.bulk, 2 KB each: the four x-contiguous elements of a row are
+//    contiguous in a DynamicBlockVector) that complete on an mbarrier.  The copies for the next tile are issued, per CTA
+//    half, right after pass 3 of the current one (the last reader of the u buffer), so they are in flight during passes
+//    4 and 5 and no thread waits on a global load of u.
 //  * Shared memory is unpadded (2 x 32 KB per CTA -> 3 CTAs/SM).  Pass 1 rewrites u in place into a swizzled layout:
 //    within the 128-byte row of an (element, z-plane k) the 32-byte x-line j sits at line slot j^k, rotated by 16 bytes
 //    for odd element layers.  With that, all three pencil directions are bank-conflict free: z-pencils (64-bit, a half
 //    warp = the 16 nodes of a plane), y-pencils (64-bit, half warp = 4 i x 4 k), x-pencils (128-bit, quarter warp = 4 j x
 //    2 element layers).  The in-place rewrite only permutes data among the lanes of one half warp (they own the column of
 //    elements they read), so a __syncwarp between the reads and the writes is all it needs.
-//  * Pass 5 and the next tile's pass 1 use the same thread -> column mapping, so no block barrier separates two tiles.
-// Requires brick extents that are multiples of 4 (otherwise the masked k_apply_uniform is used).
+//  * Passes 2-4 couple the element layers {0,1} and {2,3} of a tile separately: 128-thread named barriers.  Pass 5 and the
+//    next tile's pass 1 use the same thread -> column mapping, so no block barrier separates two tiles.
+//  * Multi-GPU (NVLink peer-memory halo): the CTAs pack and publish the brick's boundary traces before their first tile.
+// Requires brick extents that are multiples of 4 (otherwise the masked k_apply_uniform is used).  Measurements, what bounds
+// the kernel and what was tried: DESIGN.md section 6.
 #pragma once
 #include <cstddef>
 #include <cstdint>
