@@ -98,7 +98,7 @@ void free_level(Level& L) {
   cudaFree(L.d_deg); cudaFree(L.d_pdeg); cudaFree(L.d_off); cudaFree(L.d_elist);
   cudaFree(L.jd.d_inv); cudaFree(L.jf.d_fac); cudaFree(L.jf.d_idx);
   cudaFree(L.mg_x); cudaFree(L.mg_r); cudaFree(L.mg_t1); cudaFree(L.mg_t2);
-  cudaFree(L.d_tiles_int); cudaFree(L.d_tiles_bnd); cudaFree(L.d_tiles_all); cudaFree(L.d_tile_desc);
+  cudaFree(L.d_tiles_int); cudaFree(L.d_tiles_bnd); cudaFree(L.d_tiles_all); cudaFree(L.d_tile_desc); cudaFree(L.d_jinv);
   cudaFree(L.bcrs.d_rowptr); cudaFree(L.bcrs.d_col); cudaFree(L.bcrs.d_brow); cudaFree(L.bcrs.d_boff); cudaFree(L.bcrs.d_val);
   cudaFree(L.bcrs.d_wave); cudaFree(L.bcrs.d_res); cudaFree(L.bcrs.d_l1reg);
   for (int f = 0; f < 6; f++) { cudaFree(L.cg.d_send[f]); cudaFree(L.cg.d_recv[f]); }
@@ -786,6 +786,21 @@ int hpdg_time_apply_device(hpdg_ctx* ctx, int level, const double* d_x, double* 
   HPDG_CUDA(cudaEventCreate(&e0)); HPDG_CUDA(cudaEventCreate(&e1));
   HPDG_CUDA(cudaEventRecord(e0, ctx->stream));
   for (int i = 0; i < reps; i++) if (op_apply_async(ctx, *L, d_x, d_y, 1.0)) return 1;
+  HPDG_CUDA(cudaEventRecord(e1, ctx->stream));
+  HPDG_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  HPDG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_per_apply = ms / reps;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+int hpdg_time_jacobi_device(hpdg_ctx* ctx, int level, int form, const double* d_r, double* d_c, double damping, int reps,
+                            float* ms_per_apply) {
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  cudaEvent_t e0, e1;
+  HPDG_CUDA(cudaEventCreate(&e0)); HPDG_CUDA(cudaEventCreate(&e1));
+  HPDG_CUDA(cudaEventRecord(e0, ctx->stream));
+  for (int i = 0; i < reps; i++) if (jacobi_async(ctx, *L, form, d_r, d_c, damping)) return 1;
   HPDG_CUDA(cudaEventRecord(e1, ctx->stream));
   HPDG_CUDA(cudaEventSynchronize(e1));
   float ms = 0;

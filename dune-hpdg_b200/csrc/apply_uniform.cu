@@ -545,20 +545,7 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
         HPDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hpdg_k_apply_q3_persist, 256, kQ3pSmemBytes));
         slots = nsm * std::max(occ, 1);
       }
-      if (!ctx->d_sched) {  // tile counters of the dynamic scheduler: {next, done} per launch kind
-        HPDG_CUDA(cudaMalloc(&ctx->d_sched, 12 * sizeof(int)));
-        HPDG_CUDA(cudaMemset(ctx->d_sched, 0, 12 * sizeof(int)));
-      }
-      if (!L.d_tile_desc) {  // tile descriptors, once per level
-        std::vector<int4> td((size_t)ntiles_total);
-        for (int tz = 0, i = 0; tz < P.ntile[2]; tz++) for (int ty = 0; ty < P.ntile[1]; ty++) for (int tx = 0; tx < P.ntile[0]; tx++, i++) {
-          const int fl = (tx == 0) | (tx == P.ntile[0] - 1) << 1 | (ty == 0) << 2 | (ty == P.ntile[1] - 1) << 3 |
-                         (tz == 0) << 4 | (tz == P.ntile[2] - 1) << 5;
-          td[i] = make_int4(4 * tx + L.n[0] * (4 * ty + L.n[1] * 4 * tz), tx | ty << 10 | tz << 20, fl, 0);
-        }
-        HPDG_CUDA(cudaMalloc(&L.d_tile_desc, sizeof(int4) * td.size()));
-        HPDG_CUDA(cudaMemcpy(L.d_tile_desc, td.data(), sizeof(int4) * td.size(), cudaMemcpyHostToDevice));
-      }
+      if (q3p_level_setup(ctx, L)) return 1;
       const int grid = (int)std::min<long>(ntiles, ctx->q3p_grid > 0 ? ctx->q3p_grid : slots);
       if (ctx->variant != 42) {  // default: nodal arithmetic
         Q3pPack PK = {};
@@ -613,6 +600,26 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
 
 int uniform_tile_height(const Level& L) {
   switch (L.p_uni) { case 4: return 3; case 5: return 2; default: return 4; }
+}
+
+// what the persistent Q3 kernels (operator apply, block Jacobi) need per context / level: the tile counters of the dynamic
+// scheduler and the tile descriptors {first element, packed tile coordinates, brick-face bits, 0} of the 4x4x4 tiling
+int q3p_level_setup(Ctx* ctx, Level& L) {
+  if (!ctx->d_sched) {  // {next, done} per launch kind: apply parts 0..3 -> ints 0..7, halo pack 8, block Jacobi 10..11
+    HPDG_CUDA(cudaMalloc(&ctx->d_sched, 12 * sizeof(int)));
+    HPDG_CUDA(cudaMemset(ctx->d_sched, 0, 12 * sizeof(int)));
+  }
+  if (!L.d_tile_desc) {
+    const int nt[3] = {L.n[0] / 4, L.n[1] / 4, L.n[2] / 4};
+    std::vector<int4> td((size_t)nt[0] * nt[1] * nt[2]);
+    for (int tz = 0, i = 0; tz < nt[2]; tz++) for (int ty = 0; ty < nt[1]; ty++) for (int tx = 0; tx < nt[0]; tx++, i++) {
+      const int fl = (tx == 0) | (tx == nt[0] - 1) << 1 | (ty == 0) << 2 | (ty == nt[1] - 1) << 3 | (tz == 0) << 4 | (tz == nt[2] - 1) << 5;
+      td[i] = make_int4(4 * tx + L.n[0] * (4 * ty + L.n[1] * 4 * tz), tx | ty << 10 | tz << 20, fl, 0);
+    }
+    HPDG_CUDA(cudaMalloc(&L.d_tile_desc, sizeof(int4) * td.size()));
+    HPDG_CUDA(cudaMemcpy(L.d_tile_desc, td.data(), sizeof(int4) * td.size(), cudaMemcpyHostToDevice));
+  }
+  return 0;
 }
 
 int uniform_persistent(const Ctx* ctx, const Level& L) {

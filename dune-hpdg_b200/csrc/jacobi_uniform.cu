@@ -11,9 +11,14 @@
 //   P4 x-pencils: Vx                     P5 z-pencils: damping * Vz -> global c
 // Algorithmic HBM traffic: 16 B/DoF.
 #include <algorithm>
+#include <cmath>
+#include <cstdint>
 #include <cstdio>
+#include <cstring>
+#include <vector>
 
 #include "ctx.hpp"
+#include "jacobi_uniform_q3p.cuh"
 
 namespace hpdg {
 
@@ -221,9 +226,101 @@ static int launch_fdu(Ctx* ctx, Level& L, const double* r, double* c, double dam
   return 0;
 }
 
+// 1-D generalised eigen-decomposition of the diagonal block's factor in direction d for a boundary variant
+// (bit 0: first element of its line at a domain boundary, bit 1: last); see launch_fdu
+static void fd_factor(const Ctx* ctx, const Level& L, int N, int d, int var, double* V, double* lam) {
+  const DegTable& T = host_tables().deg[N - 1];
+  const double cpen = ctx->sigma * (double)L.pen_uni * L.pen_uni;
+  double kappa = 1.0 / L.h[d];
+  for (int dd = 0; dd < 3; dd++) if (dd != d) kappa *= L.h[dd];
+  double w[2], cc[2];
+  for (int s = 0; s < 2; s++) {
+    const bool at_bnd = (var >> s) & 1;
+    if (!at_bnd) { w[s] = 0.5; cc[s] = cpen; }                 // interior face (ipdgblockjacobi.hh:69,80-86)
+    else if (ctx->dirichlet) { w[s] = 1.0; cc[s] = cpen; }     // Dirichlet face (:74)
+    else { w[s] = 0.0; cc[s] = 0.0; }                          // natural boundary (:72-73)
+  }
+  std::vector<double> D((size_t)N * N), M((size_t)N * N);
+  for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) {
+    double v = kappa * T.S[i * kMaxN + j];
+    for (int s = 0; s < 2; s++) {
+      const double nu = s ? 1.0 : -1.0;
+      v += -w[s] * nu * kappa * (T.t[s][i] * T.g[s][j] + T.g[s][i] * T.t[s][j]) + cc[s] * T.t[s][i] * T.t[s][j];
+    }
+    D[i * N + j] = v; M[i * N + j] = T.M[i * kMaxN + j];
+  }
+  gen_eig(N, D.data(), M.data(), V, lam);
+}
+
+// persistent Q3 kernel (jacobi_uniform_q3p.cuh): same conditions as the persistent operator kernel.
+// Returns -1 if the interior factor does not have the mirror structure the kernel relies on (then the tile kernel runs).
+static int launch_q3j(Ctx* ctx, Level& L, const double* r, double* c, double damping) {
+  static Q3jParams P;
+  if (L.q3j_state < 0) return -1;
+  double (&lam)[3][3][4] = L.q3j_lam;
+  if (L.q3j_state == 0) {  // once per level: the 1-D factors (the context's sigma / boundary type are fixed at creation)
+    L.q3j_state = -1;
+    for (int d = 0; d < 3; d++)
+      for (int var = 0; var < 3; var++) fd_factor(ctx, L, 4, d, var, L.q3j_V[d][var], lam[d][var]);
+    // interior factor: reorder the eigenpairs to even, odd, even, odd under the node reflection i -> 3 - i
+    for (int d = 0; d < 3; d++) {
+      double* V = L.q3j_V[d][0];
+      int even[4], odd[4], ne = 0, no = 0;
+      for (int k = 0; k < 4; k++) {
+        double se = 0, so = 0, nn = 0;
+        for (int i = 0; i < 4; i++) {
+          se += std::fabs(V[i * 4 + k] - V[(3 - i) * 4 + k]); so += std::fabs(V[i * 4 + k] + V[(3 - i) * 4 + k]); nn += std::fabs(V[i * 4 + k]);
+        }
+        if (se <= 1e-13 * nn) even[ne++] = k; else if (so <= 1e-13 * nn) odd[no++] = k; else return -1;
+      }
+      if (ne != 2 || no != 2) return -1;
+      const int order[4] = {even[0], odd[0], even[1], odd[1]};
+      double Vn[16], ln[4];
+      for (int k = 0; k < 4; k++) { ln[k] = lam[d][0][order[k]]; for (int i = 0; i < 4; i++) Vn[i * 4 + k] = V[i * 4 + order[k]]; }
+      for (int k = 0; k < 4; k++) { lam[d][0][k] = ln[k]; for (int i = 0; i < 4; i++) V[i * 4 + k] = Vn[i * 4 + k]; }
+    }
+    L.q3j_state = 1;
+  }
+  std::memcpy(P.V, L.q3j_V, sizeof(P.V));
+  if (q3p_level_setup(ctx, L)) return 1;
+  if (!L.d_jinv || L.jinv_damping != damping) {
+    std::vector<double> inv(27 * 64);
+    for (int vx = 0; vx < 3; vx++) for (int vz = 0; vz < 3; vz++) for (int vy = 0; vy < 3; vy++)
+      for (int i = 0; i < 4; i++) for (int k = 0; k < 4; k++) for (int j = 0; j < 4; j++)
+        inv[(size_t)((vx * 3 + vz) * 3 + vy) * 64 + (i * 4 + k) * 4 + j] = damping / (lam[0][vx][i] + lam[1][vy][j] + lam[2][vz][k]);
+    if (!L.d_jinv) HPDG_CUDA(cudaMalloc(&L.d_jinv, sizeof(double) * inv.size()));
+    HPDG_CUDA(cudaMemcpyAsync(L.d_jinv, inv.data(), sizeof(double) * inv.size(), cudaMemcpyHostToDevice, ctx->stream));
+    HPDG_CUDA(cudaStreamSynchronize(ctx->stream));  // inv is a local
+    L.jinv_damping = damping;
+  }
+  for (int f = 0; f < 6; f++) P.bnd[f] = ctx->bnd_is_rank[f] ? 0 : 1;
+  for (int d = 0; d < 3; d++) P.n[d] = L.n[d];
+  P.r = r; P.c = c; P.xacc = ctx->fuse_xacc; P.inv = L.d_jinv;
+  P.tile_desc = static_cast<const int4*>(L.d_tile_desc);
+  P.sched = ctx->d_sched + 10;
+  P.ntiles = (L.n[0] / 4) * (L.n[1] / 4) * (L.n[2] / 4);
+  static int slots = 0;
+  if (!slots) {
+    HPDG_CUDA(cudaFuncSetAttribute(hpdg_k_jacobi_fd_q3_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, kQ3jSmemBytes));
+    int nsm = 0, occ = 0;
+    HPDG_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+    HPDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hpdg_k_jacobi_fd_q3_persist, 256, kQ3jSmemBytes));
+    slots = nsm * std::max(occ, 1);
+  }
+  const int grid = std::min(P.ntiles, ctx->q3p_grid > 0 ? ctx->q3p_grid : slots);
+  hpdg_k_jacobi_fd_q3_persist<<<grid, 256, kQ3jSmemBytes, ctx->stream>>>(P);
+  ctx->launches++;
+  HPDG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // returns -1 when there is no specialised kernel for this level
 int jacobi_apply_fd_uniform(Ctx* ctx, Level& L, const double* r, double* c, double damping) {
   if (!uniform_supported(ctx, L)) return -1;
+  if (uniform_persistent(ctx, L) && (reinterpret_cast<uintptr_t>(r) & 15) == 0) {
+    const int rc = launch_q3j(ctx, L, r, c, damping);
+    if (rc >= 0) return rc;
+  }
   switch (L.p_uni) {
     case 1: return launch_fdu<2, 4, 4, 4, 4>(ctx, L, r, c, damping);
     case 2: return launch_fdu<3, 4, 4, 4, 4>(ctx, L, r, c, damping);

@@ -79,6 +79,7 @@ SIGNATURES = {
     "hpdg_launch_count": (C.c_long, [_vp]),
     "hpdg_uses_uniform_kernel": (C.c_int, [_vp, C.c_int]),
     "hpdg_time_apply_device": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.POINTER(C.c_float)]),
+    "hpdg_time_jacobi_device": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_double, C.c_int, C.POINTER(C.c_float)]),
 }
 
 
@@ -289,6 +290,12 @@ class BlockJacobi:
 
     def apply_device(self, dr, dc):
         self.ctx._ck(lib().hpdg_jacobi_apply_device(self.ctx._h, self.level, self.form, dr, dc, self.damping))
+
+    def time_device(self, dr, dc, reps):
+        """ms per application, CUDA events around `reps` back-to-back launches on the context stream"""
+        ms = C.c_float()
+        self.ctx._ck(lib().hpdg_time_jacobi_device(self.ctx._h, self.level, self.form, dr, dc, self.damping, reps, C.byref(ms)))
+        return ms.value
 
     @property
     def bytes(self):

@@ -149,6 +149,9 @@ long hpdg_launch_count(const hpdg_ctx* ctx);      /* kernels launched so far by 
 int hpdg_uses_uniform_kernel(const hpdg_ctx* ctx, int level);
 /* time `reps` back-to-back operator applies with CUDA events on the context stream; ms per apply */
 int hpdg_time_apply_device(hpdg_ctx* ctx, int level, const double* d_x, double* d_y, int reps, float* ms_per_apply);
+/* the same for `reps` back-to-back block-Jacobi applications c = damping * D^-1 r (hpdg_jacobi_setup first) */
+int hpdg_time_jacobi_device(hpdg_ctx* ctx, int level, int form, const double* d_r, double* d_c, double damping, int reps,
+                            float* ms_per_apply);
 
 #ifdef __cplusplus
 }

@@ -183,6 +183,26 @@ def test_block_jacobi_vs_oracle(orc, hp, form):
                 assert np.abs(jac.diag_block(e) - m.diag_block_mf(e)).max() < 1e-12 * np.abs(m.diag_block_mf(e)).max()
 
 
+def test_fd_jacobi_persistent_q3(orc, hp):
+    # uniform Q3 bricks whose extents are multiples of 4 run the persistent tile kernel (jacobi_uniform_q3p.cuh); variant 40
+    # keeps the one-tile-per-CTA kernel: both must match the oracle's exact block solve (ipdgblockjacobi.hh:58-178)
+    for n, L, dirichlet in [((4, 4, 4), None, True), ((8, 4, 12), [1.0, 1.5, 0.5], True), ((8, 8, 8), None, False),
+                            ((12, 4, 4), [2.0, 1.0, 1.0], False)]:
+        m = orc.Mesh(n, L=L, degree=3, dirichlet=dirichlet)
+        r = orc.fill_random(m.ndof)
+        ref = m.blockjacobi_apply(r, factor=0.75)
+        for variant in (0, 40):
+            ctx = hp.Context(n, L=L, degree=3, dirichlet=dirichlet)
+            ctx.set_option("variant", variant)
+            jac = hp.BlockJacobi(ctx, form=hp.JACOBI_FD, damping=0.75)
+            before = ctx.launch_count
+            assert rel(jac(r), ref) < 1e-12
+            assert ctx.launch_count == before + 1
+            # a second damping on the same level rebuilds the reciprocal table
+            assert rel(hp.BlockJacobi(ctx, form=hp.JACOBI_FD, damping=0.5)(r), ref * (0.5 / 0.75)) < 1e-12
+            ctx.close()
+
+
 def test_transfer_vs_oracle(orc, hp):
     rng = np.random.default_rng(4)
     for n in [(3, 4, 2), (5, 3)]:
