@@ -233,6 +233,28 @@ def main():
     # dominant kernel alone (the tile kernel; at N=1 it is the whole step), timed on its launching stream
     kernel_ms = ctx.time_apply_device(dxs[0], dys[0], max(10, min(args.steps, 100)))
 
+    # the smoother sweep of the same level (block Jacobi, fast-diagonalisation form: c = damping * D_e^-1 r per element), N = 1 only:
+    # it needs no exchange, so every rank would repeat the same number
+    smoother = None
+    if world == 1:
+        jac = hp.BlockJacobi(ctx, form=hp.JACOBI_FD, damping=0.75)
+        for i in range(args.warmup):
+            jac.time_device(dxs[i % NBUF], dys[i % NBUF], 1)
+        jsteps = max(10, min(args.steps, 100))
+        j0, j1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lj = ctx.launch_count
+        barrier()
+        j0.record(stream)
+        for i in range(jsteps):
+            jac.apply_device(dxs[i % NBUF], dys[i % NBUF], sync=False)
+        j1.record(stream)
+        ctx.sync()
+        jms = j0.elapsed_time(j1) / jsteps
+        smoother = {"what": "block-Jacobi sweep, fast-diagonalisation form (exact D_e^-1), same level, rotating buffers",
+                    "kernel": "hpdg_k_jacobi_fd_q3_persist" if degree == 3 else "k_jacobi_fd_uniform",
+                    "value": ndof / (jms * 1e-3), "unit": "DoF/s", "ms_per_sweep": jms, "steps": jsteps,
+                    "gpu_launches": ctx.launch_count - lj, "algorithmic_bytes_per_launch": BYTES_PER_DOF * ndof}
+
     # end-to-end leg: the drop-in call with HOST buffers, copies inside the timed region
     e2e_steps = args.e2e_steps or min(args.steps, 50)
     for _ in range(3):
@@ -271,6 +293,9 @@ def main():
                          "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
                          "kernel": "hpdg_k_apply_q3_persist" if degree == 3 else "k_apply_uniform", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": BYTES_PER_DOF * ndof},
         }
+        if smoother:
+            smoother["roofline_frac"] = smoother["algorithmic_bytes_per_launch"] / (smoother["ms_per_sweep"] * 1e-3) / 1e9 / peak
+            out["smoother"] = smoother
         if world == 1 and not args.no_cpu_baseline:
             rate, thr, sdof, reps, el = cpu_reference_rate(32, degree, 10.0)
             out["cpu_baseline"] = {"value": rate, "unit": "DoF/s", "cores": thr, "kind": "port",

@@ -591,9 +591,12 @@ int hpdg_jacobi_setup(hpdg_ctx* ctx, int level, int form) {
   if (form == HPDG_JACOBI_FD) return jacobi_setup_fd(ctx, *L);
   ctx->err = "unknown block-Jacobi form"; return 1;
 }
-int hpdg_jacobi_apply_device(hpdg_ctx* ctx, int level, int form, const double* d_r, double* d_c, double damping) {
+int hpdg_jacobi_apply_async(hpdg_ctx* ctx, int level, int form, const double* d_r, double* d_c, double damping) {
   Level* L = get_level(ctx, level); if (!L) return 1;
-  if (jacobi_async(ctx, *L, form, d_r, d_c, damping)) return 1;
+  return jacobi_async(ctx, *L, form, d_r, d_c, damping);
+}
+int hpdg_jacobi_apply_device(hpdg_ctx* ctx, int level, int form, const double* d_r, double* d_c, double damping) {
+  if (hpdg_jacobi_apply_async(ctx, level, form, d_r, d_c, damping)) return 1;
   HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }

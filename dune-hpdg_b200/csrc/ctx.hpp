@@ -84,7 +84,7 @@ struct Level {
   // compact tile lists (interior / rank-boundary tiles) of the distributed apply, per tile shape
   int *d_tiles_int = nullptr, *d_tiles_bnd = nullptr, *d_tiles_all = nullptr;  // all = interior first, boundary last
   long n_tiles_int = 0, n_tiles_bnd = 0, tile_key = -1;
-  double* d_jinv = nullptr;     // persistent Q3 block Jacobi: damping / eigenvalue sums, [vx][vz][vy][i][k][j]
+  double* d_jinv = nullptr;     // persistent Q3 block Jacobi: damping / eigenvalue sums, [vx][vy][vz][j][k][i]
   double jinv_damping = 0;      // the damping d_jinv was built with (0: not built)
   int q3j_state = 0;            // persistent Q3 block Jacobi: 0 = not set up, 1 = usable, -1 = factor lacks the mirror structure
   double q3j_V[3][3][16], q3j_lam[3][3][4];  // its 1-D eigenvectors / eigenvalues, [direction][boundary variant]

@@ -285,9 +285,9 @@ static int launch_q3j(Ctx* ctx, Level& L, const double* r, double* c, double dam
   if (q3p_level_setup(ctx, L)) return 1;
   if (!L.d_jinv || L.jinv_damping != damping) {
     std::vector<double> inv(27 * 64);
-    for (int vx = 0; vx < 3; vx++) for (int vz = 0; vz < 3; vz++) for (int vy = 0; vy < 3; vy++)
-      for (int i = 0; i < 4; i++) for (int k = 0; k < 4; k++) for (int j = 0; j < 4; j++)
-        inv[(size_t)((vx * 3 + vz) * 3 + vy) * 64 + (i * 4 + k) * 4 + j] = damping / (lam[0][vx][i] + lam[1][vy][j] + lam[2][vz][k]);
+    for (int vx = 0; vx < 3; vx++) for (int vy = 0; vy < 3; vy++) for (int vz = 0; vz < 3; vz++)
+      for (int j = 0; j < 4; j++) for (int k = 0; k < 4; k++) for (int i = 0; i < 4; i++)
+        inv[(size_t)((vx * 3 + vy) * 3 + vz) * 64 + (j * 4 + k) * 4 + i] = damping / (lam[0][vx][i] + lam[1][vy][j] + lam[2][vz][k]);
     if (!L.d_jinv) HPDG_CUDA(cudaMalloc(&L.d_jinv, sizeof(double) * inv.size()));
     HPDG_CUDA(cudaMemcpyAsync(L.d_jinv, inv.data(), sizeof(double) * inv.size(), cudaMemcpyHostToDevice, ctx->stream));
     HPDG_CUDA(cudaStreamSynchronize(ctx->stream));  // inv is a local
@@ -298,6 +298,7 @@ static int launch_q3j(Ctx* ctx, Level& L, const double* r, double* c, double dam
   P.r = r; P.c = c; P.xacc = ctx->fuse_xacc; P.inv = L.d_jinv;
   P.tile_desc = static_cast<const int4*>(L.d_tile_desc);
   P.sched = ctx->d_sched + 10;
+  P.tune = ctx->q3p_tune;
   P.ntiles = (L.n[0] / 4) * (L.n[1] / 4) * (L.n[2] / 4);
   static int slots = 0;
   if (!slots) {

@@ -3,19 +3,27 @@
 //   c_e = damping * (Vx x Vy x Vz) diag(1/(lx_i + ly_j + lz_k)) (Vx x Vy x Vz)^T r_e          (see jacobi.cu, jacobi_uniform.cu)
 //
 // Replaces IPDGBlockJacobi driven by Operator::apply (matrix-free/localoperators/ipdgblockjacobi.hh:58-178) with an exact local
-// solver.  Same skeleton as the persistent operator kernel (apply_uniform_q3p.cuh): persistent CTAs, tiles of 4x4x4 elements
-// from a global counter, unpadded swizzled shared memory, five pencil passes
-//   P1 z-pencils: Vz^T      P2 x-pencils: Vx^T      P3 y-pencils: Vy^T, scale by 1/(sum of eigenvalues), Vy
-//   P4 x-pencils: Vx        P5 z-pencils: Vz -> global c (+ optional x += c); the damping is folded into the reciprocals
-// but there is no neighbour coupling, so one array per tile is enough and the tile buffer is DOUBLE-buffered: the bulk copies of
-// the next tile are issued at the start of the current one and have a whole tile time to land.
+// solver.  Skeleton of the persistent operator kernel (apply_uniform_q3p.cuh): persistent CTAs, tiles of 4x4x4 elements from a
+// global counter, the tile of r double-buffered in shared memory by bulk async copies (cp.async.bulk + mbarrier) issued a whole
+// tile ahead.  There is no neighbour coupling, so the six 1-D sweeps are grouped into THREE stages that each keep their data in
+// registers and rewrite the tile in place (the shared-memory pipe was the limiter of the five-pass version, ncu: 63 % busy):
+//   A  one thread per (y,z)-plane of an element (fixed x-node i): Vy^T along j, Vz^T along k                 [16 values / thread]
+//   B  one thread per x-line, the same (j,k) line in 4 elements: Vx^T, scale by damping/(lx_i+ly_j+lz_k), Vx [128-bit accesses]
+//   C  planes again: Vz, Vy, then straight to global c (+ optional x += c); a store instruction fills whole 32-byte sectors
+// i.e. 5 shared-memory accesses per DoF instead of 9 and 2 block barriers per tile instead of 4.
+// Layout: element e = ex + 4 ey + 16 ez of the tile at 66 e doubles (one 512-byte bulk copy each, 16 bytes of padding): with the
+// lane assignments below every access of stages A-C is bank-conflict free (A/C: a half warp = 4 i x 4 elements of stride 2;
+// B: a quarter warp = 4 j x 2 neighbouring elements).
 // The 1-D factor of a direction depends only on whether the element is the first / last of its grid line at a domain boundary
-// (variants 1 / 2; 0 = interior faces on both sides).  Inside a pencil only element 0 / 3 of a boundary tile can differ, so
-// the variant is a warp-uniform branch on two of the four unrolled elements.  The reciprocals 1/(lx + ly + lz) come from a
-// small host-built table (27 variant combinations x 64 doubles, L1/L2 resident): no FP64 divisions in the kernel.
-// The interior factor is mirror symmetric (even / odd eigenvectors): 8 instead of 16 distinct table entries per direction, so
-// the tables of all three directions fit in the uniform register file.
+// (variants 1 / 2; 0 = interior faces on both sides).  Tiles that touch no domain boundary (2/3 of cfg2) run with the interior
+// tables as immediate-offset constant-bank operands: the interior factor is mirror symmetric (even / odd eigenvectors), 8 instead
+// of 16 distinct entries per direction, so the tables of all three directions fit in the uniform register file.  Tiles on the
+// domain boundary take a second instantiation that reads each element's factors from a shared-memory copy with run-time
+// variant indices (no divergence inside a tile).  The reciprocals come from a host-built table (27 variant combinations x 64
+// doubles, L1 resident): no FP64 divisions in the kernel.
 #pragma once
+#include <type_traits>
+
 #include "q3p_common.cuh"
 
 namespace hpdg {
@@ -23,17 +31,18 @@ namespace hpdg {
 struct Q3jParams {
   // [direction][variant][row-major 4x4: node x eigenvector].  Variant 0 (interior faces on both sides) is mirror symmetric: the
   // host orders its eigenvectors even, odd, even, odd under the node reflection (jacobi_uniform.cu), so V[3 - i][k] = (-1)^k V[i][k]
-  // and the kernel reads only rows 0 and 1 (8 doubles per direction).  The damping is folded into `inv`.
+  // and the fast path reads only rows 0 and 1 (8 doubles per direction).  The damping is folded into `inv`.
   double V[3][3][16];
   const double* r;
   double* c;
   double* xacc;          // optional: x += c
-  const double* inv;     // [vx][vz][vy][i][k][j] = damping / (lx_i + ly_j + lz_k)
+  const double* inv;     // [vx][vy][vz][j][k][i] = damping / (lx_i + ly_j + lz_k)
   const int4* tile_desc;
   int* sched;
   int n[3];
   int bnd[6];            // brick face f is a domain boundary (as opposed to a rank boundary)
   int ntiles;
+  int tune;              // timing experiments (not for production): bit 0 = no stores, bit 1 = interior tables on every tile
 };
 
 template <int OFF>
@@ -62,12 +71,9 @@ __device__ __forceinline__ void q3j_line(double (&a)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; i++) a[i] = o[i];
 }
-// Boundary variants (the first / last element of a grid line at a domain boundary; only in tiles on the brick surface): the table
-// is read from a small shared-memory copy with a run-time index.  Selecting between three inlined constant-bank versions makes
-// ptxas preload the tables of all variants and spill the 63 uniform registers (R2UR / local memory) in every pass; an
-// out-of-line function costs uniform-register saves around every call site.
+// the same with a run-time table held in registers (boundary variants)
 template <bool TRANS>
-__device__ __forceinline__ void q3j_line_rt(const double* __restrict__ V, double (&a)[4]) {
+__device__ __forceinline__ void q3j_line_rt(const double (&V)[16], double (&a)[4]) {
   double o[4];
 #pragma unroll
   for (int i = 0; i < 4; i++) {
@@ -79,44 +85,52 @@ __device__ __forceinline__ void q3j_line_rt(const double* __restrict__ V, double
 #pragma unroll
   for (int i = 0; i < 4; i++) a[i] = o[i];
 }
-// vb: shared-memory copy of the boundary variants, [D][var - 1][16].
-// E = position of the element in its pencil (compile time); var: 0, or 1 / 2 if the element is the first / last of its grid
-// line at a domain boundary (only possible for E = 0 / 3)
-template <int D, bool TRANS, int E>
-__device__ __forceinline__ void q3j_sweep(const double* __restrict__ vb, int var, double (&a)[4]) {
-  if ((E == 0 || E == 3) && var != 0) q3j_line_rt<TRANS>(vb + ((D * 2 + var - 1) << 4), a);
+// GENERAL: V is the element's factor of direction D (loaded from shared memory); otherwise the interior factor from the constant bank
+template <int D, bool TRANS, bool GENERAL>
+__device__ __forceinline__ void q3j_sweep(const double (&V)[16], double (&a)[4]) {
+  if constexpr (GENERAL) q3j_line_rt<TRANS>(V, a);
   else q3j_line<D, TRANS>(a);
 }
+template <bool GENERAL>
+__device__ __forceinline__ void q3j_load_factor(const double* __restrict__ src, double (&V)[16]) {
+  if constexpr (GENERAL) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const double2 v = reinterpret_cast<const double2*>(src)[q];
+      V[2 * q] = v.x; V[2 * q + 1] = v.y;
+    }
+  }
+}
 
-constexpr int kQ3jSmemBytes = 2 * 4096 * 8 + 32 + 6 * 16 * 8;
+constexpr int kQ3jEStride = 66;                    // doubles between the elements of a tile in shared memory
+constexpr int kQ3jBuf = 64 * kQ3jEStride;          // one tile buffer
+constexpr int kQ3jSmemBytes = (2 * kQ3jBuf + 4 + 9 * 16) * 8;
 
 }  // namespace hpdg
 
 extern "C" __global__ void __launch_bounds__(256, 3)
 hpdg_k_jacobi_fd_q3_persist(const __grid_constant__ hpdg::Q3jParams P) {
   using namespace hpdg;
-  constexpr int N3 = 64;
+  constexpr int N3 = 64, ES = kQ3jEStride;
   extern __shared__ __align__(128) double q3j_sm[];
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(q3j_sm + 8192);  // one per buffer
-  volatile int* s_next = reinterpret_cast<volatile int*>(q3j_sm + 8194);
-  double* __restrict__ vb = q3j_sm + 8196;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(q3j_sm + 2 * kQ3jBuf);  // one per buffer
+  volatile int* s_next = reinterpret_cast<volatile int*>(q3j_sm + 2 * kQ3jBuf + 2);
+  double* __restrict__ vb = q3j_sm + 2 * kQ3jBuf + 4;                  // [direction][variant][16]
   const double* __restrict__ R = P.r;
   const int n0 = P.n[0], n01 = P.n[0] * P.n[1];
   const int ntiles = P.ntiles;
 
-  // threads 0..15 fetch the tile's 16 rows of four x-contiguous elements (2 KB each) into buffer b
+  // the first 8 lanes of every warp fetch one element each (512 B) into buffer b: a bulk copy is issued lane by lane, so the
+  // 64 copies of a tile are spread over the 8 warps
   auto prefetch = [&](int tid, int e0, int b) {
-    if (tid < 16) {
+    if ((tid & 31) < 8) {
       if (tid == 0) q3p_mbar_expect_tx(mbar + b, 32768u);
-      const int ey = tid & 3, ez = tid >> 2;
-      q3p_bulk_g2s(q3j_sm + 4096 * b + (4 * ey + 16 * ez) * N3, R + (long)(e0 + n0 * ey + n01 * ez) * N3, 2048u, mbar + b);
+      const int e = (tid & 7) + 8 * (tid >> 5);
+      q3p_bulk_g2s(q3j_sm + kQ3jBuf * b + ES * e, R + (long)(e0 + (e & 3) + n0 * ((e >> 2) & 3) + n01 * (e >> 4)) * N3, 512u, mbar + b);
     }
   };
 
-  if (threadIdx.x < 96) {
-    const int d = threadIdx.x >> 5, v = (threadIdx.x >> 4) & 1, i = threadIdx.x & 15;
-    vb[threadIdx.x] = P.V[d][v + 1][i];
-  }
+  if (threadIdx.x < 144) vb[threadIdx.x] = (&P.V[0][0][0])[threadIdx.x];
   if (threadIdx.x == 0) {
     q3p_mbar_init(mbar, 1);
     q3p_mbar_init(mbar + 1, 1);
@@ -129,142 +143,171 @@ hpdg_k_jacobi_fd_q3_persist(const __grid_constant__ hpdg::Q3jParams P) {
   prefetch(threadIdx.x, td.x, 0);
   uint32_t phase = 0;  // bit b: phase of buffer b
   int buf = 0;
+  const int bmask = (P.bnd[0] ? 1 : 0) | (P.bnd[1] ? 2 : 0) | (P.bnd[2] ? 4 : 0) | (P.bnd[3] ? 8 : 0) | (P.bnd[4] ? 16 : 0) | (P.bnd[5] ? 32 : 0);
 
   for (;;) {
     // dynamic tile scheduling as in the operator kernel: thread 0 draws the next tile, the others read it after the first barrier
     if (threadIdx.x == 0) *s_next = (int)gridDim.x + atomicAdd(P.sched, 1);
-    const int e0 = td.x, fl = td.z;
-    double* __restrict__ sw = q3j_sm + 4096 * buf;
-    const bool lox = (fl & 1) && P.bnd[0], hix = (fl & 2) && P.bnd[1];
-    const bool loy = (fl & 4) && P.bnd[2], hiy = (fl & 8) && P.bnd[3];
-    const bool loz = (fl & 16) && P.bnd[4], hiz = (fl & 32) && P.bnd[5];
-    auto variant = [](int e, bool lo, bool hi) { return (e == 0 && lo) ? 1 : (e == 3 && hi) ? 2 : 0; };
+    const int e0 = td.x, fl = (P.tune & 2) ? 0 : (td.z & bmask);  // faces of the tile on a domain boundary
+    double* __restrict__ sw = q3j_sm + kQ3jBuf * buf;
+    bool has_next = false;
+    int tn = 0;
 
-    // ---------------- P1: z-pencils, Vz^T; raw tile rewritten in place (swizzled) ----------------
-    {
-      const int tid = q3p_tid();
-      const int zq = tid & 15, zex = (tid >> 4) & 3, zey = tid >> 6;
-      const int zcol = (zex + 4 * zey) * N3;
-      while (!q3p_mbar_try_wait(mbar + buf, (phase >> buf) & 1)) {}
-      phase ^= 1u << buf;
-      double v[4][4];
-#pragma unroll
-      for (int e = 0; e < 4; e++)
-#pragma unroll
-        for (int k = 0; k < 4; k++) v[e][k] = sw[zcol + 1024 * e + 16 * k + zq];
-      __syncwarp();
-      q3p_for<4>([&](auto ec) {
-        constexpr int e = decltype(ec)::value;
-        q3j_sweep<2, true, e>(vb, variant(e, loz, hiz), v[e]);
-#pragma unroll
-        for (int k = 0; k < 4; k++) sw[zcol + 1024 * e + 16 * k + (((zq ^ (4 * k)) + 2 * (e & 1)) & 15)] = v[e][k];
-      });
-    }
-    __syncthreads();
+    // G: bit d set = the tile touches a domain boundary in direction d, the sweeps of that direction take the elements' factors
+    // from shared memory (run-time variant, uniform over the tile's code path: no divergence)
+    auto tile = [&](auto gc) {
+      constexpr int G = decltype(gc)::value;
+      constexpr bool GX = G & 1, GY = (G >> 1) & 1, GZ = (G >> 2) & 1;
+      // boundary variant of an element of the tile along one direction: 1 / 2 = first / last of its grid line at a domain boundary
+      auto var = [&](int ec, int dir) { return (ec == 0 && ((fl >> (2 * dir)) & 1)) ? 1 : (ec == 3 && ((fl >> (2 * dir + 1)) & 1)) ? 2 : 0; };
 
-    // the other buffer is free (every warp is past pass 5 of the previous tile): fetch the next tile, a whole tile ahead
-    const int tn = *s_next;
-    const bool has_next = tn < ntiles;
-    if (has_next) {
-      td = __ldg(P.tile_desc + tn);
-      const int tid = q3p_tid();
-      if (tid < 16) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-      prefetch(tid, td.x, buf ^ 1);
-    }
-
-    // ---------------- P2: x-pencils, Vx^T (128-bit shared-memory accesses) ----------------
-    {
-      const int tid = q3p_tid();
-      const int xj = tid & 3, xez = ((tid >> 2) & 1) | ((tid >> 6) & 2), xk = (tid >> 3) & 3, xey = (tid >> 5) & 3;
-      const int xq = 2 * (xj ^ xk) + (xez & 1);
-      const int xo0 = (4 * xey + 16 * xez) * N3 + 16 * xk + 2 * (xq & 7);
-      const int xo1 = (4 * xey + 16 * xez) * N3 + 16 * xk + 2 * ((xq + 1) & 7);
-      q3p_for<4>([&](auto ec) {
-        constexpr int e = decltype(ec)::value;
-        const double2 lo = *reinterpret_cast<const double2*>(sw + xo0 + 64 * e);
-        const double2 hi = *reinterpret_cast<const double2*>(sw + xo1 + 64 * e);
-        double a[4] = {lo.x, lo.y, hi.x, hi.y};
-        q3j_sweep<0, true, e>(vb, variant(e, lox, hix), a);
-        *reinterpret_cast<double2*>(sw + xo0 + 64 * e) = make_double2(a[0], a[1]);
-        *reinterpret_cast<double2*>(sw + xo1 + 64 * e) = make_double2(a[2], a[3]);
-      });
-    }
-
-    // ---------------- P3: y-pencils: Vy^T, scale by the reciprocal eigenvalue sums, Vy ----------------
-    {
-      const int tid = q3p_tid();
-      const int yi = tid & 3, yk = (tid >> 2) & 3, yex = (tid >> 4) & 3, yez = tid >> 6;
-      const int ybase = (yex + 16 * yez) * N3 + 16 * yk;
-      const int yr = yi + 2 * (yez & 1);
-      auto yo = [&](int j) { return ybase + (((4 * j) ^ (4 * yk)) + yr & 15); };
-      const int vx = (yex == 0 && lox) ? 1 : (yex == 3 && hix) ? 2 : 0;
-      const int vz = (yez == 0 && loz) ? 1 : (yez == 3 && hiz) ? 2 : 0;
-      const double* __restrict__ ip = P.inv + ((vx * 3 + vz) * 3) * 64 + (yi * 4 + yk) * 4;  // + vy * 64 + j
-      const double2 i0a = __ldg(reinterpret_cast<const double2*>(ip)), i0b = __ldg(reinterpret_cast<const double2*>(ip) + 1);
-      q3p_bar_half(tid >> 7);
-      q3p_for<4>([&](auto ec) {
-        constexpr int e = decltype(ec)::value;
-        double a[4];
+      // ---------------- A: (y,z)-planes: Vy^T along j, Vz^T along k; in place ----------------
+      {
+        const int tid = q3p_tid();
+        const int e = 2 * ((tid >> 2) & 3) + ((tid >> 4) & 1) + 8 * (tid >> 5);
+        const int base = ES * e + (tid & 3);
+        while (!q3p_mbar_try_wait(mbar + buf, (phase >> buf) & 1)) {}
+        phase ^= 1u << buf;
+        double a[4][4];  // [k][j]
 #pragma unroll
-        for (int j = 0; j < 4; j++) a[j] = sw[yo(j) + 256 * e];
-        q3j_sweep<1, true, e>(vb, variant(e, loy, hiy), a);
-        if ((e == 0 && loy) || (e == 3 && hiy)) {
-          const double* q = ip + (e == 0 ? 64 : 128);
-          const double2 ia = __ldg(reinterpret_cast<const double2*>(q)), ib = __ldg(reinterpret_cast<const double2*>(q) + 1);
-          a[0] *= ia.x; a[1] *= ia.y; a[2] *= ib.x; a[3] *= ib.y;
-        } else { a[0] *= i0a.x; a[1] *= i0a.y; a[2] *= i0b.x; a[3] *= i0b.y; }
-        q3j_sweep<1, false, e>(vb, variant(e, loy, hiy), a);
+        for (int k = 0; k < 4; k++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) sw[yo(j) + 256 * e] = a[j];
-      });
-      q3p_bar_half(tid >> 7);
-    }
-
-    // ---------------- P4: x-pencils, Vx ----------------
-    {
-      const int tid = q3p_tid();
-      const int xj = tid & 3, xez = ((tid >> 2) & 1) | ((tid >> 6) & 2), xk = (tid >> 3) & 3, xey = (tid >> 5) & 3;
-      const int xq = 2 * (xj ^ xk) + (xez & 1);
-      const int xo0 = (4 * xey + 16 * xez) * N3 + 16 * xk + 2 * (xq & 7);
-      const int xo1 = (4 * xey + 16 * xez) * N3 + 16 * xk + 2 * ((xq + 1) & 7);
-      q3p_for<4>([&](auto ec) {
-        constexpr int e = decltype(ec)::value;
-        const double2 lo = *reinterpret_cast<const double2*>(sw + xo0 + 64 * e);
-        const double2 hi = *reinterpret_cast<const double2*>(sw + xo1 + 64 * e);
-        double a[4] = {lo.x, lo.y, hi.x, hi.y};
-        q3j_sweep<0, false, e>(vb, variant(e, lox, hix), a);
-        *reinterpret_cast<double2*>(sw + xo0 + 64 * e) = make_double2(a[0], a[1]);
-        *reinterpret_cast<double2*>(sw + xo1 + 64 * e) = make_double2(a[2], a[3]);
-      });
-    }
-    __syncthreads();
-
-    // ---------------- P5: damping * Vz, coalesced store (and x += c) ----------------
-    {
-      const int tid = q3p_tid();
-      const int zq = tid & 15, zex = (tid >> 4) & 3, zey = tid >> 6;
-      const int zcol = (zex + 4 * zey) * N3;
-      const long gofs = (long)(e0 + zex + n0 * zey) * N3 + zq;
-      double* __restrict__ co = P.c + gofs;
-      auto tile_out = [&](auto acc) {
-        q3p_for<4>([&](auto ec) {
-          constexpr int e = decltype(ec)::value;
-          double a[4];
+          for (int j = 0; j < 4; j++) a[k][j] = sw[base + 4 * j + 16 * k];
+        {
+          double V[16];
+          q3j_load_factor<GY>(vb + (3 + var((e >> 2) & 3, 1)) * 16, V);
 #pragma unroll
-          for (int k = 0; k < 4; k++) a[k] = sw[zcol + 1024 * e + 16 * k + (((zq ^ (4 * k)) + 2 * (e & 1)) & 15)];
-          q3j_sweep<2, false, e>(vb, variant(e, loz, hiz), a);
-          const long eo = (long)(n01 * e) * N3;
+          for (int k = 0; k < 4; k++) q3j_sweep<1, true, GY>(V, a[k]);
+        }
+        {
+          double V[16];
+          q3j_load_factor<GZ>(vb + (6 + var(e >> 4, 2)) * 16, V);
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            co[eo + 16 * k] = a[k];
-            if (decltype(acc)::value) P.xacc[gofs + eo + 16 * k] += a[k];
+          for (int j = 0; j < 4; j++) {
+            double l[4] = {a[0][j], a[1][j], a[2][j], a[3][j]};
+            q3j_sweep<2, true, GZ>(V, l);
+#pragma unroll
+            for (int k = 0; k < 4; k++) a[k][j] = l[k];
           }
-        });
-      };
-      if (P.xacc) tile_out(std::true_type{}); else tile_out(std::false_type{});
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) sw[base + 4 * j + 16 * k] = a[k][j];
+      }
+      __syncthreads();
+
+      // the other buffer is free (every warp is past stage C of the previous tile): fetch the next tile, a whole tile ahead
+      tn = *s_next;
+      has_next = tn < ntiles;
+      if (has_next) {
+        td = __ldg(P.tile_desc + tn);
+        const int tid = q3p_tid();
+        if ((tid & 31) < 8) {
+          asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // this lane's bulk store of the tile before (same slot)
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        }
+        prefetch(tid, td.x, buf ^ 1);
+      }
+
+      // ---------------- B: x-lines, the same (j,k) line of 4 elements: Vx^T, scale, Vx; in place, 128-bit accesses ----------------
+      {
+        const int tid = q3p_tid();
+        const int j = tid & 3, k = (tid >> 3) & 3;
+        const int eb = ((tid >> 2) & 1) + 8 * (tid >> 5);  // elements eb + 2 it
+        const int lofs = 4 * j + 16 * k;
+        const double* __restrict__ ip = P.inv + 16 * j + 4 * k;  // [variant combination][j][k][i]
+        double2 s0, s1;
+        if constexpr (G == 0) { s0 = __ldg(reinterpret_cast<const double2*>(ip)); s1 = __ldg(reinterpret_cast<const double2*>(ip) + 1); }
+#pragma unroll
+        for (int px = 0; px < 2; px++) {  // the two x-positions of this thread's elements share a factor
+          double V[16];
+          q3j_load_factor<GX>(vb + var((eb & 1) + 2 * px, 0) * 16, V);
+#pragma unroll
+          for (int py = 0; py < 2; py++) {
+            const int e = eb + 2 * (px + 2 * py);
+            double* __restrict__ lp = sw + ES * e + lofs;
+            if constexpr (G != 0) {
+              const int vx = GX ? var(e & 3, 0) : 0, vy = GY ? var((e >> 2) & 3, 1) : 0, vz = GZ ? var(e >> 4, 2) : 0;
+              const double2* q = reinterpret_cast<const double2*>(ip + ((vx * 3 + vy) * 3 + vz) * 64);
+              s0 = __ldg(q); s1 = __ldg(q + 1);
+            }
+            const double2 lo = *reinterpret_cast<const double2*>(lp), hi = *reinterpret_cast<const double2*>(lp + 2);
+            double a[4] = {lo.x, lo.y, hi.x, hi.y};
+            q3j_sweep<0, true, GX>(V, a);
+            a[0] *= s0.x; a[1] *= s0.y; a[2] *= s1.x; a[3] *= s1.y;
+            q3j_sweep<0, false, GX>(V, a);
+            *reinterpret_cast<double2*>(lp) = make_double2(a[0], a[1]);
+            *reinterpret_cast<double2*>(lp + 2) = make_double2(a[2], a[3]);
+          }
+        }
+      }
+      __syncthreads();
+
+      // ---------------- C: planes again: Vz along k, Vy along j; out ----------------
+      {
+        const int tid = q3p_tid();
+        const int e = 2 * ((tid >> 2) & 3) + ((tid >> 4) & 1) + 8 * (tid >> 5);
+        const int base = ES * e + (tid & 3);
+        double a[4][4];  // [k][j]
+        {
+          double V[16];
+          q3j_load_factor<GZ>(vb + (6 + var(e >> 4, 2)) * 16, V);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            double l[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) l[k] = sw[base + 4 * j + 16 * k];
+            q3j_sweep<2, false, GZ>(V, l);
+#pragma unroll
+            for (int k = 0; k < 4; k++) a[k][j] = l[k];
+          }
+        }
+        {
+          double V[16];
+          q3j_load_factor<GY>(vb + (3 + var((e >> 2) & 3, 1)) * 16, V);
+#pragma unroll
+          for (int k = 0; k < 4; k++) q3j_sweep<1, false, GY>(V, a[k]);
+        }
+        if (P.xacc) {
+          // V-cycle: c and x += c straight from the registers (a store instruction fills whole 32-byte sectors)
+          const long gofs = (long)(e0 + (e & 3) + n0 * ((e >> 2) & 3) + n01 * (e >> 4)) * N3 + (tid & 3);
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              P.c[gofs + 4 * j + 16 * k] = a[k][j];
+              P.xacc[gofs + 4 * j + 16 * k] += a[k][j];
+            }
+        } else {
+          // back in place, then one bulk store per element (512 B) issued by the warp that owns the element in this stage
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) sw[base + 4 * j + 16 * k] = a[k][j];
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+          __syncwarp();
+          if ((tid & 31) < 8 && !(P.tune & 1)) {
+            const int es = (tid & 7) + 8 * (tid >> 5);
+            q3p_bulk_s2g(P.c + (long)(e0 + (es & 3) + n0 * ((es >> 2) & 3) + n01 * (es >> 4)) * N3, sw + ES * es, 512u);
+          }
+        }
+      }
+    };
+    switch ((fl & 3 ? 1 : 0) | (fl & 12 ? 2 : 0) | (fl & 48 ? 4 : 0)) {
+      case 0: tile(std::integral_constant<int, 0>{}); break;
+      case 1: tile(std::integral_constant<int, 1>{}); break;
+      case 2: tile(std::integral_constant<int, 2>{}); break;
+      case 3: tile(std::integral_constant<int, 3>{}); break;
+      case 4: tile(std::integral_constant<int, 4>{}); break;
+      case 5: tile(std::integral_constant<int, 5>{}); break;
+      case 6: tile(std::integral_constant<int, 6>{}); break;
+      default: tile(std::integral_constant<int, 7>{}); break;
     }
     if (!has_next) break;
     t = tn; buf ^= 1;
   }
+  // shared memory must outlive the bulk stores that read it
+  if ((threadIdx.x & 31) < 8) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
   if (threadIdx.x == 0 && atomicAdd(P.sched + 1, 1) == (int)gridDim.x - 1) { P.sched[0] = 0; P.sched[1] = 0; __threadfence(); }
 }

@@ -25,6 +25,11 @@ __device__ __forceinline__ void q3p_bulk_g2s(void* dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                ::"r"(q3p_smem_u32(dst)), "l"(src), "r"(bytes), "r"(q3p_smem_u32(b)) : "memory");
 }
+// shared -> global bulk store, committed as this thread's own bulk group (wait with cp.async.bulk.wait_group.read)
+__device__ __forceinline__ void q3p_bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(q3p_smem_u32(src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
 
 template <int... I, class F>
 __device__ __forceinline__ void q3p_for_impl(std::integer_sequence<int, I...>, F f) { (f(std::integral_constant<int, I>{}), ...); }

@@ -57,6 +57,7 @@ SIGNATURES = {
     "hpdg_jacobi_setup": (C.c_int, [_vp, C.c_int, C.c_int]),
     "hpdg_jacobi_apply": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_double]),
     "hpdg_jacobi_apply_device": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_double]),
+    "hpdg_jacobi_apply_async": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_double]),
     "hpdg_jacobi_bytes": (C.c_size_t, [_vp, C.c_int, C.c_int]),
     "hpdg_diag_block": (C.c_int, [_vp, C.c_int, C.c_long, _dp]),
     "hpdg_bcrs_sizes": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_long), C.POINTER(C.c_long)]),
@@ -288,8 +289,9 @@ class BlockJacobi:
         self.ctx._ck(lib().hpdg_jacobi_apply(self.ctx._h, self.level, self.form, _hptr(r), _hptr(c), self.damping))
         return c
 
-    def apply_device(self, dr, dc):
-        self.ctx._ck(lib().hpdg_jacobi_apply_device(self.ctx._h, self.level, self.form, dr, dc, self.damping))
+    def apply_device(self, dr, dc, sync=True):
+        f = lib().hpdg_jacobi_apply_device if sync else lib().hpdg_jacobi_apply_async
+        self.ctx._ck(f(self.ctx._h, self.level, self.form, dr, dc, self.damping))
 
     def time_device(self, dr, dc, reps):
         """ms per application, CUDA events around `reps` back-to-back launches on the context stream"""

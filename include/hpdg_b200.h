@@ -94,6 +94,8 @@ int hpdg_op_apply_async(hpdg_ctx* ctx, int level, const double* d_x, double* d_y
 int hpdg_jacobi_setup(hpdg_ctx* ctx, int level, int form);
 int hpdg_jacobi_apply(hpdg_ctx* ctx, int level, int form, const double* h_r, double* h_c, double damping);
 int hpdg_jacobi_apply_device(hpdg_ctx* ctx, int level, int form, const double* d_r, double* d_c, double damping);
+/* enqueue only (no synchronisation): pair with hpdg_sync, like hpdg_op_apply_async */
+int hpdg_jacobi_apply_async(hpdg_ctx* ctx, int level, int form, const double* d_r, double* d_c, double damping);
 size_t hpdg_jacobi_bytes(const hpdg_ctx* ctx, int level, int form);
 /* MatrixCreator protocol bind(e) + matrix() (matrix-free/localoperators/ipdgdiagonalblock.hh:29-360,
  * slowipdgdiag.hh:32-218): the diagonal block A_ee, n_e x n_e row-major, to host memory. */

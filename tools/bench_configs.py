@@ -65,13 +65,13 @@ if "cfg3" in which:
     t0 = time.time()
     jf = hp.BlockJacobi(ctx, form=hp.JACOBI_FD)
     tf = time.time() - t0
-    ms = timed(ctx, lambda: jf.apply_device(dx, dy), a.reps)
+    ms = timed(ctx, lambda: jf.apply_device(dx, dy, sync=False), a.reps)
     emit(config="cfg3 block-Jacobi fd apply", ndof=nd, us=ms * 1e3, gdofs=nd / ms / 1e6, setup_s=tf, bytes=jf.bytes,
          gbs=bytes_alg / ms / 1e6, frac=bytes_alg / ms / 1e6 / PEAK)
     t0 = time.time()
     jd = hp.BlockJacobi(ctx, form=hp.JACOBI_DENSE)
     td = time.time() - t0
-    ms = timed(ctx, lambda: jd.apply_device(dx, dy), a.reps)
+    ms = timed(ctx, lambda: jd.apply_device(dx, dy, sync=False), a.reps)
     off = ctx.block_offsets()
     ne = np.diff(off).astype(np.float64)
     bj = float((8 * ne * ne + 16 * ne).sum())
@@ -86,13 +86,13 @@ if "jacobi" in which:
         t0 = time.time()
         jd = hp.BlockJacobi(ctx, form=hp.JACOBI_DENSE)
         td = time.time() - t0
-        ms = timed(ctx, lambda: jd.apply_device(dx, dy), a.reps)
+        ms = timed(ctx, lambda: jd.apply_device(dx, dy, sync=False), a.reps)
         ne = (p + 1) ** 3
         bj = float(np.prod(n)) * (8 * ne * ne + 16 * ne)
         emit(config=f"block-Jacobi dense apply {n[0]}^3 Q{p}", ndof=nd, us=ms * 1e3, gdofs=nd / ms / 1e6, setup_s=td, bytes=jd.bytes,
              gbs=bj / ms / 1e6, frac=bj / ms / 1e6 / PEAK)
         jf = hp.BlockJacobi(ctx, form=hp.JACOBI_FD)
-        ms = timed(ctx, lambda: jf.apply_device(dx, dy), a.reps)
+        ms = timed(ctx, lambda: jf.apply_device(dx, dy, sync=False), a.reps)
         emit(config=f"block-Jacobi fd apply {n[0]}^3 Q{p}", ndof=nd, us=ms * 1e3, gdofs=nd / ms / 1e6, gbs=16 * nd / ms / 1e6,
              frac=16 * nd / ms / 1e6 / PEAK)
         ctx.close()
