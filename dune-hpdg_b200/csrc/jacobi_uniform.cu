@@ -298,7 +298,6 @@ static int launch_q3j(Ctx* ctx, Level& L, const double* r, double* c, double dam
   P.r = r; P.c = c; P.xacc = ctx->fuse_xacc; P.inv = L.d_jinv;
   P.tile_desc = static_cast<const int4*>(L.d_tile_desc);
   P.sched = ctx->d_sched + 10;
-  P.tune = ctx->q3p_tune;
   P.ntiles = (L.n[0] / 4) * (L.n[1] / 4) * (L.n[2] / 4);
   static int slots = 0;
   if (!slots) {

@@ -42,7 +42,6 @@ struct Q3jParams {
   int n[3];
   int bnd[6];            // brick face f is a domain boundary (as opposed to a rank boundary)
   int ntiles;
-  int tune;              // timing experiments (not for production): bit 0 = no stores, bit 1 = interior tables on every tile
 };
 
 template <int OFF>
@@ -148,7 +147,7 @@ hpdg_k_jacobi_fd_q3_persist(const __grid_constant__ hpdg::Q3jParams P) {
   for (;;) {
     // dynamic tile scheduling as in the operator kernel: thread 0 draws the next tile, the others read it after the first barrier
     if (threadIdx.x == 0) *s_next = (int)gridDim.x + atomicAdd(P.sched, 1);
-    const int e0 = td.x, fl = (P.tune & 2) ? 0 : (td.z & bmask);  // faces of the tile on a domain boundary
+    const int e0 = td.x, fl = td.z & bmask;  // faces of the tile on a domain boundary
     double* __restrict__ sw = q3j_sm + kQ3jBuf * buf;
     bool has_next = false;
     int tn = 0;
@@ -287,7 +286,7 @@ hpdg_k_jacobi_fd_q3_persist(const __grid_constant__ hpdg::Q3jParams P) {
             for (int j = 0; j < 4; j++) sw[base + 4 * j + 16 * k] = a[k][j];
           asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
           __syncwarp();
-          if ((tid & 31) < 8 && !(P.tune & 1)) {
+          if ((tid & 31) < 8) {
             const int es = (tid & 7) + 8 * (tid >> 5);
             q3p_bulk_s2g(P.c + (long)(e0 + (es & 3) + n0 * ((es >> 2) & 3) + n01 * (es >> 4)) * N3, sw + ES * es, 512u);
           }
