@@ -448,7 +448,7 @@ int uniform_tile_lists(Ctx* ctx, Level& L, int TX, int TY, int TZ, const int* bm
 
 template <int N, int TX, int TY, int TZ, int MINB, bool EARLY = true>
 static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream) {
-  static UniParams<N> P;  // rebuilt per call (cheap); static to keep it off the stack
+  static thread_local UniParams<N> P;  // rebuilt per call (cheap); static to keep it off the stack, per thread: contexts on different host threads launch concurrently
   const DegTable& T = host_tables().deg[N - 1];
   const double c = ctx->sigma * (double)L.pen_uni * L.pen_uni;
   for (int d = 0; d < 3; d++) {
@@ -565,7 +565,7 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
         }
         hpdg_k_apply_q3_persist<<<grid, 256, kQ3pSmemBytes, stream>>>(P, static_cast<const int4*>(L.d_tile_desc), (int)ntiles, (int)ntiles_total, ctx->d_sched + 2 * (part & 3), PK);
       } else {  // variant 42: even/odd arithmetic (apply_uniform_q3e.cuh); fewer FP64 operations but measured slower (94.9 vs 91.7 us on cfg2)
-        static Q3eTab E;
+        static thread_local Q3eTab E;
         for (int d = 0; d < 3; d++) {
           for (int a = 0; a < 2; a++) {
             for (int b = 0; b < 2; b++) {

@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(256, MINB) k_apply_uniform3(const __grid_const
 }
 
 int launch_apply_uniform3(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream) {
-  static Uni3Params P;
+  static thread_local Uni3Params P;
   constexpr int N = 4, T = 4;
   const DegTable& Tb = host_tables().deg[N - 1];
   const double c = ctx->sigma * (double)L.pen_uni * L.pen_uni;

@@ -180,7 +180,7 @@ k_jacobi_fd_uniform(const __grid_constant__ FDUniParams<N> P) {
 
 template <int N, int TX, int TY, int TZ, int MINB>
 static int launch_fdu(Ctx* ctx, Level& L, const double* r, double* c, double damping) {
-  static FDUniParams<N> P;
+  static thread_local FDUniParams<N> P;
   const DegTable& T = host_tables().deg[N - 1];
   const double cpen = ctx->sigma * (double)L.pen_uni * L.pen_uni;
   for (int d = 0; d < 3; d++) {
@@ -255,7 +255,7 @@ static void fd_factor(const Ctx* ctx, const Level& L, int N, int d, int var, dou
 // persistent Q3 kernel (jacobi_uniform_q3p.cuh): same conditions as the persistent operator kernel.
 // Returns -1 if the interior factor does not have the mirror structure the kernel relies on (then the tile kernel runs).
 static int launch_q3j(Ctx* ctx, Level& L, const double* r, double* c, double damping) {
-  static Q3jParams P;
+  static thread_local Q3jParams P;
   if (L.q3j_state < 0) return -1;
   double (&lam)[3][3][4] = L.q3j_lam;
   if (L.q3j_state == 0) {  // once per level: the 1-D factors (the context's sigma / boundary type are fixed at creation)
