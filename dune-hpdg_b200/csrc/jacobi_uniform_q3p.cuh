@@ -5,20 +5,25 @@
 // Replaces IPDGBlockJacobi driven by Operator::apply (matrix-free/localoperators/ipdgblockjacobi.hh:58-178) with an exact local
 // solver.  Skeleton of the persistent operator kernel (apply_uniform_q3p.cuh): persistent CTAs, tiles of 4x4x4 elements from a
 // global counter, the tile of r double-buffered in shared memory by bulk async copies (cp.async.bulk + mbarrier) issued a whole
-// tile ahead.  There is no neighbour coupling, so the six 1-D sweeps are grouped into THREE stages that each keep their data in
-// registers and rewrite the tile in place (the shared-memory pipe was the limiter of the five-pass version, ncu: 63 % busy):
+// tile ahead, the result written back in place and sent off by bulk stores.  There is no neighbour coupling, so the six 1-D
+// sweeps are grouped into THREE stages that each keep their data in registers and rewrite the tile in place (the shared-memory
+// pipe was the limiter of the five-pass version, ncu: 63 % busy):
 //   A  one thread per (y,z)-plane of an element (fixed x-node i): Vy^T along j, Vz^T along k                 [16 values / thread]
-//   B  one thread per x-line, the same (j,k) line in 4 elements: Vx^T, scale by damping/(lx_i+ly_j+lz_k), Vx [128-bit accesses]
-//   C  planes again: Vz, Vy, then straight to global c (+ optional x += c); a store instruction fills whole 32-byte sectors
+//   B  one thread per x-line, line (j,k) of the 4 elements of a row: Vx^T, scale by damping/(lx_i+ly_j+lz_k), Vx [128-bit accesses]
+//   C  planes again: Vz, Vy, back in place, bulk store to c  (V-cycle mode: c and x += c straight from the registers)
 // i.e. 5 shared-memory accesses per DoF instead of 9 and 2 block barriers per tile instead of 4.
-// Layout: element e = ex + 4 ey + 16 ez of the tile at 66 e doubles (one 512-byte bulk copy each, 16 bytes of padding): with the
-// lane assignments below every access of stages A-C is bank-conflict free (A/C: a half warp = 4 i x 4 elements of stride 2;
-// B: a quarter warp = 4 j x 2 neighbouring elements).
+// Layout: the tile's 16 rows (ey + 4 ez) of four x-contiguous elements (2 KB, contiguous in a DynamicBlockVector) arrive by one bulk
+// copy each and sit 258 doubles apart (16 bytes of padding per row): with the lane assignments below every access of stages A-C is
+// bank-conflict free (A/C: a half warp = 4 i x 4 rows of stride 2 at one x-position, bank (2 row + i + 4 j) mod 16; B: a quarter
+// warp = 4 j x 2 neighbouring rows, 16-byte unit (row + 2 j) mod 8).  A bulk copy costs ~10 issue slots in a per-lane loop, hence
+// rows in (16 per tile); the result leaves element by element (64 per tile) because in stage C a warp owns whole elements but
+// not whole rows, and a warp-local hand-over to the async proxy needs no block barrier.
 // The 1-D factor of a direction depends only on whether the element is the first / last of its grid line at a domain boundary
 // (variants 1 / 2; 0 = interior faces on both sides).  Tiles that touch no domain boundary (2/3 of cfg2) run with the interior
 // tables as immediate-offset constant-bank operands: the interior factor is mirror symmetric (even / odd eigenvectors), 8 instead
 // of 16 distinct entries per direction, so the tables of all three directions fit in the uniform register file.  Tiles on the
-// domain boundary take a second instantiation that reads each element's factors from a shared-memory copy with run-time
+// domain boundary take one of seven further instantiations (one per set of touched directions) in which only the sweeps normal
+// to a touched boundary read their element's factor from a shared-memory copy into registers, once per stage, with run-time
 // variant indices (no divergence inside a tile).  The reciprocals come from a host-built table (27 variant combinations x 64
 // doubles, L1 resident): no FP64 divisions in the kernel.
 #pragma once
@@ -101,8 +106,8 @@ __device__ __forceinline__ void q3j_load_factor(const double* __restrict__ src, 
   }
 }
 
-constexpr int kQ3jEStride = 66;                    // doubles between the elements of a tile in shared memory
-constexpr int kQ3jBuf = 64 * kQ3jEStride;          // one tile buffer
+constexpr int kQ3jRStride = 258;                   // doubles between the rows (4 x-contiguous elements, 256 doubles) of a tile in shared memory
+constexpr int kQ3jBuf = 16 * kQ3jRStride;          // one tile buffer
 constexpr int kQ3jSmemBytes = (2 * kQ3jBuf + 4 + 9 * 16) * 8;
 
 }  // namespace hpdg
@@ -110,7 +115,7 @@ constexpr int kQ3jSmemBytes = (2 * kQ3jBuf + 4 + 9 * 16) * 8;
 extern "C" __global__ void __launch_bounds__(256, 3)
 hpdg_k_jacobi_fd_q3_persist(const __grid_constant__ hpdg::Q3jParams P) {
   using namespace hpdg;
-  constexpr int N3 = 64, ES = kQ3jEStride;
+  constexpr int N3 = 64, RS = kQ3jRStride;
   extern __shared__ __align__(128) double q3j_sm[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(q3j_sm + 2 * kQ3jBuf);  // one per buffer
   volatile int* s_next = reinterpret_cast<volatile int*>(q3j_sm + 2 * kQ3jBuf + 2);
@@ -119,13 +124,13 @@ hpdg_k_jacobi_fd_q3_persist(const __grid_constant__ hpdg::Q3jParams P) {
   const int n0 = P.n[0], n01 = P.n[0] * P.n[1];
   const int ntiles = P.ntiles;
 
-  // the first 8 lanes of every warp fetch one element each (512 B) into buffer b: a bulk copy is issued lane by lane, so the
-  // 64 copies of a tile are spread over the 8 warps
+  // the first 2 lanes of every warp fetch one row of 4 x-contiguous elements each (2 KB) into buffer b: a bulk copy is issued lane
+  // by lane (~10 instructions per copy), so the 16 copies of a tile are spread over the 8 warps
   auto prefetch = [&](int tid, int e0, int b) {
-    if ((tid & 31) < 8) {
+    if ((tid & 31) < 2) {
       if (tid == 0) q3p_mbar_expect_tx(mbar + b, 32768u);
-      const int e = (tid & 7) + 8 * (tid >> 5);
-      q3p_bulk_g2s(q3j_sm + kQ3jBuf * b + ES * e, R + (long)(e0 + (e & 3) + n0 * ((e >> 2) & 3) + n01 * (e >> 4)) * N3, 512u, mbar + b);
+      const int row = (tid & 1) + 2 * (tid >> 5);  // ey + 4 ez
+      q3p_bulk_g2s(q3j_sm + kQ3jBuf * b + RS * row, R + (long)(e0 + n0 * (row & 3) + n01 * (row >> 2)) * N3, 2048u, mbar + b);
     }
   };
 
@@ -163,8 +168,8 @@ hpdg_k_jacobi_fd_q3_persist(const __grid_constant__ hpdg::Q3jParams P) {
       // ---------------- A: (y,z)-planes: Vy^T along j, Vz^T along k; in place ----------------
       {
         const int tid = q3p_tid();
-        const int e = 2 * ((tid >> 2) & 3) + ((tid >> 4) & 1) + 8 * (tid >> 5);
-        const int base = ES * e + (tid & 3);
+        const int row = 2 * ((tid >> 2) & 3) + ((tid >> 4) & 1) + 8 * ((tid >> 5) & 1);  // ey + 4 ez
+        const int base = RS * row + 64 * (tid >> 6) + (tid & 3);
         while (!q3p_mbar_try_wait(mbar + buf, (phase >> buf) & 1)) {}
         phase ^= 1u << buf;
         double a[4][4];  // [k][j]
@@ -174,13 +179,13 @@ hpdg_k_jacobi_fd_q3_persist(const __grid_constant__ hpdg::Q3jParams P) {
           for (int j = 0; j < 4; j++) a[k][j] = sw[base + 4 * j + 16 * k];
         {
           double V[16];
-          q3j_load_factor<GY>(vb + (3 + var((e >> 2) & 3, 1)) * 16, V);
+          q3j_load_factor<GY>(vb + (3 + var(row & 3, 1)) * 16, V);
 #pragma unroll
           for (int k = 0; k < 4; k++) q3j_sweep<1, true, GY>(V, a[k]);
         }
         {
           double V[16];
-          q3j_load_factor<GZ>(vb + (6 + var(e >> 4, 2)) * 16, V);
+          q3j_load_factor<GZ>(vb + (6 + var(row >> 2, 2)) * 16, V);
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             double l[4] = {a[0][j], a[1][j], a[2][j], a[3][j]};
@@ -194,64 +199,61 @@ hpdg_k_jacobi_fd_q3_persist(const __grid_constant__ hpdg::Q3jParams P) {
 #pragma unroll
           for (int j = 0; j < 4; j++) sw[base + 4 * j + 16 * k] = a[k][j];
       }
+      // the bulk stores of the tile before (other buffer) have had this stage to read their source
+      if ((q3p_tid() & 31) < 8) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
       __syncthreads();
 
-      // the other buffer is free (every warp is past stage C of the previous tile): fetch the next tile, a whole tile ahead
+      // the other buffer is free (every warp is past stage C of the previous tile and its stores have been read): fetch the next
+      // tile, a whole tile ahead
       tn = *s_next;
       has_next = tn < ntiles;
       if (has_next) {
         td = __ldg(P.tile_desc + tn);
         const int tid = q3p_tid();
-        if ((tid & 31) < 8) {
-          asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // this lane's bulk store of the tile before (same slot)
-          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        }
+        if ((tid & 31) < 2) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         prefetch(tid, td.x, buf ^ 1);
       }
 
-      // ---------------- B: x-lines, the same (j,k) line of 4 elements: Vx^T, scale, Vx; in place, 128-bit accesses ----------------
+      // ---------------- B: x-lines, line (j,k) of the 4 elements of a row: Vx^T, scale, Vx; in place, 128-bit accesses ----------------
       {
         const int tid = q3p_tid();
         const int j = tid & 3, k = (tid >> 3) & 3;
-        const int eb = ((tid >> 2) & 1) + 8 * (tid >> 5);  // elements eb + 2 it
-        const int lofs = 4 * j + 16 * k;
+        const int row = ((tid >> 2) & 1) + 2 * (tid >> 5);
+        double* __restrict__ lp = sw + RS * row + 4 * j + 16 * k;
         const double* __restrict__ ip = P.inv + 16 * j + 4 * k;  // [variant combination][j][k][i]
         double2 s0, s1;
         if constexpr (G == 0) { s0 = __ldg(reinterpret_cast<const double2*>(ip)); s1 = __ldg(reinterpret_cast<const double2*>(ip) + 1); }
-#pragma unroll
-        for (int px = 0; px < 2; px++) {  // the two x-positions of this thread's elements share a factor
+        const int vy = GY ? var(row & 3, 1) : 0, vz = GZ ? var(row >> 2, 2) : 0;
+        q3p_for<4>([&](auto exc) {
+          constexpr int ex = decltype(exc)::value;
+          constexpr bool RT = GX && (ex == 0 || ex == 3);  // only the ends of the row can sit on an x-boundary
+          const int vx = RT ? var(ex, 0) : 0;
           double V[16];
-          q3j_load_factor<GX>(vb + var((eb & 1) + 2 * px, 0) * 16, V);
-#pragma unroll
-          for (int py = 0; py < 2; py++) {
-            const int e = eb + 2 * (px + 2 * py);
-            double* __restrict__ lp = sw + ES * e + lofs;
-            if constexpr (G != 0) {
-              const int vx = GX ? var(e & 3, 0) : 0, vy = GY ? var((e >> 2) & 3, 1) : 0, vz = GZ ? var(e >> 4, 2) : 0;
-              const double2* q = reinterpret_cast<const double2*>(ip + ((vx * 3 + vy) * 3 + vz) * 64);
-              s0 = __ldg(q); s1 = __ldg(q + 1);
-            }
-            const double2 lo = *reinterpret_cast<const double2*>(lp), hi = *reinterpret_cast<const double2*>(lp + 2);
-            double a[4] = {lo.x, lo.y, hi.x, hi.y};
-            q3j_sweep<0, true, GX>(V, a);
-            a[0] *= s0.x; a[1] *= s0.y; a[2] *= s1.x; a[3] *= s1.y;
-            q3j_sweep<0, false, GX>(V, a);
-            *reinterpret_cast<double2*>(lp) = make_double2(a[0], a[1]);
-            *reinterpret_cast<double2*>(lp + 2) = make_double2(a[2], a[3]);
+          q3j_load_factor<RT>(vb + vx * 16, V);
+          if constexpr (G != 0) {
+            const double2* q = reinterpret_cast<const double2*>(ip + ((vx * 3 + vy) * 3 + vz) * 64);
+            s0 = __ldg(q); s1 = __ldg(q + 1);
           }
-        }
+          const double2 lo = *reinterpret_cast<const double2*>(lp + 64 * ex), hi = *reinterpret_cast<const double2*>(lp + 64 * ex + 2);
+          double a[4] = {lo.x, lo.y, hi.x, hi.y};
+          q3j_sweep<0, true, RT>(V, a);
+          a[0] *= s0.x; a[1] *= s0.y; a[2] *= s1.x; a[3] *= s1.y;
+          q3j_sweep<0, false, RT>(V, a);
+          *reinterpret_cast<double2*>(lp + 64 * ex) = make_double2(a[0], a[1]);
+          *reinterpret_cast<double2*>(lp + 64 * ex + 2) = make_double2(a[2], a[3]);
+        });
       }
       __syncthreads();
 
       // ---------------- C: planes again: Vz along k, Vy along j; out ----------------
       {
         const int tid = q3p_tid();
-        const int e = 2 * ((tid >> 2) & 3) + ((tid >> 4) & 1) + 8 * (tid >> 5);
-        const int base = ES * e + (tid & 3);
+        const int row = 2 * ((tid >> 2) & 3) + ((tid >> 4) & 1) + 8 * ((tid >> 5) & 1);
+        const int base = RS * row + 64 * (tid >> 6) + (tid & 3);
         double a[4][4];  // [k][j]
         {
           double V[16];
-          q3j_load_factor<GZ>(vb + (6 + var(e >> 4, 2)) * 16, V);
+          q3j_load_factor<GZ>(vb + (6 + var(row >> 2, 2)) * 16, V);
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             double l[4];
@@ -264,13 +266,13 @@ hpdg_k_jacobi_fd_q3_persist(const __grid_constant__ hpdg::Q3jParams P) {
         }
         {
           double V[16];
-          q3j_load_factor<GY>(vb + (3 + var((e >> 2) & 3, 1)) * 16, V);
+          q3j_load_factor<GY>(vb + (3 + var(row & 3, 1)) * 16, V);
 #pragma unroll
           for (int k = 0; k < 4; k++) q3j_sweep<1, false, GY>(V, a[k]);
         }
         if (P.xacc) {
           // V-cycle: c and x += c straight from the registers (a store instruction fills whole 32-byte sectors)
-          const long gofs = (long)(e0 + (e & 3) + n0 * ((e >> 2) & 3) + n01 * (e >> 4)) * N3 + (tid & 3);
+          const long gofs = (long)(e0 + (tid >> 6) + n0 * (row & 3) + n01 * (row >> 2)) * N3 + (tid & 3);
 #pragma unroll
           for (int k = 0; k < 4; k++)
 #pragma unroll
@@ -286,9 +288,9 @@ hpdg_k_jacobi_fd_q3_persist(const __grid_constant__ hpdg::Q3jParams P) {
             for (int j = 0; j < 4; j++) sw[base + 4 * j + 16 * k] = a[k][j];
           asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
           __syncwarp();
-          if ((tid & 31) < 8) {
-            const int es = (tid & 7) + 8 * (tid >> 5);
-            q3p_bulk_s2g(P.c + (long)(e0 + (es & 3) + n0 * ((es >> 2) & 3) + n01 * (es >> 4)) * N3, sw + ES * es, 512u);
+          if ((tid & 31) < 8) {  // this warp's 8 elements: x-position tid >> 6, rows 8 ((tid >> 5) & 1) + 0..7
+            const int rs = (tid & 7) + 8 * ((tid >> 5) & 1), exs = tid >> 6;
+            q3p_bulk_s2g(P.c + (long)(e0 + exs + n0 * (rs & 3) + n01 * (rs >> 2)) * N3, sw + RS * rs + 64 * exs, 512u);
           }
         }
       }
