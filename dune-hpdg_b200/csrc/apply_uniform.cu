@@ -604,17 +604,17 @@ int uniform_tile_height(const Level& L) {
 
 // what the persistent Q3 kernels (operator apply, block Jacobi) need per context / level: the tile counters of the dynamic
 // scheduler and the tile descriptors {first element, packed tile coordinates, brick-face bits, 0} of the 4x4x4 tiling
-int q3p_level_setup(Ctx* ctx, Level& L) {
+int q3p_level_setup(Ctx* ctx, Level& L, int tile_h) {  // tiles of 4 x 4 x tile_h elements
   if (!ctx->d_sched) {  // {next, done} per launch kind: apply parts 0..3 -> ints 0..7, halo pack 8, block Jacobi 10..11
     HPDG_CUDA(cudaMalloc(&ctx->d_sched, 12 * sizeof(int)));
     HPDG_CUDA(cudaMemset(ctx->d_sched, 0, 12 * sizeof(int)));
   }
   if (!L.d_tile_desc) {
-    const int nt[3] = {L.n[0] / 4, L.n[1] / 4, L.n[2] / 4};
+    const int nt[3] = {L.n[0] / 4, L.n[1] / 4, L.n[2] / tile_h};
     std::vector<int4> td((size_t)nt[0] * nt[1] * nt[2]);
     for (int tz = 0, i = 0; tz < nt[2]; tz++) for (int ty = 0; ty < nt[1]; ty++) for (int tx = 0; tx < nt[0]; tx++, i++) {
       const int fl = (tx == 0) | (tx == nt[0] - 1) << 1 | (ty == 0) << 2 | (ty == nt[1] - 1) << 3 | (tz == 0) << 4 | (tz == nt[2] - 1) << 5;
-      td[i] = make_int4(4 * tx + L.n[0] * (4 * ty + L.n[1] * 4 * tz), tx | ty << 10 | tz << 20, fl, 0);
+      td[i] = make_int4(4 * tx + L.n[0] * (4 * ty + L.n[1] * tile_h * tz), tx | ty << 10 | tz << 20, fl, 0);
     }
     HPDG_CUDA(cudaMalloc(&L.d_tile_desc, sizeof(int4) * td.size()));
     HPDG_CUDA(cudaMemcpy(L.d_tile_desc, td.data(), sizeof(int4) * td.size(), cudaMemcpyHostToDevice));

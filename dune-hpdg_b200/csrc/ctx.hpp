@@ -88,6 +88,7 @@ struct Level {
   double jinv_damping = 0;      // the damping d_jinv was built with (0: not built)
   int q3j_state = 0;            // persistent Q3 block Jacobi: 0 = not set up, 1 = usable, -1 = factor lacks the mirror structure
   double q3j_V[3][3][16], q3j_lam[3][3][4];  // its 1-D eigenvectors / eigenvalues, [direction][boundary variant]
+  double q4j_V[3][3][25], q4j_lam[3][3][5];  // the same for the experimental persistent Q4 kernel (variant 50)
   void* d_tile_desc = nullptr;  // persistent Q3 kernel: int4 per 4x4x4 tile {first element, packed tile coordinates, brick-face bits, 0}
   // scratch vectors for the V-cycle (device, ndof each)
   double *mg_x = nullptr, *mg_r = nullptr, *mg_t1 = nullptr, *mg_t2 = nullptr;
@@ -146,7 +147,7 @@ int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double 
 int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream = nullptr);
 int uniform_supported(const Ctx* ctx, const Level& L);
 int uniform_persistent(const Ctx* ctx, const Level& L);  // the level's apply runs the persistent Q3 tile kernel
-int q3p_level_setup(Ctx* ctx, Level& L);                 // tile descriptors + scheduler counters of the persistent Q3 kernels
+int q3p_level_setup(Ctx* ctx, Level& L, int tile_h = 4);  // descriptors of the 4 x 4 x tile_h tiles + scheduler counters of the persistent kernels
 int uniform_tile_height(const Level& L);
 int uniform_tile_lists(Ctx* ctx, Level& L, int TX, int TY, int TZ, const int* bmode);
 int launch_apply_uniform3(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream);

@@ -19,6 +19,7 @@
 
 #include "ctx.hpp"
 #include "jacobi_uniform_q3p.cuh"
+#include "jacobi_uniform_q4p.cuh"
 
 namespace hpdg {
 
@@ -314,11 +315,78 @@ static int launch_q3j(Ctx* ctx, Level& L, const double* r, double* c, double dam
   return 0;
 }
 
+// EXPERIMENTAL persistent Q4 kernel (jacobi_uniform_q4p.cuh), opt-in through option "variant" = 50: uniform Q4 bricks with extents
+// multiple of (4, 4, 2).  Returns -1 when it does not apply.
+static int launch_q4j(Ctx* ctx, Level& L, const double* r, double* c, double damping) {
+  static thread_local Q4jParams P;
+  if (L.q3j_state < 0) return -1;
+  double (&lam)[3][3][5] = L.q4j_lam;
+  if (L.q3j_state == 0) {  // once per level
+    L.q3j_state = -1;
+    for (int d = 0; d < 3; d++)
+      for (int var = 0; var < 3; var++) fd_factor(ctx, L, 5, d, var, L.q4j_V[d][var], lam[d][var]);
+    for (int d = 0; d < 3; d++) {  // interior factor: eigenpairs in the order even, odd, even, odd, even under i -> 4 - i
+      double* V = L.q4j_V[d][0];
+      int even[5], odd[5], ne = 0, no = 0;
+      for (int k = 0; k < 5; k++) {
+        double se = 0, so = 0, nn = 0;
+        for (int i = 0; i < 5; i++) {
+          se += std::fabs(V[i * 5 + k] - V[(4 - i) * 5 + k]); so += std::fabs(V[i * 5 + k] + V[(4 - i) * 5 + k]); nn += std::fabs(V[i * 5 + k]);
+        }
+        if (se <= 1e-13 * nn) even[ne++] = k; else if (so <= 1e-13 * nn) odd[no++] = k; else return -1;
+      }
+      if (ne != 3 || no != 2) return -1;
+      const int order[5] = {even[0], odd[0], even[1], odd[1], even[2]};
+      double Vn[25], ln[5];
+      for (int k = 0; k < 5; k++) { ln[k] = lam[d][0][order[k]]; for (int i = 0; i < 5; i++) Vn[i * 5 + k] = V[i * 5 + order[k]]; }
+      for (int k = 0; k < 5; k++) { lam[d][0][k] = ln[k]; for (int i = 0; i < 5; i++) V[i * 5 + k] = Vn[i * 5 + k]; }
+    }
+    // tile descriptors of the 4x4x2 tiles + the scheduler counters
+    if (q3p_level_setup(ctx, L, 2)) return 1;
+    L.q3j_state = 1;
+  }
+  std::memcpy(P.V, L.q4j_V, sizeof(P.V));
+  if (!L.d_jinv || L.jinv_damping != damping) {
+    std::vector<double> inv(27 * 125);
+    for (int vx = 0; vx < 3; vx++) for (int vy = 0; vy < 3; vy++) for (int vz = 0; vz < 3; vz++)
+      for (int k = 0; k < 5; k++) for (int j = 0; j < 5; j++) for (int i = 0; i < 5; i++)
+        inv[(size_t)((vx * 3 + vy) * 3 + vz) * 125 + (k * 5 + j) * 5 + i] = damping / (lam[0][vx][i] + lam[1][vy][j] + lam[2][vz][k]);
+    if (!L.d_jinv) HPDG_CUDA(cudaMalloc(&L.d_jinv, sizeof(double) * inv.size()));
+    HPDG_CUDA(cudaMemcpyAsync(L.d_jinv, inv.data(), sizeof(double) * inv.size(), cudaMemcpyHostToDevice, ctx->stream));
+    HPDG_CUDA(cudaStreamSynchronize(ctx->stream));  // inv is a local
+    L.jinv_damping = damping;
+  }
+  for (int f = 0; f < 6; f++) P.bnd[f] = ctx->bnd_is_rank[f] ? 0 : 1;
+  for (int d = 0; d < 3; d++) P.n[d] = L.n[d];
+  P.r = r; P.c = c; P.xacc = ctx->fuse_xacc; P.inv = L.d_jinv;
+  P.tile_desc = static_cast<const int4*>(L.d_tile_desc);
+  P.sched = ctx->d_sched + 10;
+  P.ntiles = (L.n[0] / 4) * (L.n[1] / 4) * (L.n[2] / 2);
+  static int slots = 0;
+  if (!slots) {
+    HPDG_CUDA(cudaFuncSetAttribute(hpdg_k_jacobi_fd_q4_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, kQ4jSmemBytes));
+    int nsm = 0, occ = 0;
+    HPDG_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+    HPDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hpdg_k_jacobi_fd_q4_persist, 160, kQ4jSmemBytes));
+    slots = nsm * std::max(occ, 1);
+  }
+  const int grid = std::min(P.ntiles, ctx->q3p_grid > 0 ? ctx->q3p_grid : slots);
+  hpdg_k_jacobi_fd_q4_persist<<<grid, 160, kQ4jSmemBytes, ctx->stream>>>(P);
+  ctx->launches++;
+  HPDG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // returns -1 when there is no specialised kernel for this level
 int jacobi_apply_fd_uniform(Ctx* ctx, Level& L, const double* r, double* c, double damping) {
   if (!uniform_supported(ctx, L)) return -1;
   if (uniform_persistent(ctx, L) && (reinterpret_cast<uintptr_t>(r) & 15) == 0) {
     const int rc = launch_q3j(ctx, L, r, c, damping);
+    if (rc >= 0) return rc;
+  }
+  if (ctx->variant == 50 && L.p_uni == 4 && L.n[0] % 4 == 0 && L.n[1] % 4 == 0 && L.n[2] % 2 == 0 && L.ndof < (1L << 31) &&
+      (reinterpret_cast<uintptr_t>(r) & 15) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+    const int rc = launch_q4j(ctx, L, r, c, damping);
     if (rc >= 0) return rc;
   }
   switch (L.p_uni) {

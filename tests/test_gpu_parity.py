@@ -1,4 +1,6 @@
 """Parity of the CUDA path (through the C ABI) against the CPU oracle.  Bar: relative L2 <= 1e-12 (FP64)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -201,6 +203,19 @@ def test_fd_jacobi_persistent_q3(orc, hp):
             # a second damping on the same level rebuilds the reciprocal table
             assert rel(hp.BlockJacobi(ctx, form=hp.JACOBI_FD, damping=0.5)(r), ref * (0.5 / 0.75)) < 1e-12
             ctx.close()
+
+
+@pytest.mark.skipif(not os.environ.get("HPDG_EXPERIMENTAL"), reason="experimental kernel (variant 50), not yet validated on a GPU: set HPDG_EXPERIMENTAL=1")
+def test_fd_jacobi_persistent_q4_experimental(orc, hp):
+    # jacobi_uniform_q4p.cuh: uniform Q4 bricks with extents multiple of (4, 4, 2); must match the oracle and the default kernel
+    for n, L, dirichlet in [((4, 4, 2), None, True), ((8, 4, 6), [1.0, 1.5, 0.5], True), ((8, 8, 4), None, False), ((4, 12, 2), None, False)]:
+        m = orc.Mesh(n, L=L, degree=4, dirichlet=dirichlet)
+        r = orc.fill_random(m.ndof)
+        ref = m.blockjacobi_apply(r, factor=0.75)
+        ctx = hp.Context(n, L=L, degree=4, dirichlet=dirichlet)
+        ctx.set_option("variant", 50)
+        assert rel(hp.BlockJacobi(ctx, form=hp.JACOBI_FD, damping=0.75)(r), ref) < 1e-12
+        ctx.close()
 
 
 def test_transfer_vs_oracle(orc, hp):
