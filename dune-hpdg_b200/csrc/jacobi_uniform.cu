@@ -380,7 +380,8 @@ static int launch_q4j(Ctx* ctx, Level& L, const double* r, double* c, double dam
 // returns -1 when there is no specialised kernel for this level
 int jacobi_apply_fd_uniform(Ctx* ctx, Level& L, const double* r, double* c, double damping) {
   if (!uniform_supported(ctx, L)) return -1;
-  if (uniform_persistent(ctx, L) && (reinterpret_cast<uintptr_t>(r) & 15) == 0) {
+  // the bulk copies / bulk stores of the persistent kernel need 16-byte aligned vectors
+  if (uniform_persistent(ctx, L) && ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(c)) & 15) == 0) {
     const int rc = launch_q3j(ctx, L, r, c, damping);
     if (rc >= 0) return rc;
   }
