@@ -28,6 +28,7 @@ WORKLOADS = {
 }
 PGRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 METRIC = "IPDG matvec DoF/s (3D Q3, FP64)"
+NBUF = 3  # rotating (x, y) buffer pairs
 BYTES_PER_DOF = 16  # algorithmic: read x once + write y once
 
 
@@ -77,11 +78,20 @@ def ncu_traffic(workload):
         return None
 
 
+def host_threads():
+    """threads the CPU arm uses: every core this process may run on (torchrun exports OMP_NUM_THREADS=1, which is ignored here:
+    the thread count is passed to the oracle explicitly)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_rate(n, degree, budget_s, threads=None, min_reps=1):
     """Time the CPU restatement of the reference's matrix-free apply (Operator::apply over IPDGOperator,
     /root/reference/dune/hpdg/matrix-free/operator.hh:41, localoperators/ipdgoperator.hh:80) on an n^3 sample."""
     from oracle import orc
-    threads = threads or orc.max_threads()
+    threads = threads or host_threads()
     m = orc.Mesh((n, n, n), degree=degree, sigma=2.0, dirichlet=True)
     x = orc.fill_random(m.ndof)
     m.apply_mf(x, threads=threads)  # warm caches
@@ -98,18 +108,33 @@ def cpu_reference_rate(n, degree, budget_s, threads=None, min_reps=1):
     return m.ndof * reps / el, threads, m.ndof, reps, el
 
 
+def workload_config(workload, world, p2p=True):
+    nelem_dir, degree, desc = WORKLOADS[workload]
+    ndof = nelem_dir ** 3 * (degree + 1) ** 3
+    return {"workload": desc, "elements_per_gpu": [nelem_dir] * 3, "degree": degree, "dof_per_gpu": ndof,
+            "pgrid": list(PGRID[world]), "sigma": 2.0, "dirichlet": True,
+            "l2": f"{NBUF} rotating (x,y) pairs of {ndof * 8 / 1e6:.0f} MB each: inputs larger than the 126 MB L2",
+            "halo": ("none" if world == 1 else "NVLink peer-memory stores of the face traces + step flags, issued by the tile kernel itself "
+                     "before its first tile; its rank-boundary tiles (scheduled last) wait on the neighbours' flags" if p2p else
+                     "NCCL send/recv of face traces overlapped with interior tiles")}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path (here: its plain-C restatement, the
-    reference being uncompilable in this image) on the host cores, all threads, bounded sample per step."""
+    reference being uncompilable in this image) on the host cores, all threads, a bounded sample of the workload per step.
+    The sample and the thread count do not depend on the number of ranks, so the driver's ratios are comparable across N."""
     if rank != 0:
         return
     from oracle import orc
     nelem_dir, degree, desc = WORKLOADS[args.workload]
-    threads = orc.max_threads()
-    rate, _, _, _, _ = cpu_reference_rate(8, degree, 0.5)
-    per_step = max(0.02, min(2.0, 150.0 / max(1, args.steps + args.warmup)))
-    n = int(round((rate * per_step / (degree + 1) ** 3) ** (1.0 / 3.0)))
-    n = max(4, min(32, n))
+    threads = host_threads()
+    rate, _, _, _, _ = cpu_reference_rate(8, degree, 0.5, threads=threads)
+    # one brick of the workload per step if the whole run then stays within ~2.5 minutes, otherwise a 32^3 (16^3) sample
+    n = 16
+    for cand in (nelem_dir, 32):
+        if cand <= nelem_dir and cand ** 3 * (degree + 1) ** 3 / rate * (args.steps + args.warmup) <= 150.0:
+            n = cand
+            break
     m = orc.Mesh((n, n, n), degree=degree, sigma=2.0, dirichlet=True)
     x = orc.fill_random(m.ndof)
     for _ in range(args.warmup):
@@ -119,15 +144,70 @@ def run_reference(args, rank, world):
         m.apply_mf(x, threads=threads)
     el = time.perf_counter() - t0
     val = m.ndof * args.steps / el
-    sample = f"{n}^3 elements Q{degree} ({m.ndof} DoF) per step, matrix-free quadrature-loop apply, {threads} OpenMP threads"
+    sample = (f"{n}^3 elements Q{degree} ({m.ndof} DoF) per step" + (" = one GPU's brick of the workload" if n == nelem_dir else "") +
+              f", matrix-free quadrature-loop apply (CPU restatement of ipdgoperator.hh), {threads} OpenMP threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "DoF/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "sample": sample},
+        "config": workload_config(args.workload, world if world in PGRID else 1),
         "cpu_baseline": {"value": val, "unit": "DoF/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "DoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
+
+
+def make_context(hp, torch, dist, n, degree, world, rank, local_rank):
+    """one rank's brick context (distributed when world > 1: NCCL id from rank 0, NVLink peer-memory halo when possible)"""
+    from hpdg_b200 import partition as part
+    if world == 1:
+        return hp.Context(n, L=[1.0, 1.0, 1.0], degree=degree, sigma=2.0, dirichlet=True, device=local_rank), False
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        import ctypes
+        buf = ctypes.create_string_buffer(128)
+        assert hp.lib().hpdg_nccl_unique_id(buf) == 0
+        idt = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
+    dist.broadcast(idt, 0)
+    # the global domain is [0,px]x[0,py]x[0,pz] so that every brick is a unit cube
+    ctx = hp.Context(n, L=[1.0, 1.0, 1.0], degree=degree, sigma=2.0, dirichlet=True, device=local_rank, pgrid=PGRID[world],
+                     rank=rank, nranks=world, nccl_id=bytes(idt.cpu().tolist()))
+    return ctx, part.enable_p2p_halo(ctx, dist, torch, world)
+
+
+def parity_check(hp, torch, dist, degree, world, rank, local_rank):
+    """Before any number is reported: the same code path (same kernels, same halo transport) on an 8^3-per-rank brick of the
+    global (8 px, 8 py, 8 pz) mesh against the CPU oracle applied to the GLOBAL mesh; two chained applies so that both parities
+    of the double-buffered halo arena are exercised.  Returns the worst relative L2 error over all ranks."""
+    import numpy as np
+    from hpdg_b200 import partition as part
+    from oracle import orc
+    nb, pgrid = (8, 8, 8), PGRID[world]
+    m = orc.Mesh([nb[d] * pgrid[d] for d in range(3)], L=[float(pgrid[d]) for d in range(3)], degree=degree, sigma=2.0, dirichlet=True)
+    xg = orc.fill_random(m.ndof)
+    thr = max(1, host_threads() // world)
+    r1 = m.apply_mf(xg, threads=thr)
+    r2 = m.apply_mf(r1, threads=thr)
+    ne = (degree + 1) ** 3
+    ctx, _ = make_context(hp, torch, dist, nb, degree, world, rank, local_rank)
+    dx, dy = ctx.upload(part.scatter_global_vector(xg, rank, pgrid, nb, ne)), ctx.vec_alloc()
+    op = hp.Operator(ctx)
+    op.apply_device(dx, dy)
+    y1 = ctx.download(dy)
+    op.apply_device(dy, dx)
+    y2 = ctx.download(dx)
+    ctx.vec_free(dx)
+    ctx.vec_free(dy)
+    ctx.close()
+    e = 0.0
+    for y, r in ((y1, r1), (y2, r2)):
+        rl = part.scatter_global_vector(r, rank, pgrid, nb, ne)
+        e = max(e, float(np.linalg.norm(y - rl) / np.linalg.norm(rl)))
+    if world > 1:
+        t = torch.tensor([e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e = float(t.item())
+    return {"rel_l2": e, "tolerance": 1e-12, "n": int(m.ndof), "mesh": [nb[d] * pgrid[d] for d in range(3)], "degree": degree,
+            "against": "CPU oracle (restatement of ipdgoperator.hh) on the global mesh, two chained applies", "ranks": world}
 
 
 def main():
@@ -168,28 +248,15 @@ def main():
     if world not in PGRID:
         raise SystemExit(f"unsupported GPU count {world}")
     pgrid = PGRID[world]
-    # the global domain is [0,px]x[0,py]x[0,pz] so that every brick is a unit cube with h = 1/nelem_dir
-    L = [1.0, 1.0, 1.0]
-    if world > 1:
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            import ctypes
-            buf = ctypes.create_string_buffer(128)
-            assert hp.lib().hpdg_nccl_unique_id(buf) == 0
-            idt = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
-        dist.broadcast(idt, 0)
-        ctx = hp.Context(n, L=L, degree=degree, sigma=2.0, dirichlet=True, device=local_rank, pgrid=pgrid, rank=rank,
-                         nranks=world, nccl_id=bytes(idt.cpu().tolist()))
-    else:
-        ctx = hp.Context(n, L=L, degree=degree, sigma=2.0, dirichlet=True, device=local_rank)
-    from hpdg_b200 import partition as part
-    p2p = part.enable_p2p_halo(ctx, dist, torch, world) if world > 1 else False
+    parity = parity_check(hp, torch, dist, degree, world, rank, local_rank)
+    if not parity["rel_l2"] < parity["tolerance"]:
+        raise SystemExit(f"bench.py: parity check against the CPU oracle FAILED ({parity}); no number is reported")
+    ctx, p2p = make_context(hp, torch, dist, n, degree, world, rank, local_rank)
     ndof = ctx.dimension()
     op = hp.Operator(ctx)
     assert ctx.uses_uniform_kernel()
 
     # synthetic input resident in HBM: NBUF (x, y) pairs rotated so no step re-reads what the previous one left in L2
-    NBUF = 3
     rng = np.random.default_rng(1887 + rank)
     hx, hx_ptr = ctx.host_alloc(ndof)
     hy, hy_ptr = ctx.host_alloc(ndof)
@@ -274,30 +341,30 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        achieved = BYTES_PER_DOF * ndof / (kernel_ms * 1e-3) / 1e9
+        # roofline of the dominant kernel over the SAME rotating buffers as the timed region (at N = 1 the step is that one launch;
+        # at N > 1 the launch also packs / waits for the halo); kernel_ms_same_buffers (one fixed buffer pair, partly L2-warm) is
+        # reported beside it
+        achieved = BYTES_PER_DOF * ndof / (ms_per_step * 1e-3) / 1e9
         out = {
             "metric": METRIC, "value": value, "unit": "DoF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": desc, "elements_per_gpu": list(n), "degree": degree, "dof_per_gpu": ndof,
-                       "pgrid": list(pgrid), "sigma": 2.0, "dirichlet": True,
-                       "l2": f"{NBUF} rotating (x,y) pairs of {ndof * 8 / 1e6:.0f} MB each: inputs larger than the 126 MB L2",
-                       "halo": ("none" if world == 1 else "NVLink peer-memory stores of the face traces + step flags, issued by the tile kernel itself "
-                                "before its first tile; its rank-boundary tiles (scheduled last) wait on the neighbours' flags" if p2p else
-                                "NCCL send/recv of face traces overlapped with interior tiles")},
+            "config": workload_config(args.workload, world, p2p),
+            "parity": parity,
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "DoF/s", "h2d_bytes_per_step": ndof * 8, "d2h_bytes_per_step": ndof * 8,
                     "steps": e2e_steps, "api": "hpdg_op_apply (host pointers, pinned)", "checksum": checksum},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
-                         "kernel": "hpdg_k_apply_q3_persist" if degree == 3 else "k_apply_uniform", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": BYTES_PER_DOF * ndof},
+                         "kernel": "hpdg_k_apply_q3_persist" if degree == 3 else "k_apply_uniform", "kernel_ms": ms_per_step,
+                         "kernel_ms_same_buffers": kernel_ms, "algorithmic_bytes_per_launch": BYTES_PER_DOF * ndof},
         }
         if smoother:
             smoother["roofline_frac"] = smoother["algorithmic_bytes_per_launch"] / (smoother["ms_per_sweep"] * 1e-3) / 1e9 / peak
             out["smoother"] = smoother
         if world == 1 and not args.no_cpu_baseline:
-            rate, thr, sdof, reps, el = cpu_reference_rate(32, degree, 10.0)
+            rate, thr, sdof, reps, el = cpu_reference_rate(32, degree, 10.0, threads=host_threads())
             out["cpu_baseline"] = {"value": rate, "unit": "DoF/s", "cores": thr, "kind": "port",
                                    "sample": f"32^3 elements Q{degree} ({sdof} DoF) x {reps} applies in {el:.1f} s, matrix-free "
                                              f"quadrature-loop apply (CPU restatement of ipdgoperator.hh), {thr} OpenMP threads"}

@@ -56,6 +56,25 @@ bool load_nccl(std::string& err) {
 
 int ipow_h(int b, int e) { int r = 1; while (e-- > 0) r *= b; return r; }
 
+// Every extern "C" entry point that touches the device starts here: the context's device becomes the calling thread's current
+// device (a process may hold contexts on several devices, and the caller's current device is its own business).
+#define HPDG_ENTER(ctx) HPDG_CUDA(cudaSetDevice((ctx)->device))
+
+// Synchronise the context's streams and report a halo time-out of the NVLink peer-memory path: a rank-boundary tile that gave up
+// waiting for a neighbour's traces has computed from stale data, so EVERY synchronising entry point fails (and clears the flag, so
+// that the next exchange starts clean).  The flag lives in mapped pinned host memory: reading it costs nothing.
+int sync_check(Ctx* ctx) {
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream_comm));
+  if (ctx->h_ghost_err && *ctx->h_ghost_err) {
+    *ctx->h_ghost_err = 0;
+    cudaMemset(ctx->ghost.arena + ctx->ghost.flag_off + 12 * sizeof(int), 0, sizeof(int));
+    ctx->err = "halo exchange timed out waiting for a neighbour rank's face traces (results of this step are invalid)";
+    return 1;
+  }
+  return 0;
+}
+
 int setup_level(Ctx* ctx, Level& L, int dim, const int* n, const double* h, const std::vector<int>& deg,
                 const std::vector<int>& pdeg) {
   L.dim = dim;
@@ -169,7 +188,7 @@ int op_apply_distributed(Ctx* ctx, Level& L, const double* d_x, double* d_y, dou
     // interior tiles first; its rank-boundary tiles wait on the flags the NEIGHBOURS raise (the local pack is not a dependency
     // of the local apply).  The compute stream joins the halo stream at the end so that x may be overwritten afterwards.
     ctx->ghost.step++;
-    if (uniform_persistent(ctx, L) && ctx->variant != 42) {
+    if (uniform_persistent(ctx, L, d_x)) {
       // persistent Q3 kernel: packing the face traces, publishing the flags and all tiles are ONE launch (its CTAs fill every
       // SM for the whole run, so a separate pack kernel would not be scheduled next to it)
       return launch_apply_uniform(ctx, L, d_x, d_y, factor, 3, ctx->stream);
@@ -183,6 +202,7 @@ int op_apply_distributed(Ctx* ctx, Level& L, const double* d_x, double* d_y, dou
     HPDG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
     return 0;
   }
+  if (!ctx->nccl) { ctx->err = "this distributed context has no NCCL communicator (created with nccl_id = NULL) and the peer-memory halo is not attached for this level"; return 1; }
   HPDG_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));                    // x is ready
   HPDG_CUDA(cudaStreamWaitEvent(ctx->stream_comm, ctx->ev_a, 0));
   if (launch_pack_traces(ctx, L, d_x, ctx->stream_comm)) return 1;
@@ -309,6 +329,41 @@ int vcycle_device(Ctx* ctx, const VC& v, double* d_x, double* d_b) {
 }
 }  // namespace
 
+namespace hpdg {
+int kernel_slots(Ctx* ctx, const void* func, int threads, size_t smem, int* slots) {
+  auto it = ctx->kattr.find(func);
+  if (it == ctx->kattr.end()) {
+    if (smem > 48 * 1024) HPDG_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nsm = 0, occ = 0;
+    HPDG_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+    HPDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, threads, smem));
+    it = ctx->kattr.emplace(func, nsm * std::max(occ, 1)).first;
+  }
+  if (slots) *slots = it->second;
+  return 0;
+}
+}  // namespace hpdg
+
+// CUDA events around `reps` asynchronous launches on the context stream (events are destroyed on every path)
+template <class Launch>
+static int time_launches(Ctx* ctx, int reps, float* ms_per_launch, Launch launch) {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = 0;
+  float ms = 0;
+  auto ck = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && !rc) { ctx->err = std::string(what) + ": " + cudaGetErrorString(e); rc = 1; } };
+  ck(cudaEventCreate(&e0), "cudaEventCreate"); ck(cudaEventCreate(&e1), "cudaEventCreate");
+  if (!rc) ck(cudaEventRecord(e0, ctx->stream), "cudaEventRecord");
+  for (int i = 0; i < reps && !rc; i++) rc = launch();
+  if (!rc) ck(cudaEventRecord(e1, ctx->stream), "cudaEventRecord");
+  if (!rc) ck(cudaEventSynchronize(e1), "cudaEventSynchronize");
+  if (!rc) ck(cudaEventElapsedTime(&ms, e0, e1), "cudaEventElapsedTime");
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (rc) return 1;
+  *ms_per_launch = ms / std::max(reps, 1);
+  return sync_check(ctx);
+}
+
 // =================================================================================================
 extern "C" {
 
@@ -344,7 +399,15 @@ int hpdg_create_distributed(hpdg_ctx** out, int dim, const int* n, const double*
                             int dirichlet, int device, const int* pgrid, int rank, int nranks, const void* nccl_id) {
   *out = nullptr;
   if (dim != 3) { g_create_err = "distributed bricks are 3-D"; return 1; }
-  if (pgrid[0] * pgrid[1] * pgrid[2] != nranks) { g_create_err = "pgrid does not match nranks"; return 1; }
+  if (!n || !L || !pgrid) { g_create_err = "null argument"; return 1; }
+  for (int d = 0; d < 3; d++) {
+    if (n[d] < 1) { g_create_err = "mesh extents must be positive"; return 1; }
+    if (pgrid[d] < 1) { g_create_err = "pgrid entries must be positive"; return 1; }
+  }
+  if (nranks < 1 || pgrid[0] * pgrid[1] * pgrid[2] != nranks) { g_create_err = "pgrid does not match nranks"; return 1; }
+  if (rank < 0 || rank >= nranks) { g_create_err = "rank out of range"; return 1; }
+  if (degree < 0 || degree > kMaxP) { g_create_err = "polynomial degree out of range 0..13"; return 1; }
+  if (nranks > 1 && (degree < 1 || degree > 5)) { g_create_err = "distributed path needs a degree with a specialised uniform kernel (1..5)"; return 1; }
   long nelem = (long)n[0] * n[1] * n[2];
   std::vector<int> deg(nelem, degree);
   hpdg_ctx* ctx = new hpdg_ctx();
@@ -356,14 +419,16 @@ int hpdg_create_distributed(hpdg_ctx** out, int dim, const int* n, const double*
   if (nranks > 1) {
     Level& Lv = ctx->levels.back();
     if (!uniform_supported(ctx, Lv)) return fail("distributed path needs a degree with a specialised uniform kernel (1..5)");
-    std::string err;
-    if (!load_nccl(err)) return fail(err);
-    ncclUniqueId id; memcpy(&id, nccl_id, 128);
-    ncclComm_t comm;
-    if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice failed");
-    ncclResult_t r = g_nccl.CommInitRank(&comm, nranks, id, rank);
-    if (r != ncclSuccess) return fail(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
-    ctx->nccl = comm;
+    if (nccl_id) {  // nccl_id == NULL: no NCCL communicator (peer-memory halo only; entry points that need NCCL then fail)
+      std::string err;
+      if (!load_nccl(err)) return fail(err);
+      ncclUniqueId id; memcpy(&id, nccl_id, 128);
+      ncclComm_t comm;
+      if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice failed");
+      ncclResult_t r = g_nccl.CommInitRank(&comm, nranks, id, rank);
+      if (r != ncclSuccess) return fail(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+      ctx->nccl = comm;
+    }
     const int N2 = (degree + 1) * (degree + 1);
     const int pstride[3] = {1, pgrid[0], pgrid[0] * pgrid[1]};
     for (int f = 0; f < 6; f++) {
@@ -389,6 +454,11 @@ int hpdg_create_distributed(hpdg_ctx** out, int dim, const int* n, const double*
     ctx->ghost.arena_bytes = offb;
     if (cudaMalloc(&ctx->ghost.arena, offb) != cudaSuccess || cudaMemset(ctx->ghost.arena, 0, offb) != cudaSuccess)
       return fail("cudaMalloc of the halo arena failed");
+    int* herr = nullptr;
+    if (cudaHostAlloc(&herr, sizeof(int), cudaHostAllocMapped) != cudaSuccess) return fail("cudaHostAlloc of the halo time-out flag failed");
+    *herr = 0;
+    ctx->h_ghost_err = herr;
+    if (cudaHostGetDevicePointer(&ctx->d_ghost_err, herr, 0) != cudaSuccess) return fail("cudaHostGetDevicePointer failed");
   }
   *out = ctx;
   return 0;
@@ -403,6 +473,9 @@ void hpdg_destroy(hpdg_ctx* ctx) {
   for (auto& L : ctx->levels) free_level(L);
   for (int f = 0; f < 6; f++) { cudaFree(ctx->ghost.d_send[f]); cudaFree(ctx->ghost.d_recv[f]); if (ctx->ghost.peer_arena[f]) cudaIpcCloseMemHandle(ctx->ghost.peer_arena[f]); }
   cudaFree(ctx->ghost.arena);
+  if (ctx->h_ghost_err) cudaFreeHost(const_cast<int*>(ctx->h_ghost_err));
+  cudaFree(ctx->d_scalar); cudaFree(ctx->d_partial);
+  if (ctx->cg_p) { cudaFree(ctx->cg_p); cudaFree(ctx->cg_q); cudaFree(ctx->cg_r); cudaFree(ctx->cg_z); }
   cudaFree(ctx->d_tab); cudaFree(ctx->d_sched); cudaFree(ctx->d_P); cudaFree(ctx->d_T); cudaFree(ctx->d_Mab); cudaFree(ctx->d_in); cudaFree(ctx->d_out);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
@@ -416,10 +489,12 @@ void hpdg_destroy(hpdg_ctx* ctx) {
 const char* hpdg_last_error(const hpdg_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 int hpdg_set_option(hpdg_ctx* ctx, const char* name, long value) {
+  HPDG_ENTER(ctx);
   if (!strcmp(name, "force_generic")) { ctx->force_generic = (int)value; return 0; }
   if (!strcmp(name, "variant")) { ctx->variant = (int)value; return 0; }
   if (!strcmp(name, "q3p_grid")) { ctx->q3p_grid = (int)value; return 0; }
   if (!strcmp(name, "q3p_tune")) { ctx->q3p_tune = (int)value; return 0; }
+  if (!strcmp(name, "halo_timeout_ms")) { ctx->halo_timeout_cycles = (long long)value * 2000000LL; return 0; }  // ~2 GHz SM clock
   if (!strcmp(name, "halo_p2p")) {  // switch between the NVLink peer-memory halo and NCCL send/recv (attach must have succeeded for 1)
     if (value && !ctx->ghost.peer_attached) { ctx->err = "halo_p2p: hpdg_halo_ipc_attach has not succeeded on this context"; return 1; }
     ctx->ghost.p2p = value != 0; return 0;
@@ -447,6 +522,7 @@ int hpdg_level_degrees(const hpdg_ctx* ctx, int level, int* degree) {
 }
 
 int hpdg_build_p_hierarchy(hpdg_ctx* ctx) {
+  HPDG_ENTER(ctx);
   if (ctx->levels.size() != 1) { ctx->err = "hierarchy already built"; return 1; }
   Level fine = ctx->levels[0];
   const int pmax = fine.maxp;
@@ -459,7 +535,12 @@ int hpdg_build_p_hierarchy(hpdg_ctx* ctx) {
     std::vector<int> deg(fine.nelem);
     for (long e = 0; e < fine.nelem; e++) deg[e] = std::min(lv[idx + 1].deg[e], cap);  // ordertransfer.hh:62-67
     Level L;
-    if (setup_level(ctx, L, fine.dim, fine.n, fine.h, deg, fine.pdeg)) return 1;
+    if (setup_level(ctx, L, fine.dim, fine.n, fine.h, deg, fine.pdeg)) {  // leave the context as it was: one level
+      free_level(L);
+      for (int k = idx + 1; k < pLevels; k++) free_level(lv[k]);
+      ctx->levels.assign(1, fine);
+      return 1;
+    }
     lv[idx] = L;
   }
   ctx->levels = lv;
@@ -467,39 +548,31 @@ int hpdg_build_p_hierarchy(hpdg_ctx* ctx) {
 }
 
 int hpdg_vec_alloc(hpdg_ctx* ctx, int level, double** d_vec) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   HPDG_CUDA(cudaMalloc(d_vec, sizeof(double) * std::max<long>(L->ndof, 1)));
   HPDG_CUDA(cudaMemsetAsync(*d_vec, 0, sizeof(double) * L->ndof, ctx->stream));
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
-int hpdg_vec_free(hpdg_ctx* ctx, double* d_vec) { HPDG_CUDA(cudaFree(d_vec)); return 0; }
+int hpdg_vec_free(hpdg_ctx* ctx, double* d_vec) { HPDG_ENTER(ctx); HPDG_CUDA(cudaFree(d_vec)); return 0; }
 int hpdg_vec_upload(hpdg_ctx* ctx, int level, const double* h_src, double* d_dst) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   HPDG_CUDA(cudaMemcpyAsync(d_dst, h_src, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
 int hpdg_vec_download(hpdg_ctx* ctx, int level, const double* d_src, double* h_dst) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   HPDG_CUDA(cudaMemcpyAsync(h_dst, d_src, sizeof(double) * L->ndof, cudaMemcpyDeviceToHost, ctx->stream));
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
-int hpdg_host_alloc(hpdg_ctx* ctx, size_t bytes, void** h_ptr) { HPDG_CUDA(cudaMallocHost(h_ptr, bytes)); return 0; }
-int hpdg_host_free(hpdg_ctx* ctx, void* h_ptr) { HPDG_CUDA(cudaFreeHost(h_ptr)); return 0; }
-int hpdg_sync(hpdg_ctx* ctx) {
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream_comm));
-  if (ctx->ghost.p2p) {
-    int err = 0;
-    HPDG_CUDA(cudaMemcpy(&err, ctx->ghost.arena + ctx->ghost.flag_off + 12 * sizeof(int), sizeof(int), cudaMemcpyDeviceToHost));
-    if (err) { ctx->err = "halo exchange timed out waiting for a neighbour rank's face traces"; return 1; }
-  }
-  return 0;
-}
+int hpdg_host_alloc(hpdg_ctx* ctx, size_t bytes, void** h_ptr) { HPDG_ENTER(ctx); HPDG_CUDA(cudaMallocHost(h_ptr, bytes)); return 0; }
+int hpdg_host_free(hpdg_ctx* ctx, void* h_ptr) { HPDG_ENTER(ctx); HPDG_CUDA(cudaFreeHost(h_ptr)); return 0; }
+int hpdg_sync(hpdg_ctx* ctx) { HPDG_ENTER(ctx); return sync_check(ctx); }
 
 int hpdg_halo_ipc_handle(hpdg_ctx* ctx, void* out64) {
+  HPDG_ENTER(ctx);
   if (!ctx->ghost.arena) { ctx->err = "not a distributed context"; return 1; }
   cudaIpcMemHandle_t h;
   HPDG_CUDA(cudaIpcGetMemHandle(&h, ctx->ghost.arena));
@@ -508,6 +581,7 @@ int hpdg_halo_ipc_handle(hpdg_ctx* ctx, void* out64) {
   return 0;
 }
 int hpdg_halo_ipc_attach(hpdg_ctx* ctx, const void* handles /* nranks x 64 bytes, indexed by rank */) {
+  HPDG_ENTER(ctx);
   if (!ctx->ghost.arena) { ctx->err = "not a distributed context"; return 1; }
   for (int f = 0; f < 6; f++) {
     if (!ctx->ghost.active[f]) continue;
@@ -524,18 +598,20 @@ int hpdg_halo_ipc_attach(hpdg_ctx* ctx, const void* handles /* nranks x 64 bytes
 void* hpdg_stream(hpdg_ctx* ctx) { return (void*)ctx->stream; }
 
 int hpdg_op_apply_async(hpdg_ctx* ctx, int level, const double* d_x, double* d_y, double factor) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   return op_apply_async(ctx, *L, d_x, d_y, factor);
 }
 int hpdg_op_apply_device(hpdg_ctx* ctx, int level, const double* d_x, double* d_y, double factor) {
+  HPDG_ENTER(ctx);
   if (hpdg_op_apply_async(ctx, level, d_x, d_y, factor)) return 1;
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
 // Host-pointer apply as a 3-stage pipeline over z-slabs: H2D of slab c+1, tile kernel on slab c and D2H of slab c-1 run on
 // three streams, so the PCIe copies in both directions overlap each other and the compute (the kernel on slab c needs slabs
 // c-1..c+1 resident because of the z-neighbour traces).
 static int op_apply_host_chunked(hpdg_ctx* ctx, Level& L, const double* h_x, double* h_y, double factor) {
+  HPDG_ENTER(ctx);
   const int th = uniform_tile_height(L);
   const int layers = L.n[2];
   int nchunk = std::min(16, layers / th);
@@ -569,11 +645,11 @@ static int op_apply_host_chunked(hpdg_ctx* ctx, Level& L, const double* h_x, dou
                               cudaMemcpyDeviceToHost, ctx->stream_d2h));
   }
   HPDG_CUDA(cudaStreamSynchronize(ctx->stream_d2h));
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
 
 int hpdg_op_apply(hpdg_ctx* ctx, int level, const double* h_x, double* h_y, double factor) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   if (ensure_stage(ctx, L->ndof)) return 1;
   if (ctx->nranks == 1 && uniform_supported(ctx, *L) && L->n[2] >= 4 * uniform_tile_height(*L) && L->ndof >= (1 << 20))
@@ -581,33 +657,34 @@ int hpdg_op_apply(hpdg_ctx* ctx, int level, const double* h_x, double* h_y, doub
   HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_x, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
   if (op_apply_async(ctx, *L, ctx->d_in, ctx->d_out, factor)) return 1;
   HPDG_CUDA(cudaMemcpyAsync(h_y, ctx->d_out, sizeof(double) * L->ndof, cudaMemcpyDeviceToHost, ctx->stream));
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
 
 int hpdg_jacobi_setup(hpdg_ctx* ctx, int level, int form) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   if (form == HPDG_JACOBI_DENSE) return jacobi_setup_dense(ctx, *L);
   if (form == HPDG_JACOBI_FD) return jacobi_setup_fd(ctx, *L);
   ctx->err = "unknown block-Jacobi form"; return 1;
 }
 int hpdg_jacobi_apply_async(hpdg_ctx* ctx, int level, int form, const double* d_r, double* d_c, double damping) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   return jacobi_async(ctx, *L, form, d_r, d_c, damping);
 }
 int hpdg_jacobi_apply_device(hpdg_ctx* ctx, int level, int form, const double* d_r, double* d_c, double damping) {
+  HPDG_ENTER(ctx);
   if (hpdg_jacobi_apply_async(ctx, level, form, d_r, d_c, damping)) return 1;
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
 int hpdg_jacobi_apply(hpdg_ctx* ctx, int level, int form, const double* h_r, double* h_c, double damping) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   if (ensure_stage(ctx, L->ndof)) return 1;
   HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_r, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
   if (jacobi_async(ctx, *L, form, ctx->d_in, ctx->d_out, damping)) return 1;
   HPDG_CUDA(cudaMemcpyAsync(h_c, ctx->d_out, sizeof(double) * L->ndof, cudaMemcpyDeviceToHost, ctx->stream));
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
 size_t hpdg_jacobi_bytes(const hpdg_ctx* ctx, int level, int form) {
   Level* L = get_level(const_cast<hpdg_ctx*>(ctx), level); if (!L) return 0;
@@ -615,6 +692,7 @@ size_t hpdg_jacobi_bytes(const hpdg_ctx* ctx, int level, int form) {
   return (size_t)L->jf.nfac * (kMaxN * kMaxN + kMaxN) * sizeof(double) + (size_t)L->nelem * 3 * sizeof(int);
 }
 int hpdg_diag_block(hpdg_ctx* ctx, int level, long element, double* h_out) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   if (element < 0 || element >= L->nelem) { ctx->err = "element index out of range"; return 1; }
   int n1 = L->deg[element] + 1, ne = ipow_h(n1, L->dim);
@@ -627,6 +705,7 @@ int hpdg_diag_block(hpdg_ctx* ctx, int level, long element, double* h_out) {
 }
 
 int hpdg_bcrs_sizes(hpdg_ctx* ctx, int level, long* nblocks, long* nentries) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   long nb = 0, ne = 0;
   const long stride[3] = {1, L->n[0], (long)L->n[0] * L->n[1]};
@@ -647,6 +726,7 @@ int hpdg_bcrs_sizes(hpdg_ctx* ctx, int level, long* nblocks, long* nentries) {
   return 0;
 }
 int hpdg_assemble_bcrs(hpdg_ctx* ctx, int level, long* h_rowptr, int* h_col, long* h_boff, double* h_entries) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   if (ctx->nranks > 1) { ctx->err = "assembled export is single-rank"; return 1; }
   if (bcrs_build(ctx, *L)) return 1;
@@ -658,60 +738,62 @@ int hpdg_assemble_bcrs(hpdg_ctx* ctx, int level, long* h_rowptr, int* h_col, lon
   return 0;
 }
 int hpdg_bcrs_mv_device(hpdg_ctx* ctx, int level, const double* d_x, double* d_y) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   if (bcrs_mv(ctx, *L, d_x, d_y)) return 1;
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
 int hpdg_bcrs_mv(hpdg_ctx* ctx, int level, const double* h_x, double* h_y) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   if (ensure_stage(ctx, L->ndof)) return 1;
   HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_x, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
   if (bcrs_mv(ctx, *L, ctx->d_in, ctx->d_out)) return 1;
   HPDG_CUDA(cudaMemcpyAsync(h_y, ctx->d_out, sizeof(double) * L->ndof, cudaMemcpyDeviceToHost, ctx->stream));
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
 int hpdg_blockgs_iterate_device(hpdg_ctx* ctx, int level, const double* d_b, double* d_x) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   if (blockgs_iterate(ctx, *L, d_b, d_x)) return 1;
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
 int hpdg_blockgs_iterate(hpdg_ctx* ctx, int level, const double* h_b, double* h_x) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   if (ensure_stage(ctx, L->ndof)) return 1;
   HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_b, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
   HPDG_CUDA(cudaMemcpyAsync(ctx->d_out, h_x, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
   if (blockgs_iterate(ctx, *L, ctx->d_in, ctx->d_out)) return 1;
   HPDG_CUDA(cudaMemcpyAsync(h_x, ctx->d_out, sizeof(double) * L->ndof, cudaMemcpyDeviceToHost, ctx->stream));
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
 
 int hpdg_l1_setup(hpdg_ctx* ctx, int level, const long* ghosts, long nghost) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   if (nghost > 0 && !ghosts) { ctx->err = "ghost index list is null"; return 1; }
   return l1_setup(ctx, *L, ghosts, nghost);
 }
 int hpdg_l1_iterate_device(hpdg_ctx* ctx, int level, const double* d_b, double* d_x) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   if (blockgs_iterate(ctx, *L, d_b, d_x, 1)) return 1;
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
 int hpdg_l1_iterate(hpdg_ctx* ctx, int level, const double* h_b, double* h_x) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   if (ensure_stage(ctx, L->ndof)) return 1;
   HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_b, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
   HPDG_CUDA(cudaMemcpyAsync(ctx->d_out, h_x, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
   if (blockgs_iterate(ctx, *L, ctx->d_in, ctx->d_out, 1)) return 1;
   HPDG_CUDA(cudaMemcpyAsync(h_x, ctx->d_out, sizeof(double) * L->ndof, cudaMemcpyDeviceToHost, ctx->stream));
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
 
 static int xfer_host(hpdg_ctx* ctx, int fine_level, const double* h_in, double* h_out, bool restrict_) {
+  HPDG_ENTER(ctx);
   Level* F = get_level(ctx, fine_level); if (!F) return 1;
   int fl = (int)(F - &ctx->levels[0]);
   if (fl < 1) { ctx->err = "no coarser level below this one"; return 1; }
@@ -721,35 +803,35 @@ static int xfer_host(hpdg_ctx* ctx, int fine_level, const double* h_in, double* 
   HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_in, sizeof(double) * nin, cudaMemcpyHostToDevice, ctx->stream));
   if (restrict_ ? launch_restrict(ctx, *F, C, ctx->d_in, ctx->d_out) : launch_prolong(ctx, *F, C, ctx->d_in, ctx->d_out)) return 1;
   HPDG_CUDA(cudaMemcpyAsync(h_out, ctx->d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost, ctx->stream));
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
 int hpdg_restrict(hpdg_ctx* ctx, int fine_level, const double* h_fine, double* h_coarse) { return xfer_host(ctx, fine_level, h_fine, h_coarse, true); }
 int hpdg_prolong(hpdg_ctx* ctx, int fine_level, const double* h_coarse, double* h_fine) { return xfer_host(ctx, fine_level, h_coarse, h_fine, false); }
 int hpdg_restrict_device(hpdg_ctx* ctx, int fine_level, const double* d_fine, double* d_coarse) {
+  HPDG_ENTER(ctx);
   Level* F = get_level(ctx, fine_level); if (!F) return 1;
   int fl = (int)(F - &ctx->levels[0]);
   if (fl < 1) { ctx->err = "no coarser level below this one"; return 1; }
   if (launch_restrict(ctx, *F, ctx->levels[fl - 1], d_fine, d_coarse)) return 1;
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
 int hpdg_prolong_device(hpdg_ctx* ctx, int fine_level, const double* d_coarse, double* d_fine) {
+  HPDG_ENTER(ctx);
   Level* F = get_level(ctx, fine_level); if (!F) return 1;
   int fl = (int)(F - &ctx->levels[0]);
   if (fl < 1) { ctx->err = "no coarser level below this one"; return 1; }
   if (launch_prolong(ctx, *F, ctx->levels[fl - 1], d_coarse, d_fine)) return 1;
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
 
 int hpdg_vcycle_device(hpdg_ctx* ctx, int form, double damping, int pre, int post, int coarse_its, double* d_x, double* d_b) {
+  HPDG_ENTER(ctx);
   VC v = {form, damping, pre, post, coarse_its};
   if (vcycle_device(ctx, v, d_x, d_b)) return 1;
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
 int hpdg_vcycle(hpdg_ctx* ctx, int form, double damping, int pre, int post, int coarse_its, double* h_x, double* h_b) {
+  HPDG_ENTER(ctx);
   Level& F = ctx->levels.back();
   if (ensure_stage(ctx, F.ndof)) return 1;
   HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_x, sizeof(double) * F.ndof, cudaMemcpyHostToDevice, ctx->stream));
@@ -758,24 +840,201 @@ int hpdg_vcycle(hpdg_ctx* ctx, int form, double damping, int pre, int post, int 
   if (vcycle_device(ctx, v, ctx->d_in, ctx->d_out)) return 1;
   HPDG_CUDA(cudaMemcpyAsync(h_x, ctx->d_in, sizeof(double) * F.ndof, cudaMemcpyDeviceToHost, ctx->stream));
   HPDG_CUDA(cudaMemcpyAsync(h_b, ctx->d_out, sizeof(double) * F.ndof, cudaMemcpyDeviceToHost, ctx->stream));
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return sync_check(ctx);
 }
 
-int hpdg_dot_device(hpdg_ctx* ctx, int level, const double* d_x, const double* d_y, double* h_result) {
+// ---- accumulate mode: y += factor * A x -------------------------------------------------------------
+// Operator::apply over a TUPLE of local operators zeroes Ax once and lets every local operator add its own factor * (A x)
+// (matrix-free/operator.hh:42-55, test: matrix-free/test/testoperator.cc:80-98).  The first operator of a tuple maps to
+// hpdg_op_apply*, every further one to hpdg_op_apply_accum*.
+int hpdg_op_apply_accum_async(hpdg_ctx* ctx, int level, const double* d_x, double* d_y, double factor) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
-  static double* d_res = nullptr;
-  if (!d_res) HPDG_CUDA(cudaMalloc(&d_res, sizeof(double)));
-  if (launch_dot(ctx, L->ndof, d_x, d_y, d_res)) return 1;
+  ctx->fuse_accum = 1;
+  const int rc = op_apply_async(ctx, *L, d_x, d_y, factor);
+  ctx->fuse_accum = 0;
+  return rc;
+}
+int hpdg_op_apply_accum_device(hpdg_ctx* ctx, int level, const double* d_x, double* d_y, double factor) {
+  if (hpdg_op_apply_accum_async(ctx, level, d_x, d_y, factor)) return 1;
+  return sync_check(ctx);
+}
+int hpdg_op_apply_accum(hpdg_ctx* ctx, int level, const double* h_x, double* h_y, double factor) {
+  HPDG_ENTER(ctx);
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  if (ensure_stage(ctx, L->ndof)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_x, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
+  HPDG_CUDA(cudaMemcpyAsync(ctx->d_out, h_y, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->fuse_accum = 1;
+  const int rc = op_apply_async(ctx, *L, ctx->d_in, ctx->d_out, factor);
+  ctx->fuse_accum = 0;
+  if (rc) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(h_y, ctx->d_out, sizeof(double) * L->ndof, cudaMemcpyDeviceToHost, ctx->stream));
+  return sync_check(ctx);
+}
+
+// ---- BLAS-1 (DynamicBlockVector: common/dynamicbvector.hh:185-314) -----------------------------------
+// this rank's dot product into device scalar `slot`, summed over all ranks of a distributed context (NCCL on the same stream:
+// no host round trip)
+static int dot_to_slot(hpdg_ctx* ctx, long n, const double* d_x, const double* d_y, int slot) {
+  if (blas_scratch(ctx)) return 1;
+  if (launch_dot(ctx, n, d_x, d_y, ctx->d_scalar + slot)) return 1;
+  if (ctx->nranks > 1 && !ctx->nccl) { ctx->err = "dot product over ranks needs the NCCL communicator (context created with nccl_id = NULL)"; return 1; }
   if (ctx->nranks > 1)
-    HPDG_NCCL(g_nccl.AllReduce(d_res, d_res, 1, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
-  HPDG_CUDA(cudaMemcpyAsync(h_result, d_res, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+    HPDG_NCCL(g_nccl.AllReduce(ctx->d_scalar + slot, ctx->d_scalar + slot, 1, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
+  return 0;
+}
+int hpdg_dot_device(hpdg_ctx* ctx, int level, const double* d_x, const double* d_y, double* h_result) {
+  HPDG_ENTER(ctx);
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  if (dot_to_slot(ctx, L->ndof, d_x, d_y, 15)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(h_result, ctx->d_scalar + 15, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  return sync_check(ctx);
+}
+int hpdg_two_norm_device(hpdg_ctx* ctx, int level, const double* d_x, double* h_result) {
+  if (hpdg_dot_device(ctx, level, d_x, d_x, h_result)) return 1;
+  *h_result = std::sqrt(*h_result);
   return 0;
 }
 int hpdg_axpy_device(hpdg_ctx* ctx, int level, double a, const double* d_x, double* d_y) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
   return launch_axpy(ctx, L->ndof, a, d_x, d_y);
+}
+int hpdg_scale_device(hpdg_ctx* ctx, int level, double a, double* d_x) {
+  HPDG_ENTER(ctx);
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  return launch_scale(ctx, L->ndof, a, d_x);
+}
+int hpdg_assign_device(hpdg_ctx* ctx, int level, const double* d_src, double* d_dst) {
+  HPDG_ENTER(ctx);
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(d_dst, d_src, sizeof(double) * L->ndof, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+
+// ---- solver loops around the hot path ------------------------------------------------------------------
+// Preconditioned CG on the finest level, vectors and scalars resident on the device: per iteration one operator apply, one
+// preconditioner application, three dot products (each ending in a 1-double ncclAllReduce on the context stream when the
+// context is distributed) and two fused vector updates whose step lengths are read from device memory -- nothing returns
+// to the host except, every `check_every` iterations, the residual norm.
+//   precond: HPDG_PRECOND_NONE, HPDG_PRECOND_JACOBI (fd block Jacobi, `damping`), HPDG_PRECOND_VCYCLE (one V-cycle with fd
+//   block-Jacobi smoothing: `damping`, pre = post = `smooth`, `coarse_its` coarse iterations).
+// Stops when ||r||_2 <= tol * ||r_0||_2 or after maxit iterations.
+static int pcg_device(hpdg_ctx* ctx, int precond, double damping, int smooth, int coarse_its, double* d_x, const double* d_b,
+                      double tol, int maxit, int check_every, int* iters, double* relres) {
+  Level& F = ctx->levels.back();
+  const long n = F.ndof;
+  if (blas_scratch(ctx)) return 1;
+  if (!ctx->cg_p) {
+    HPDG_CUDA(cudaMalloc(&ctx->cg_p, sizeof(double) * n)); HPDG_CUDA(cudaMalloc(&ctx->cg_q, sizeof(double) * n));
+    HPDG_CUDA(cudaMalloc(&ctx->cg_r, sizeof(double) * n)); HPDG_CUDA(cudaMalloc(&ctx->cg_z, sizeof(double) * n));
+  }
+  double *p = ctx->cg_p, *q = ctx->cg_q, *r = ctx->cg_r, *z = ctx->cg_z;
+  if (precond == HPDG_PRECOND_JACOBI && !F.jf.ready) { if (jacobi_setup_fd(ctx, F)) return 1; }
+  if (check_every < 1) check_every = 1;
+  const VC vc = {HPDG_JACOBI_FD, damping, smooth, smooth, coarse_its};
+  auto apply_precond = [&](const double* rin, double* zout) -> int {
+    if (precond == HPDG_PRECOND_NONE) { HPDG_CUDA(cudaMemcpyAsync(zout, rin, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream)); return 0; }
+    if (precond == HPDG_PRECOND_JACOBI) return jacobi_async(ctx, F, HPDG_JACOBI_FD, rin, zout, damping);
+    // V-cycle: z = 0; z += MG(r); the cycle overwrites its right-hand side with the residual, so it works on a copy (q is free here)
+    HPDG_CUDA(cudaMemsetAsync(zout, 0, sizeof(double) * n, ctx->stream));
+    HPDG_CUDA(cudaMemcpyAsync(q, rin, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    return vcycle_device(ctx, vc, zout, q);
+  };
+  enum { RZ0 = 0, RZ1 = 1, PQ = 2, RR = 3 };
+  double rr0 = 0, rr = 0;
+  if (op_apply_async(ctx, F, d_x, q, 1.0)) return 1;
+  if (launch_xpay_sub(ctx, n, d_b, q, r)) return 1;                       // r = b - A x
+  if (dot_to_slot(ctx, n, r, r, RR)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(&rr0, ctx->d_scalar + RR, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (sync_check(ctx)) return 1;
+  rr = rr0;
+  int it = 0;
+  if (rr0 > 0) {
+    if (apply_precond(r, z)) return 1;
+    HPDG_CUDA(cudaMemcpyAsync(p, z, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (dot_to_slot(ctx, n, r, z, RZ0)) return 1;
+    for (it = 1; it <= maxit; it++) {
+      const int cur = (it - 1) & 1, nxt = it & 1;                         // rz of this / the next iteration
+      if (op_apply_async(ctx, F, p, q, 1.0)) return 1;                    // q = A p
+      if (dot_to_slot(ctx, n, p, q, PQ)) return 1;
+      if (launch_cg_update(ctx, n, cur, PQ, p, q, d_x, r)) return 1;      // x += (rz/pq) p ; r -= (rz/pq) q
+      if (dot_to_slot(ctx, n, r, r, RR)) return 1;
+      if (it % check_every == 0 || it == maxit) {
+        HPDG_CUDA(cudaMemcpyAsync(&rr, ctx->d_scalar + RR, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (sync_check(ctx)) return 1;
+        if (!(rr == rr)) { ctx->err = "pcg: residual is not a number (operator or preconditioner not SPD?)"; return 1; }
+        if (std::sqrt(rr) <= tol * std::sqrt(rr0)) break;
+      }
+      if (apply_precond(r, z)) return 1;
+      if (dot_to_slot(ctx, n, r, z, nxt)) return 1;
+      if (launch_cg_direction(ctx, n, nxt, cur, z, p)) return 1;          // p = z + (rz_new/rz) p
+    }
+    if (it > maxit) it = maxit;
+  }
+  if (iters) *iters = it;
+  if (relres) *relres = rr0 > 0 ? std::sqrt(rr / rr0) : 0.0;
+  return sync_check(ctx);
+}
+int hpdg_pcg_device(hpdg_ctx* ctx, int precond, double damping, int smooth, int coarse_its, double* d_x, const double* d_b,
+                    double tol, int maxit, int check_every, int* iters, double* relres) {
+  HPDG_ENTER(ctx);
+  if (precond < HPDG_PRECOND_NONE || precond > HPDG_PRECOND_VCYCLE) { ctx->err = "unknown preconditioner"; return 1; }
+  return pcg_device(ctx, precond, damping, smooth, coarse_its, d_x, d_b, tol, maxit, check_every, iters, relres);
+}
+int hpdg_pcg(hpdg_ctx* ctx, int precond, double damping, int smooth, int coarse_its, double* h_x, const double* h_b, double tol,
+             int maxit, int check_every, int* iters, double* relres) {
+  HPDG_ENTER(ctx);
+  Level& F = ctx->levels.back();
+  if (ensure_stage(ctx, F.ndof)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_x, sizeof(double) * F.ndof, cudaMemcpyHostToDevice, ctx->stream));
+  HPDG_CUDA(cudaMemcpyAsync(ctx->d_out, h_b, sizeof(double) * F.ndof, cudaMemcpyHostToDevice, ctx->stream));
+  if (hpdg_pcg_device(ctx, precond, damping, smooth, coarse_its, ctx->d_in, ctx->d_out, tol, maxit, check_every, iters, relres)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(h_x, ctx->d_in, sizeof(double) * F.ndof, cudaMemcpyDeviceToHost, ctx->stream));
+  return sync_check(ctx);
+}
+
+// Dune::Solvers::LoopSolver around the multigrid step with the energy norm as the reference wires it (buildingblocks/solve.hh:150-166,
+// iterationsteps/mg/mgwrapper.hh:22-27): per iteration the step works on a COPY of the right-hand side (the cycle overwrites it),
+// the error measure is the energy norm of the correction ||x_k - x_{k-1}||_A divided by ||x_{k-1}||_A (useRelativeError = true;
+// dune-solvers' LoopSolver is un-vendored, this is its documented behaviour: with a zero old iterate the quotient is infinite and the
+// loop goes on); the loop stops when the measure drops below tol or after maxit iterations.  Each energy norm costs one operator
+// apply + one dot product.
+int hpdg_loop_solve_device(hpdg_ctx* ctx, int form, double damping, int pre, int post, int coarse_its, double* d_x,
+                           const double* d_b, double tol, int maxit, int* iters, double* last_error) {
+  HPDG_ENTER(ctx);
+  Level& F = ctx->levels.back();
+  const long n = F.ndof;
+  if (blas_scratch(ctx)) return 1;
+  if (!ctx->cg_p) {
+    HPDG_CUDA(cudaMalloc(&ctx->cg_p, sizeof(double) * n)); HPDG_CUDA(cudaMalloc(&ctx->cg_q, sizeof(double) * n));
+    HPDG_CUDA(cudaMalloc(&ctx->cg_r, sizeof(double) * n)); HPDG_CUDA(cudaMalloc(&ctx->cg_z, sizeof(double) * n));
+  }
+  double *old = ctx->cg_p, *rhs = ctx->cg_q, *corr = ctx->cg_r, *acorr = ctx->cg_z;
+  const VC vc = {form, damping, pre, post, coarse_its};
+  int it = 0;
+  double err = 0;
+  for (it = 1; it <= maxit; it++) {
+    HPDG_CUDA(cudaMemcpyAsync(old, d_x, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    HPDG_CUDA(cudaMemcpyAsync(rhs, d_b, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));   // mgwrapper.hh:23
+    if (vcycle_device(ctx, vc, d_x, rhs)) return 1;
+    if (launch_xpay_sub(ctx, n, d_x, old, corr)) return 1;                                               // correction
+    if (op_apply_async(ctx, F, corr, acorr, 1.0)) return 1;
+    if (dot_to_slot(ctx, n, corr, acorr, 4)) return 1;                                                   // ||c||_A^2
+    if (op_apply_async(ctx, F, old, acorr, 1.0)) return 1;
+    if (dot_to_slot(ctx, n, old, acorr, 5)) return 1;                                                    // ||x_old||_A^2
+    double h[2] = {0, 0};
+    HPDG_CUDA(cudaMemcpyAsync(h, ctx->d_scalar + 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sync_check(ctx)) return 1;
+    const double nc = std::sqrt(std::max(h[0], 0.0)), no = std::sqrt(std::max(h[1], 0.0));
+    err = no > 0 ? nc / no : (nc > 0 ? INFINITY : 0.0);
+    if (err < tol) break;
+  }
+  if (it > maxit) it = maxit;
+  if (iters) *iters = it;
+  if (last_error) *last_error = err;
+  return 0;
 }
 
 long hpdg_launch_count(const hpdg_ctx* ctx) { return ctx->launches; }
@@ -784,33 +1043,15 @@ int hpdg_uses_uniform_kernel(const hpdg_ctx* ctx, int level) {
   return L ? uniform_supported(ctx, *L) : 0;
 }
 int hpdg_time_apply_device(hpdg_ctx* ctx, int level, const double* d_x, double* d_y, int reps, float* ms_per_apply) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
-  cudaEvent_t e0, e1;
-  HPDG_CUDA(cudaEventCreate(&e0)); HPDG_CUDA(cudaEventCreate(&e1));
-  HPDG_CUDA(cudaEventRecord(e0, ctx->stream));
-  for (int i = 0; i < reps; i++) if (op_apply_async(ctx, *L, d_x, d_y, 1.0)) return 1;
-  HPDG_CUDA(cudaEventRecord(e1, ctx->stream));
-  HPDG_CUDA(cudaEventSynchronize(e1));
-  float ms = 0;
-  HPDG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-  *ms_per_apply = ms / reps;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  return 0;
+  return time_launches(ctx, reps, ms_per_apply, [&]() { return op_apply_async(ctx, *L, d_x, d_y, 1.0); });
 }
 int hpdg_time_jacobi_device(hpdg_ctx* ctx, int level, int form, const double* d_r, double* d_c, double damping, int reps,
                             float* ms_per_apply) {
+  HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
-  cudaEvent_t e0, e1;
-  HPDG_CUDA(cudaEventCreate(&e0)); HPDG_CUDA(cudaEventCreate(&e1));
-  HPDG_CUDA(cudaEventRecord(e0, ctx->stream));
-  for (int i = 0; i < reps; i++) if (jacobi_async(ctx, *L, form, d_r, d_c, damping)) return 1;
-  HPDG_CUDA(cudaEventRecord(e1, ctx->stream));
-  HPDG_CUDA(cudaEventSynchronize(e1));
-  float ms = 0;
-  HPDG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-  *ms_per_apply = ms / reps;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  return 0;
+  return time_launches(ctx, reps, ms_per_apply, [&]() { return jacobi_async(ctx, *L, form, d_r, d_c, damping); });
 }
 
 }  // extern "C"

@@ -28,7 +28,6 @@
 #include "ctx.hpp"
 #include "uniform_common.cuh"
 #include "apply_uniform_q3p.cuh"
-#include "apply_uniform_q3e.cuh"
 
 namespace hpdg {
 
@@ -38,16 +37,14 @@ constexpr int uni_threads() {
   return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
-// One tile.  FULL: the tile lies completely inside the brick (all masks compile away).
-struct ZTrace { double pd, pv, nd, nv; int pm, nm; };
-struct NoHook { __device__ __forceinline__ void operator()() const {} };
-
-// PIPE: u of the tile is already in su (cp.async prefetch) and the z traces come in through zt;
-// hook() runs between P3 and P4 (the pipelined kernel issues the next tile's z-halo loads there).
-template <int N, int TX, int TY, int TZ, bool FULL, bool EARLY, bool PIPE = false, class Hook = NoHook>
+// One tile.  FULL: the tile has the full TX x TY x TZ extent (all masks compile away).
+// The outside traces of every pass are loaded in two steps (uniform_common.cuh: halo_issue / halo_reduce): the loads of a
+// pass are issued before the barrier that opens it and reduced to (der, val) pairs after it, so no warp waits on L2 in
+// front of a barrier.
+template <int N, int TX, int TY, int TZ, bool FULL>
 __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restrict__ su, double* __restrict__ sw,
                                           const int x0, const int y0, const int z0, const int lenx_rt, const int leny_rt,
-                                          const int lenz_rt, const ZTrace zt = ZTrace(), Hook hook = Hook()) {
+                                          const int lenz_rt) {
   constexpr int PP = Pitch<N>::PP, EP = Pitch<N>::EP;
   constexpr int N2 = N * N, N3 = N * N * N;
   const int lenx = FULL ? TX : lenx_rt, leny = FULL ? TY : leny_rt, lenz = FULL ? TZ : lenz_rt;
@@ -66,39 +63,6 @@ __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restr
   const int yi = tid % N, yex = (tid / N) % TX, yk = (tid / (N * TX)) % N, yez = tid / (N2 * TX);
   const bool yact = (tid < N2 * TX * TZ) && yex < lenx && yez < lenz;
 
-  // ---------------- outside traces for the x- and y-roles (issued early) ----------------
-  double xpd = 0, xpv = 0, xnd = 0, xnv = 0; int xpm = 0, xnm = 0;
-  auto load_xtr = [&]() {
-  if (xact) {
-    const long erow = (long)(y0 + xey) * sy + (long)(z0 + xez) * sz;  // element (0, y, z)
-    const int node = xj + N * xk;
-    if (x0 == 0) {
-      xpm = P.bmode[0];
-      if (xpm == 3) { const double* gp = P.ghost[0] + (((long)(y0 + xey) + (long)P.n[1] * (z0 + xez)) * N2 + node) * 2; xpd = __ldcg(gp); xpv = __ldcg(gp + 1); xpm = 0; }
-    } else outside_trace<N>(P, X + erow + (long)(x0 - 1) * sx + N * xj + N2 * xk, 1, 1, xpd, xpv);
-    if (x0 + lenx == P.n[0]) {
-      xnm = P.bmode[1];
-      if (xnm == 3) { const double* gp = P.ghost[1] + (((long)(y0 + xey) + (long)P.n[1] * (z0 + xez)) * N2 + node) * 2; xnd = __ldcg(gp); xnv = __ldcg(gp + 1); xnm = 0; }
-    } else outside_trace<N>(P, X + erow + (long)(x0 + lenx) * sx + N * xj + N2 * xk, 1, 0, xnd, xnv);
-  }
-  };
-  double ypd = 0, ypv = 0, ynd = 0, ynv = 0; int ypm = 0, ynm = 0;
-  auto load_ytr = [&]() {
-  if (yact) {
-    const long ecol = (long)(x0 + yex) * sx + (long)(z0 + yez) * sz;  // element (x, 0, z)
-    const int node = yi + N * yk;
-    if (y0 == 0) {
-      ypm = P.bmode[2];
-      if (ypm == 3) { const double* gp = P.ghost[2] + (((long)(x0 + yex) + (long)P.n[0] * (z0 + yez)) * N2 + node) * 2; ypd = __ldcg(gp); ypv = __ldcg(gp + 1); ypm = 0; }
-    } else outside_trace<N>(P, X + ecol + (long)(y0 - 1) * sy + yi + N2 * yk, N, 1, ypd, ypv);
-    if (y0 + leny == P.n[1]) {
-      ynm = P.bmode[3];
-      if (ynm == 3) { const double* gp = P.ghost[3] + (((long)(x0 + yex) + (long)P.n[0] * (z0 + yez)) * N2 + node) * 2; ynd = __ldcg(gp); ynv = __ldcg(gp + 1); ynm = 0; }
-    } else outside_trace<N>(P, X + ecol + (long)(y0 + leny) * sy + yi + N2 * yk, N, 0, ynd, ynv);
-  }
-  };
-  if (EARLY) { load_xtr(); load_ytr(); }
-
   // ---------------- P1: z-pencils, global -> registers -> smem ----------------
   if (zact) {
     const long ecol = (long)(x0 + zex) * sx + (long)(y0 + zey) * sy;  // element (x, y, 0)
@@ -108,59 +72,66 @@ __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restr
 #pragma unroll
     for (int e = 0; e < TZ; e++)
 #pragma unroll
-      for (int k = 0; k < N; k++) {
-        if (PIPE) v[e][k] = (FULL || e < lenz) ? su[zbase + TX * TY * EP * e + PP * k] : 0.0;
-        else v[e][k] = (FULL || e < lenz) ? __ldg(X + ecol + (long)(z0 + e) * sz + node + N2 * k) : 0.0;
-      }
-    double pd = 0, pv = 0, nd = 0, nv = 0; int pm = 0, nm = 0;
-    if (PIPE) { pd = zt.pd; pv = zt.pv; nd = zt.nd; nv = zt.nv; pm = zt.pm; nm = zt.nm; }
-    else {
-    if (z0 == 0) {
-      pm = P.bmode[4];
-      if (pm == 3) { const double* gp = P.ghost[4] + (((long)(x0 + zex) + (long)P.n[0] * (y0 + zey)) * N2 + node) * 2; pd = __ldcg(gp); pv = __ldcg(gp + 1); pm = 0; }
-    } else outside_trace<N>(P, X + ecol + (long)(z0 - 1) * sz + node, N2, 1, pd, pv);
-    if (z0 + lenz == P.n[2]) {
-      nm = P.bmode[5];
-      if (nm == 3) { const double* gp = P.ghost[5] + (((long)(x0 + zex) + (long)P.n[0] * (y0 + zey)) * N2 + node) * 2; nd = __ldcg(gp); nv = __ldcg(gp + 1); nm = 0; }
-    } else outside_trace<N>(P, X + ecol + (long)(z0 + lenz) * sz + node, N2, 0, nd, nv);
-    }
-    pencil_apply<N, TZ, 2, FULL>(P, v, lenz, pd, pv, pm, nd, nv, nm,
+      for (int k = 0; k < N; k++) v[e][k] = (FULL || e < lenz) ? __ldg(X + ecol + (long)(z0 + e) * sz + node + N2 * k) : 0.0;
+    const long fe = (((long)(x0 + zex) + (long)P.n[0] * (y0 + zey)) * N2 + node) * 2;
+    const HaloRaw<N> hr = halo_issue<N>(z0 == 0 ? P.bmode[4] : 0, z0 + lenz == P.n[2] ? P.bmode[5] : 0,
+                                        X + ecol + (long)(z0 - 1) * sz + node, X + ecol + (long)(z0 + lenz) * sz + node, N2,
+                                        P.ghost[4] + fe, P.ghost[5] + fe);
+    const HaloTrace h = halo_reduce<N>(P, hr);
+    pencil_apply<N, TZ, 2, FULL>(P, v, lenz, h.pd, h.pv, h.pm, h.nd, h.nv, h.nm,
       [](int, int) { return 0.0; },
       [&](int e, const double (&a)[N]) {
         const int base = zbase + TX * TY * EP * e;
 #pragma unroll
-        for (int k = 0; k < N; k++) { if (!PIPE) su[base + PP * k] = v[e][k]; sw[base + PP * k] = a[k]; }
+        for (int k = 0; k < N; k++) { su[base + PP * k] = v[e][k]; sw[base + PP * k] = a[k]; }
       });
+  }
+  HaloRaw<N> hxr = HaloRaw<N>();
+  if (xact) {
+    const long erow = (long)(y0 + xey) * sy + (long)(z0 + xez) * sz;  // element (0, y, z)
+    const long fe = (((long)(y0 + xey) + (long)P.n[1] * (z0 + xez)) * N2 + xj + N * xk) * 2;
+    hxr = halo_issue<N>(x0 == 0 ? P.bmode[0] : 0, x0 + lenx == P.n[0] ? P.bmode[1] : 0,
+                        X + erow + (long)(x0 - 1) * sx + N * xj + N2 * xk, X + erow + (long)(x0 + lenx) * sx + N * xj + N2 * xk, 1,
+                        P.ghost[0] + fe, P.ghost[1] + fe);
   }
   __syncthreads();
 
   // ---------------- P2: x-pencils ----------------
-  if (!EARLY) { load_xtr(); load_ytr(); }
   if (xact) {
+    const HaloTrace h = halo_reduce<N>(P, hxr);
     double v[TX][N];
     const int xbase = TX * (xey + TY * xez) * EP + N * xj + PP * xk;
 #pragma unroll
     for (int e = 0; e < TX; e++)
 #pragma unroll
       for (int i = 0; i < N; i++) v[e][i] = (FULL || e < lenx) ? su[xbase + e * EP + i] : 0.0;
-    pencil_apply<N, TX, 0, FULL>(P, v, lenx, xpd, xpv, xpm, xnd, xnv, xnm,
+    pencil_apply<N, TX, 0, FULL>(P, v, lenx, h.pd, h.pv, h.pm, h.nd, h.nv, h.nm,
       [&](int e, int i) { return sw[xbase + e * EP + i]; },
       [&](int e, const double (&a)[N]) {
 #pragma unroll
         for (int i = 0; i < N; i++) sw[xbase + e * EP + i] = a[i];
       });
   }
+  HaloRaw<N> hyr = HaloRaw<N>();
+  if (yact) {
+    const long ecol = (long)(x0 + yex) * sx + (long)(z0 + yez) * sz;  // element (x, 0, z)
+    const long fe = (((long)(x0 + yex) + (long)P.n[0] * (z0 + yez)) * N2 + yi + N * yk) * 2;
+    hyr = halo_issue<N>(y0 == 0 ? P.bmode[2] : 0, y0 + leny == P.n[1] ? P.bmode[3] : 0,
+                        X + ecol + (long)(y0 - 1) * sy + yi + N2 * yk, X + ecol + (long)(y0 + leny) * sy + yi + N2 * yk, N,
+                        P.ghost[2] + fe, P.ghost[3] + fe);
+  }
   __syncthreads();
 
   // ---------------- P3: y-pencils, then M_y ----------------
   if (yact) {
+    const HaloTrace h = halo_reduce<N>(P, hyr);
     double v[TY][N];
     const int ybase = (yex + TX * TY * yez) * EP + yi + PP * yk;
 #pragma unroll
     for (int e = 0; e < TY; e++)
 #pragma unroll
       for (int j = 0; j < N; j++) v[e][j] = (FULL || e < leny) ? su[ybase + TX * EP * e + N * j] : 0.0;
-    pencil_apply<N, TY, 1, FULL>(P, v, leny, ypd, ypv, ypm, ynd, ynv, ynm,
+    pencil_apply<N, TY, 1, FULL>(P, v, leny, h.pd, h.pv, h.pm, h.nd, h.nv, h.nm,
       [&](int e, int j) { return sw[ybase + TX * EP * e + N * j]; },
       [&](int e, const double (&a)[N]) {
         double b[N];
@@ -172,7 +143,6 @@ __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restr
       });
   }
   __syncthreads();
-  hook();
 
   // ---------------- P4: M_x ----------------
   if (xact) {
@@ -211,7 +181,7 @@ __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restr
   }
 }
 
-template <int N, int TX, int TY, int TZ, int MINB, bool EARLY>
+template <int N, int TX, int TY, int TZ, int MINB>
 __global__ void __launch_bounds__(uni_threads<N, TX, TY, TZ>(), MINB)
 k_apply_uniform(const __grid_constant__ UniParams<N> P) {
   constexpr int EP = Pitch<N>::EP;
@@ -237,7 +207,10 @@ k_apply_uniform(const __grid_constant__ UniParams<N> P) {
           const volatile int* fl = P.ghost_flag[f];
           while (*fl < P.ghost_step) {
             __nanosleep(200);
-            if (clock64() - tstart > 4000000000LL) { atomicExch(P.ghost_err, 1); break; }  // ~2 s: give up, never hang the GPU
+            if (*reinterpret_cast<volatile int*>(P.ghost_err)) break;  // another tile already timed out: do not wait again
+            if (clock64() - tstart > P.ghost_timeout) {  // give up, never hang the GPU; every synchronising entry point reports it
+              atomicExch(P.ghost_err, 1); *reinterpret_cast<volatile int*>(P.ghost_err_host) = 1; __threadfence_system(); break;
+            }
           }
         }
         __threadfence();
@@ -245,141 +218,8 @@ k_apply_uniform(const __grid_constant__ UniParams<N> P) {
       __syncthreads();
     }
   }
-  if (lenx == TX && leny == TY && lenz == TZ) tile_body<N, TX, TY, TZ, true, EARLY>(P, su, sw, x0, y0, z0, TX, TY, TZ);
-  else tile_body<N, TX, TY, TZ, false, EARLY>(P, su, sw, x0, y0, z0, lenx, leny, lenz);
-}
-
-// ---- persistent, software-pipelined variant -----------------------------------------------------
-// One CTA per SM slot loops over tiles (stride gridDim.x, x-fastest so concurrently running CTAs work on
-// neighbouring tiles and their halo reads hit L2).  While tile t is computed, tile t+1's DoF blocks stream
-// from HBM straight into the second shared-memory u buffer with cp.async (no registers held), and its
-// z-halo lines are fetched between P3 and P4; a CTA therefore always has ~one tile of HBM reads in flight.
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K) : "memory"); }
-
-template <int N, int TX, int TY, int TZ>
-__global__ void __launch_bounds__(uni_threads<N, TX, TY, TZ>(), 2)
-k_apply_uniform_pipe(const __grid_constant__ UniParams<N> P) {
-  constexpr int PP = Pitch<N>::PP, EP = Pitch<N>::EP;
-  constexpr int N2 = N * N, N3 = N * N * N;
-  extern __shared__ double sm[];
-  double* subuf[2] = {sm, sm + TX * TY * TZ * EP};
-  double* sw = sm + 2 * TX * TY * TZ * EP;
-  const long ntiles = (long)P.ntile[0] * P.ntile[1] * P.ntile[2];
-  const long G = gridDim.x;
-  const long sx = N3, sy = (long)P.n[0] * N3, sz = (long)P.n[0] * P.n[1] * N3;
-  const double* __restrict__ X = P.x;
-  const int tid = threadIdx.x;
-  const int zi = tid % N, zj = (tid / N) % N, zex = (tid / N2) % TX, zey = tid / (N2 * TX);
-  const bool zrole = tid < N2 * TX * TY;
-  const int node = zi + N * zj;
-
-  struct Tile { int x0, y0, z0, lenx, leny, lenz; };
-  auto coords = [&](long t) {
-    Tile c;
-    const int tx = (int)(t % P.ntile[0]); t /= P.ntile[0];
-    const int ty = (int)(t % P.ntile[1]); const int tz = (int)(t / P.ntile[1]);
-    c.x0 = tx * TX; c.y0 = ty * TY; c.z0 = tz * TZ;
-    c.lenx = min(TX, P.n[0] - c.x0); c.leny = min(TY, P.n[1] - c.y0); c.lenz = min(TZ, P.n[2] - c.z0);
-    return c;
-  };
-  auto next_valid = [&](long t) {
-    if (P.part == 0) return t;
-    for (; t < ntiles; t += G) {
-      const Tile c = coords(t);
-      const bool touch = (c.x0 == 0 && P.bmode[0] == 3) || (c.x0 + c.lenx == P.n[0] && P.bmode[1] == 3) ||
-                         (c.y0 == 0 && P.bmode[2] == 3) || (c.y0 + c.leny == P.n[1] && P.bmode[3] == 3) ||
-                         (c.z0 == 0 && P.bmode[4] == 3) || (c.z0 + c.lenz == P.n[2] && P.bmode[5] == 3);
-      if ((P.part == 1) != touch) break;
-    }
-    return t;
-  };
-  auto issue_tile = [&](const Tile& c, double* sbuf) {
-    if (zrole && zex < c.lenx && zey < c.leny) {
-      const double* src = X + (long)(c.x0 + zex) * sx + (long)(c.y0 + zey) * sy + (long)c.z0 * sz + node;
-      double* dst = sbuf + (zex + TX * zey) * EP + node;
-#pragma unroll
-      for (int e = 0; e < TZ; e++)
-        if (e < c.lenz) {
-#pragma unroll
-          for (int k = 0; k < N; k++) cp_async8(dst + TX * TY * EP * e + PP * k, src + (long)e * sz + N2 * k);
-        }
-    }
-  };
-  // z-halo of a tile: raw DoF lines of the elements below / above (or the ghost trace / boundary mode)
-  auto load_zraw = [&](const Tile& c, double (&zr)[2][N], int& pm, int& nm) {
-    pm = nm = 0;
-    if (!(zrole && zex < c.lenx && zey < c.leny)) return;
-    const long ecol = (long)(c.x0 + zex) * sx + (long)(c.y0 + zey) * sy;
-    const long fe = ((long)(c.x0 + zex) + (long)P.n[0] * (c.y0 + zey)) * N2 + node;
-    if (c.z0 == 0) {
-      pm = P.bmode[4];
-      if (pm == 3) { zr[0][0] = __ldcg(P.ghost[4] + fe * 2); zr[0][1] = __ldcg(P.ghost[4] + fe * 2 + 1); pm = 4; }
-    } else {
-#pragma unroll
-      for (int k = 0; k < N; k++) zr[0][k] = __ldg(X + ecol + (long)(c.z0 - 1) * sz + node + N2 * k);
-    }
-    if (c.z0 + c.lenz == P.n[2]) {
-      nm = P.bmode[5];
-      if (nm == 3) { zr[1][0] = __ldcg(P.ghost[5] + fe * 2); zr[1][1] = __ldcg(P.ghost[5] + fe * 2 + 1); nm = 4; }
-    } else {
-#pragma unroll
-      for (int k = 0; k < N; k++) zr[1][k] = __ldg(X + ecol + (long)(c.z0 + c.lenz) * sz + node + N2 * k);
-    }
-  };
-  auto reduce_zraw = [&](const double (&zr)[2][N], int pm, int nm) {
-    ZTrace z; z.pd = z.pv = z.nd = z.nv = 0; z.pm = pm; z.nm = nm;
-    if (pm == 4) { z.pd = zr[0][0]; z.pv = zr[0][1]; z.pm = 0; }
-    else if (pm == 0) {
-      double d = 0;
-#pragma unroll
-      for (int k = 0; k < N; k++) d = fma(P.g[1][k], zr[0][k], d);
-      z.pd = d; z.pv = zr[0][N - 1];
-    }
-    if (nm == 4) { z.nd = zr[1][0]; z.nv = zr[1][1]; z.nm = 0; }
-    else if (nm == 0) {
-      double d = 0;
-#pragma unroll
-      for (int k = 0; k < N; k++) d = fma(P.g[0][k], zr[1][k], d);
-      z.nd = d; z.nv = zr[1][0];
-    }
-    return z;
-  };
-
-  long t = next_valid(blockIdx.x);
-  if (t >= ntiles) return;
-  Tile cur = coords(t);
-  issue_tile(cur, subuf[0]);
-  cp_async_commit();
-  ZTrace zt;
-  {
-    double zr[2][N] = {}; int pm, nm;
-    load_zraw(cur, zr, pm, nm);
-    zt = reduce_zraw(zr, pm, nm);
-  }
-  int buf = 0;
-  while (true) {
-    const long tn = next_valid(t + G);
-    const bool has_next = tn < ntiles;
-    Tile nxt = cur;
-    if (has_next) { nxt = coords(tn); issue_tile(nxt, subuf[buf ^ 1]); }
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    double zr[2][N] = {}; int npm = 0, nnm = 0;
-    auto hook = [&]() { if (has_next) load_zraw(nxt, zr, npm, nnm); };
-    if (cur.lenx == TX && cur.leny == TY && cur.lenz == TZ)
-      tile_body<N, TX, TY, TZ, true, true, true>(P, subuf[buf], sw, cur.x0, cur.y0, cur.z0, TX, TY, TZ, zt, hook);
-    else
-      tile_body<N, TX, TY, TZ, false, true, true>(P, subuf[buf], sw, cur.x0, cur.y0, cur.z0, cur.lenx, cur.leny, cur.lenz, zt, hook);
-    if (!has_next) break;
-    zt = reduce_zraw(zr, npm, nnm);
-    cur = nxt; t = tn; buf ^= 1;
-  }
+  if (lenx == TX && leny == TY && lenz == TZ) tile_body<N, TX, TY, TZ, true>(P, su, sw, x0, y0, z0, TX, TY, TZ);
+  else tile_body<N, TX, TY, TZ, false>(P, su, sw, x0, y0, z0, lenx, leny, lenz);
 }
 
 // ---- ghost trace packing (sender side of the halo exchange) -------------------------
@@ -446,7 +286,7 @@ int uniform_tile_lists(Ctx* ctx, Level& L, int TX, int TY, int TZ, const int* bm
   return 0;
 }
 
-template <int N, int TX, int TY, int TZ, int MINB, bool EARLY = true>
+template <int N, int TX, int TY, int TZ, int MINB>
 static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream) {
   static thread_local UniParams<N> P;  // rebuilt per call (cheap); static to keep it off the stack, per thread: contexts on different host threads launch concurrently
   const DegTable& T = host_tables().deg[N - 1];
@@ -488,6 +328,7 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
   }
   P.ghost_step = (finest && ctx->ghost.p2p && part == 3) ? ctx->ghost.step : 0;
   P.ghost_err = ctx->ghost.p2p ? reinterpret_cast<int*>(ctx->ghost.arena + ctx->ghost.flag_off) + 12 : nullptr;
+  P.ghost_err_host = ctx->d_ghost_err; P.ghost_timeout = ctx->halo_timeout_cycles;
   P.x = x; P.y = y; P.part = part; P.accum = ctx->fuse_accum;
   P.tile_list = nullptr; P.tile_offset = 0; P.tile_rot = 0;
   long nlist = 0;
@@ -499,32 +340,8 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
     nlist = part == 1 ? L.n_tiles_int : part == 2 ? L.n_tiles_bnd : L.n_tiles_int + L.n_tiles_bnd;
     if (nlist == 0) return 0;
   }
-  if (ctx->variant >= 10 && ctx->variant < 20 && part == 0 && ctx->slab_nz == 0 && !ctx->fuse_accum) {
-    constexpr int threads = uni_threads<N, TX, TY, TZ>();
-    constexpr size_t smem = sizeof(double) * 3 * TX * TY * TZ * Pitch<N>::EP;
-    static bool attr_set_pipe = false;
-    static int grid = 0;
-    if (!attr_set_pipe) {
-      HPDG_CUDA(cudaFuncSetAttribute(k_apply_uniform_pipe<N, TX, TY, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      int nsm = 0, occ = 0;
-      HPDG_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
-      HPDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_apply_uniform_pipe<N, TX, TY, TZ>, threads, smem));
-      grid = nsm * (occ > 0 ? occ : 1);
-      attr_set_pipe = true;
-    }
-    const long ntiles = (long)P.ntile[0] * P.ntile[1] * P.ntile[2];
-    k_apply_uniform_pipe<N, TX, TY, TZ><<<(unsigned)std::min<long>(grid, ntiles), threads, smem, ctx->stream>>>(P);
-    ctx->launches++;
-    HPDG_CUDA(cudaGetLastError());
-    return 0;
-  }
   constexpr int threads = uni_threads<N, TX, TY, TZ>();
   constexpr size_t smem = sizeof(double) * 2 * TX * TY * TZ * Pitch<N>::EP;
-  static bool attr_set = false;
-  if (!attr_set) {
-    HPDG_CUDA(cudaFuncSetAttribute(k_apply_uniform<N, TX, TY, TZ, MINB, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
   const long ntiles_total = (long)P.ntile[0] * P.ntile[1] * P.ntile[2];
   long ntiles = (part == 1 || part == 2) ? nlist : ntiles_total;
   if (part == 0 && ctx->slab_nz > 0) {  // element layers [slab_z0, slab_z0 + slab_nz): must be multiples of TZ
@@ -532,67 +349,37 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
     P.tile_offset = (ctx->slab_z0 / TZ) * P.ntile[0] * P.ntile[1];
     ntiles = (long)((ctx->slab_nz + TZ - 1) / TZ) * P.ntile[0] * P.ntile[1];
   }
-  if constexpr (N == 4 && TX == 4 && TY == 4 && TZ == 4 && MINB == 3 && !EARLY) {
+  if constexpr (N == 4 && TX == 4 && TY == 4 && TZ == 4) {
     // default Q3 path: persistent CTAs with bulk-copy prefetch (apply_uniform_q3p.cuh); needs full tiles
     // (not for the two-launch NCCL halo path: its interior launch would starve the halo stream's kernels of SM slots)
-    if (uniform_persistent(ctx, L) && part != 1 && part != 2 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-      static int slots = 0;
-      if (!slots) {
-        HPDG_CUDA(cudaFuncSetAttribute(hpdg_k_apply_q3_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, kQ3pSmemBytes));
-        HPDG_CUDA(cudaFuncSetAttribute(hpdg_k_apply_q3_eo, cudaFuncAttributeMaxDynamicSharedMemorySize, kQ3pSmemBytes));
-        int nsm = 0, occ = 0;
-        HPDG_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
-        HPDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hpdg_k_apply_q3_persist, 256, kQ3pSmemBytes));
-        slots = nsm * std::max(occ, 1);
-      }
+    if (uniform_persistent(ctx, L, x) && part != 1 && part != 2) {
+      int slots = 0;
+      if (kernel_slots(ctx, reinterpret_cast<const void*>(hpdg_k_apply_q3_persist), 256, kQ3pSmemBytes, &slots)) return 1;
       if (q3p_level_setup(ctx, L)) return 1;
       const int grid = (int)std::min<long>(ntiles, ctx->q3p_grid > 0 ? ctx->q3p_grid : slots);
-      if (ctx->variant != 42) {  // default: nodal arithmetic
-        Q3pPack PK = {};
-        if (part == 3) {  // interior tiles first: by the time the CTAs reach the rank-boundary tiles the neighbours' traces have landed
-          if (uniform_tile_lists(ctx, L, TX, TY, TZ, P.bmode)) return 1;
-          P.tile_list = L.d_tiles_all; P.tile_rot = 0;
-        }
-        if (part == 3 && P.ghost_step > 0) {  // p2p halo: the tile kernel packs and publishes this rank's face traces itself
-          const int par = ctx->ghost.step & 1;
-          for (int f = 0; f < 6; f++) {
-            if (!ctx->ghost.active[f]) continue;
-            PK.out[f] = reinterpret_cast<double*>(ctx->ghost.peer_arena[f] + ctx->ghost.recv_off[f ^ 1][par]);
-            PK.flag[f] = reinterpret_cast<int*>(ctx->ghost.peer_arena[f] + ctx->ghost.flag_off) + (f ^ 1) * 2 + par;
-          }
-          PK.done = ctx->d_sched + 8;
-          PK.step = ctx->ghost.step;
-        }
-        hpdg_k_apply_q3_persist<<<grid, 256, kQ3pSmemBytes, stream>>>(P, static_cast<const int4*>(L.d_tile_desc), (int)ntiles, (int)ntiles_total, ctx->d_sched + 2 * (part & 3), PK);
-      } else {  // variant 42: even/odd arithmetic (apply_uniform_q3e.cuh); fewer FP64 operations but measured slower (94.9 vs 91.7 us on cfg2)
-        static thread_local Q3eTab E;
-        for (int d = 0; d < 3; d++) {
-          for (int a = 0; a < 2; a++) {
-            for (int b = 0; b < 2; b++) {
-              E.De[d][a * 2 + b] = P.Dp[d][a * 4 + b] + P.Dp[d][a * 4 + 3 - b];
-              E.Do[d][a * 2 + b] = P.Dp[d][a * 4 + b] - P.Dp[d][a * 4 + 3 - b];
-            }
-            E.Ae[d][a] = P.A0[d][a] + P.A0[d][3 - a]; E.Ao[d][a] = P.A0[d][a] - P.A0[d][3 - a];
-            E.Be[d][a] = 0.5 * (P.B0[d][a] + P.B0[d][3 - a]); E.Bo[d][a] = 0.5 * (P.B0[d][a] - P.B0[d][3 - a]);
-          }
-          E.hc[d] = 0.5 * P.cohk[d];
-        }
-        for (int a = 0; a < 2; a++) {
-          E.ge[a] = 0.5 * (P.g[0][a] + P.g[0][3 - a]); E.go[a] = 0.5 * (P.g[0][a] - P.g[0][3 - a]);
-          for (int b = 0; b < 2; b++) {
-            E.Me[a * 2 + b] = P.M[a * 4 + b] + P.M[a * 4 + 3 - b]; E.Mo[a * 2 + b] = P.M[a * 4 + b] - P.M[a * 4 + 3 - b];
-            E.Mfe[a * 2 + b] = 0.125 * (P.Mf[a * 4 + b] + P.Mf[a * 4 + 3 - b]); E.Mfo[a * 2 + b] = 0.125 * (P.Mf[a * 4 + b] - P.Mf[a * 4 + 3 - b]);
-          }
-        }
-        for (int m = 0; m < 4; m++) E.g0[m] = P.g[0][m];
-        hpdg_k_apply_q3_eo<<<grid, 256, kQ3pSmemBytes, stream>>>(P, E, static_cast<const int4*>(L.d_tile_desc), (int)ntiles, (int)ntiles_total);
+      Q3pPack PK = {};
+      if (part == 3) {  // interior tiles first: by the time the CTAs reach the rank-boundary tiles the neighbours' traces have landed
+        if (uniform_tile_lists(ctx, L, TX, TY, TZ, P.bmode)) return 1;
+        P.tile_list = L.d_tiles_all; P.tile_rot = 0;
       }
+      if (part == 3 && P.ghost_step > 0) {  // p2p halo: the tile kernel packs and publishes this rank's face traces itself
+        const int par = ctx->ghost.step & 1;
+        for (int f = 0; f < 6; f++) {
+          if (!ctx->ghost.active[f]) continue;
+          PK.out[f] = reinterpret_cast<double*>(ctx->ghost.peer_arena[f] + ctx->ghost.recv_off[f ^ 1][par]);
+          PK.flag[f] = reinterpret_cast<int*>(ctx->ghost.peer_arena[f] + ctx->ghost.flag_off) + (f ^ 1) * 2 + par;
+        }
+        PK.done = ctx->d_sched + 8;
+        PK.step = ctx->ghost.step;
+      }
+      hpdg_k_apply_q3_persist<<<grid, 256, kQ3pSmemBytes, stream>>>(P, static_cast<const int4*>(L.d_tile_desc), (int)ntiles, (int)ntiles_total, ctx->d_sched + 2 * (part & 3), PK);
       ctx->launches++;
       HPDG_CUDA(cudaGetLastError());
       return 0;
     }
   }
-  k_apply_uniform<N, TX, TY, TZ, MINB, EARLY><<<(unsigned)ntiles, threads, smem, stream>>>(P);
+  if (kernel_slots(ctx, reinterpret_cast<const void*>(k_apply_uniform<N, TX, TY, TZ, MINB>), threads, smem, nullptr)) return 1;
+  k_apply_uniform<N, TX, TY, TZ, MINB><<<(unsigned)ntiles, threads, smem, stream>>>(P);
   ctx->launches++;
   HPDG_CUDA(cudaGetLastError());
   return 0;
@@ -622,10 +409,12 @@ int q3p_level_setup(Ctx* ctx, Level& L, int tile_h) {  // tiles of 4 x 4 x tile_
   return 0;
 }
 
-int uniform_persistent(const Ctx* ctx, const Level& L) {
-  return uniform_supported(ctx, L) && L.p_uni == 3 && ctx->variant != 40 && (ctx->variant < 1 || ctx->variant > 22) &&
+// the level's apply runs the persistent Q3 tile kernel for input vector x (bulk copies need 16-byte aligned rows; x == nullptr:
+// alignment not checked).  Option "variant" = 40 switches the persistent kernels off (cross-check against the tile kernel).
+int uniform_persistent(const Ctx* ctx, const Level& L, const double* x) {
+  return uniform_supported(ctx, L) && L.p_uni == 3 && ctx->variant != 40 &&
          L.n[0] % 4 == 0 && L.n[1] % 4 == 0 && L.n[2] % 4 == 0 && L.n[0] <= 4092 && L.n[1] <= 4092 && L.n[2] <= 4092 &&
-         L.ndof < (1L << 31);
+         L.ndof < (1L << 31) && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
 }
 
 int uniform_supported(const Ctx* ctx, const Level& L) {
@@ -639,30 +428,8 @@ int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double 
   switch (L.p_uni) {
     case 1: return launch_uni<2, 4, 4, 4, 4>(ctx, L, x, y, factor, part, stream);
     case 2: return launch_uni<3, 4, 4, 4, 3>(ctx, L, x, y, factor, part, stream);
-    case 3:
-      switch (ctx->variant) {
-        case 1: return launch_uni<4, 4, 4, 4, 2, true>(ctx, L, x, y, factor, part, stream);
-        case 3: return launch_uni<4, 4, 4, 4, 2, false>(ctx, L, x, y, factor, part, stream);
-        case 4: return launch_uni<4, 4, 4, 2, 4, false>(ctx, L, x, y, factor, part, stream);
-        case 5: return launch_uni<4, 4, 4, 2, 3, false>(ctx, L, x, y, factor, part, stream);
-        case 6: return launch_uni<4, 4, 4, 2, 4, true>(ctx, L, x, y, factor, part, stream);
-        case 7: return launch_uni<4, 4, 2, 4, 4, false>(ctx, L, x, y, factor, part, stream);
-        case 8: return launch_uni<4, 2, 4, 4, 4, false>(ctx, L, x, y, factor, part, stream);
-        case 9: return launch_uni<4, 4, 4, 4, 3, true>(ctx, L, x, y, factor, part, stream);
-        case 21: case 22: if (ctx->fuse_accum) { ctx->err = "accumulate mode is not implemented in the experimental kernel"; return 1; } return launch_apply_uniform3(ctx, L, x, y, factor, part, stream);  // experimental 3-pass kernel
-        default: return launch_uni<4, 4, 4, 4, 3, false>(ctx, L, x, y, factor, part, stream);
-      }
-    case 4:
-      switch (ctx->variant) {
-        case 1: return launch_uni<5, 4, 4, 2, 1, false>(ctx, L, x, y, factor, part, stream);
-        case 2: return launch_uni<5, 4, 4, 2, 2, false>(ctx, L, x, y, factor, part, stream);
-        case 3: return launch_uni<5, 4, 2, 2, 2, false>(ctx, L, x, y, factor, part, stream);
-        case 4: return launch_uni<5, 2, 2, 2, 4, false>(ctx, L, x, y, factor, part, stream);
-        case 5: return launch_uni<5, 3, 3, 3, 2, false>(ctx, L, x, y, factor, part, stream);
-        case 7: return launch_uni<5, 4, 4, 1, 2, false>(ctx, L, x, y, factor, part, stream);
-        case 8: return launch_uni<5, 2, 2, 2, 3, false>(ctx, L, x, y, factor, part, stream);
-        default: return launch_uni<5, 3, 3, 3, 3, false>(ctx, L, x, y, factor, part, stream);
-      }
+    case 3: return launch_uni<4, 4, 4, 4, 3>(ctx, L, x, y, factor, part, stream);
+    case 4: return launch_uni<5, 3, 3, 3, 3>(ctx, L, x, y, factor, part, stream);
     case 5: return launch_uni<6, 2, 2, 2, 2>(ctx, L, x, y, factor, part, stream);
     default: return -1;
   }

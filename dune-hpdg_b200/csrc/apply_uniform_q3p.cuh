@@ -125,22 +125,16 @@ __device__ __forceinline__ void q3p_mass(double (&a)[4]) {
 
 constexpr int kQ3pSmemBytes = 2 * 4096 * 8 + 16;
 
-struct Q3pTrace { double pd, pv, nd, nv; int pm, nm; };
-
-// (der, val) traces of the elements before / after a pencil in direction DIR.  fl: which brick faces the tile touches;
+// Loads of the (der, val) traces of the elements before / after a pencil in direction DIR; issued before the barrier that opens
+// the pass and reduced after it (uniform_common.cuh: halo_issue / halo_reduce).  fl: which brick faces the tile touches;
 // prev / next: this thread's DoF line in the element before / after the pencil (stride in doubles between its nodes);
 // gidx: index of this thread's face node in the ghost trace buffers of the direction.
-template <int DIR, class GIdx>
-__device__ __forceinline__ Q3pTrace q3p_halo(const UniParams<4>& P, int fl, const double* __restrict__ prev,
-                                             const double* __restrict__ next, int stride, GIdx gidx) {
-  Q3pTrace r; r.pd = r.pv = r.nd = r.nv = 0;
-  r.pm = (fl >> (2 * DIR)) & 1 ? P.bmode[2 * DIR] : 0;
-  r.nm = (fl >> (2 * DIR + 1)) & 1 ? P.bmode[2 * DIR + 1] : 0;
-  if (r.pm == 0) outside_trace<4>(P, prev, stride, 1, r.pd, r.pv);
-  else if (r.pm == 3) { const double* gp = P.ghost[2 * DIR] + gidx() * 2; r.pd = __ldcg(gp); r.pv = __ldcg(gp + 1); r.pm = 0; }
-  if (r.nm == 0) outside_trace<4>(P, next, stride, 0, r.nd, r.nv);
-  else if (r.nm == 3) { const double* gp = P.ghost[2 * DIR + 1] + gidx() * 2; r.nd = __ldcg(gp); r.nv = __ldcg(gp + 1); r.nm = 0; }
-  return r;
+template <int DIR>
+__device__ __forceinline__ HaloRaw<4> q3p_halo_issue(const UniParams<4>& P, int fl, const double* __restrict__ prev,
+                                                     const double* __restrict__ next, int stride, long gidx) {
+  const int pm = (fl >> (2 * DIR)) & 1 ? P.bmode[2 * DIR] : 0;
+  const int nm = (fl >> (2 * DIR + 1)) & 1 ? P.bmode[2 * DIR + 1] : 0;
+  return halo_issue<4>(pm, nm, prev, next, stride, P.ghost[2 * DIR] + gidx * 2, P.ghost[2 * DIR + 1] + gidx * 2);
 }
 
 // NVLink peer-memory halo, sender side, fused into the tile kernel (multi-GPU): before their first tile all CTAs
@@ -256,7 +250,10 @@ hpdg_k_apply_q3_persist(const __grid_constant__ hpdg::UniParams<4> P, const int4
             const volatile int* fg = P.ghost_flag[f];
             while (*fg < P.ghost_step) {
               __nanosleep(200);
-              if (clock64() - tstart > 4000000000LL) { atomicExch(P.ghost_err, 1); break; }  // ~2 s: give up, never hang the GPU
+              if (*reinterpret_cast<volatile int*>(P.ghost_err)) break;  // another tile already timed out: do not wait again
+              if (clock64() - tstart > P.ghost_timeout) {  // give up, never hang the GPU; every synchronising entry point reports it
+                atomicExch(P.ghost_err, 1); *reinterpret_cast<volatile int*>(P.ghost_err_host) = 1; __threadfence_system(); break;
+              }
             }
           }
           __threadfence();
@@ -272,8 +269,8 @@ hpdg_k_apply_q3_persist(const __grid_constant__ hpdg::UniParams<4> P, const int4
       const int zq = tid & 15, zex = (tid >> 4) & 3, zey = tid >> 6;
       const int zcol = (zex + 4 * zey) * N3;
       const double* colp = X + (long)(e0 + zex + n0 * zey) * N3 + zq;  // element (x, y, z0), this node
-      const Q3pTrace h = q3p_halo<2>(P, fl, colp - (long)n01 * N3, colp + (long)n01 * (4 * N3), N2,
-                                     [&]() { return ((long)(tx4 + zex) + (long)n0 * (ty4 + zey)) * N2 + zq; });
+      const HaloRaw<4> hr = q3p_halo_issue<2>(P, fl, colp - (long)n01 * N3, colp + (long)n01 * (4 * N3), N2,
+                                              ((long)(tx4 + zex) + (long)n0 * (ty4 + zey)) * N2 + zq);
       while (!q3p_mbar_try_wait(mbar, phase)) {}
       phase ^= 1;
       // in-place swizzle: every lane of the half warp reads its raw lines before any lane overwrites the column
@@ -283,6 +280,7 @@ hpdg_k_apply_q3_persist(const __grid_constant__ hpdg::UniParams<4> P, const int4
 #pragma unroll
         for (int k = 0; k < 4; k++) v[e][k] = su[zcol + 1024 * e + 16 * k + zq];
       __syncwarp();
+      const HaloTrace h = halo_reduce<4>(P, hr);
       q3p_pencil<2>(h.pd, h.pv, h.pm, h.nd, h.nv, h.nm,
         [&](int e, double (&l)[4]) {
 #pragma unroll
@@ -307,9 +305,10 @@ hpdg_k_apply_q3_persist(const __grid_constant__ hpdg::UniParams<4> P, const int4
       const int xo0 = (4 * xey + 16 * xez) * N3 + 16 * xk + 2 * (xq & 7);        // nodes i = 0,1 of the line (+ 64 e)
       const int xo1 = (4 * xey + 16 * xez) * N3 + 16 * xk + 2 * ((xq + 1) & 7);  // nodes i = 2,3
       const double* rowp = X + (long)(e0 + n0 * xey + n01 * xez) * N3 + N * xj + N2 * xk;  // element (x0, y, z), this line
-      const Q3pTrace h = q3p_halo<0>(P, fl, rowp - N3, rowp + 4 * N3, 1,
-                                     [&]() { return ((long)(ty4 + xey) + (long)P.n[1] * (tz4 + xez)) * N2 + xj + N * xk; });
+      const HaloRaw<4> hr = q3p_halo_issue<0>(P, fl, rowp - N3, rowp + 4 * N3, 1,
+                                              ((long)(ty4 + xey) + (long)P.n[1] * (tz4 + xez)) * N2 + xj + N * xk);
       __syncthreads();
+      const HaloTrace h = halo_reduce<4>(P, hr);
       q3p_pencil<0>(h.pd, h.pv, h.pm, h.nd, h.nv, h.nm,
         [&](int e, double (&l)[4]) {
           const double2 lo = *reinterpret_cast<const double2*>(su + xo0 + 64 * e);
@@ -336,9 +335,10 @@ hpdg_k_apply_q3_persist(const __grid_constant__ hpdg::UniParams<4> P, const int4
       const int yr = yi + 2 * (yez & 1);
       auto yo = [&](int j) { return ybase + (((4 * j) ^ (4 * yk)) + yr & 15); };  // node j of the line (+ 256 e)
       const double* colp = X + (long)(e0 + yex + n01 * yez) * N3 + yi + N2 * yk;  // element (x, y0, z), this line
-      const Q3pTrace h = q3p_halo<1>(P, fl, colp - (long)n0 * N3, colp + (long)n0 * (4 * N3), N,
-                                     [&]() { return ((long)(tx4 + yex) + (long)n0 * (tz4 + yez)) * N2 + yi + N * yk; });
+      const HaloRaw<4> hr = q3p_halo_issue<1>(P, fl, colp - (long)n0 * N3, colp + (long)n0 * (4 * N3), N,
+                                              ((long)(tx4 + yex) + (long)n0 * (tz4 + yez)) * N2 + yi + N * yk);
       q3p_bar_half(tid >> 7);
+      const HaloTrace h = halo_reduce<4>(P, hr);
       q3p_pencil<1>(h.pd, h.pv, h.pm, h.nd, h.nv, h.nm,
         [&](int e, double (&l)[4]) {
 #pragma unroll

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -129,6 +130,13 @@ struct Ctx {
   // fusion requests of the V-cycle driver, consumed by the next launch:
   int fuse_accum = 0;          // apply: y = y_old + factor * A x   (r -= A c without a separate axpy)
   double* fuse_xacc = nullptr; // block Jacobi: additionally x += c
+  std::map<const void*, int> kattr;  // kernel_slots(): kernels whose attributes are set on this context's device -> resident CTA slots
+  double* d_scalar = nullptr;        // device scratch of the BLAS-1 reductions (one context = one device)
+  double* d_partial = nullptr;       // per-CTA partial sums of the two-stage dot product
+  volatile int* h_ghost_err = nullptr;  // p2p halo: time-out flag of the tile kernels (mapped pinned host memory)
+  int* d_ghost_err = nullptr;          // its device alias
+  long long halo_timeout_cycles = 40000000000LL;  // ~20 s of SM clock; option "halo_timeout_ms"
+  double *cg_p = nullptr, *cg_q = nullptr, *cg_r = nullptr, *cg_z = nullptr;  // work vectors of the solver loops (finest level)
   long launches = 0;  // kernels launched by this context (bench.py's gpu_launches)
 };
 
@@ -146,11 +154,13 @@ int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double 
 // returns -1 if (dim, degree) has no specialised kernel
 int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream = nullptr);
 int uniform_supported(const Ctx* ctx, const Level& L);
-int uniform_persistent(const Ctx* ctx, const Level& L);  // the level's apply runs the persistent Q3 tile kernel
+int uniform_persistent(const Ctx* ctx, const Level& L, const double* x);  // the level's apply of x runs the persistent Q3 tile kernel
+// one-time, per-context (= per-device) kernel attributes: opts the kernel in to `smem` bytes of dynamic shared memory and, if
+// slots != nullptr, returns the number of CTAs of `threads` threads that are resident on the whole device at once
+int kernel_slots(Ctx* ctx, const void* func, int threads, size_t smem, int* slots);
 int q3p_level_setup(Ctx* ctx, Level& L, int tile_h = 4);  // descriptors of the 4 x 4 x tile_h tiles + scheduler counters of the persistent kernels
 int uniform_tile_height(const Level& L);
 int uniform_tile_lists(Ctx* ctx, Level& L, int TX, int TY, int TZ, const int* bmode);
-int launch_apply_uniform3(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream);
 int launch_pack_traces(Ctx* ctx, Level& L, const double* x, cudaStream_t stream);
 int level_ghost(Ctx* ctx, Level& L, Ghost** out);  // halo buffers of this level (allocated on first use for coarse levels)
 int launch_halo_flags(Ctx* ctx, cudaStream_t stream);
@@ -171,6 +181,12 @@ int launch_restrict(Ctx* ctx, Level& fine, Level& coarse, const double* xf, doub
 int launch_prolong(Ctx* ctx, Level& fine, Level& coarse, const double* xc, double* xf);
 int launch_axpy(Ctx* ctx, long n, double a, const double* x, double* y);          // y += a x
 int launch_xpay_sub(Ctx* ctx, long n, const double* b, const double* ax, double* r);  // r = b - ax
-int launch_dot(Ctx* ctx, long n, const double* x, const double* y, double* d_result);
+int launch_dot(Ctx* ctx, long n, const double* x, const double* y, double* d_result);    // *d_result = x . y (this rank's part)
+int launch_scale(Ctx* ctx, long n, double a, double* x);                                  // x *= a
+constexpr int kScalarSlots = 16;   // Ctx::d_scalar: device-resident scalars of the BLAS-1 / Krylov drivers
+int blas_scratch(Ctx* ctx);        // allocates Ctx::d_scalar / d_partial on first use
+// preconditioned CG updates with device-resident scalars s = Ctx::d_scalar (no host round trip inside an iteration)
+int launch_cg_update(Ctx* ctx, long n, int num, int den, const double* p, const double* q, double* x, double* r);  // a = s[num]/s[den]; x += a p; r -= a q
+int launch_cg_direction(Ctx* ctx, long n, int num, int den, const double* z, double* p);                          // b = s[num]/s[den]; p = z + b p
 
 }  // namespace hpdg

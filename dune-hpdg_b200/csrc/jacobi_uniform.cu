@@ -215,11 +215,7 @@ static int launch_fdu(Ctx* ctx, Level& L, const double* r, double* c, double dam
   P.damping = damping; P.r = r; P.c = c; P.xacc = ctx->fuse_xacc;
   constexpr int threads = fdu_threads<N, TX, TY, TZ>();
   constexpr size_t smem = sizeof(double) * TX * TY * TZ * PitchJ<N>::EP;
-  static bool attr_set = false;
-  if (!attr_set) {
-    HPDG_CUDA(cudaFuncSetAttribute(k_jacobi_fd_uniform<N, TX, TY, TZ, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  if (kernel_slots(ctx, reinterpret_cast<const void*>(k_jacobi_fd_uniform<N, TX, TY, TZ, MINB>), threads, smem, nullptr)) return 1;
   const long ntiles = (long)P.ntile[0] * P.ntile[1] * P.ntile[2];
   k_jacobi_fd_uniform<N, TX, TY, TZ, MINB><<<(unsigned)ntiles, threads, smem, ctx->stream>>>(P);
   ctx->launches++;
@@ -300,14 +296,8 @@ static int launch_q3j(Ctx* ctx, Level& L, const double* r, double* c, double dam
   P.tile_desc = static_cast<const int4*>(L.d_tile_desc);
   P.sched = ctx->d_sched + 10;
   P.ntiles = (L.n[0] / 4) * (L.n[1] / 4) * (L.n[2] / 4);
-  static int slots = 0;
-  if (!slots) {
-    HPDG_CUDA(cudaFuncSetAttribute(hpdg_k_jacobi_fd_q3_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, kQ3jSmemBytes));
-    int nsm = 0, occ = 0;
-    HPDG_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
-    HPDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hpdg_k_jacobi_fd_q3_persist, 256, kQ3jSmemBytes));
-    slots = nsm * std::max(occ, 1);
-  }
+  int slots = 0;
+  if (kernel_slots(ctx, reinterpret_cast<const void*>(hpdg_k_jacobi_fd_q3_persist), 256, kQ3jSmemBytes, &slots)) return 1;
   const int grid = std::min(P.ntiles, ctx->q3p_grid > 0 ? ctx->q3p_grid : slots);
   hpdg_k_jacobi_fd_q3_persist<<<grid, 256, kQ3jSmemBytes, ctx->stream>>>(P);
   ctx->launches++;
@@ -315,8 +305,8 @@ static int launch_q3j(Ctx* ctx, Level& L, const double* r, double* c, double dam
   return 0;
 }
 
-// EXPERIMENTAL persistent Q4 kernel (jacobi_uniform_q4p.cuh), opt-in through option "variant" = 50: uniform Q4 bricks with extents
-// multiple of (4, 4, 2).  Returns -1 when it does not apply.
+// persistent Q4 kernel (jacobi_uniform_q4p.cuh): uniform Q4 bricks with extents multiple of (4, 4, 2); option "variant" = 40
+// switches it off.  Returns -1 when it does not apply.
 static int launch_q4j(Ctx* ctx, Level& L, const double* r, double* c, double damping) {
   static thread_local Q4jParams P;
   if (L.q3j_state < 0) return -1;
@@ -362,14 +352,8 @@ static int launch_q4j(Ctx* ctx, Level& L, const double* r, double* c, double dam
   P.tile_desc = static_cast<const int4*>(L.d_tile_desc);
   P.sched = ctx->d_sched + 10;
   P.ntiles = (L.n[0] / 4) * (L.n[1] / 4) * (L.n[2] / 2);
-  static int slots = 0;
-  if (!slots) {
-    HPDG_CUDA(cudaFuncSetAttribute(hpdg_k_jacobi_fd_q4_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, kQ4jSmemBytes));
-    int nsm = 0, occ = 0;
-    HPDG_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
-    HPDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hpdg_k_jacobi_fd_q4_persist, 160, kQ4jSmemBytes));
-    slots = nsm * std::max(occ, 1);
-  }
+  int slots = 0;
+  if (kernel_slots(ctx, reinterpret_cast<const void*>(hpdg_k_jacobi_fd_q4_persist), 160, kQ4jSmemBytes, &slots)) return 1;
   const int grid = std::min(P.ntiles, ctx->q3p_grid > 0 ? ctx->q3p_grid : slots);
   hpdg_k_jacobi_fd_q4_persist<<<grid, 160, kQ4jSmemBytes, ctx->stream>>>(P);
   ctx->launches++;
@@ -381,11 +365,11 @@ static int launch_q4j(Ctx* ctx, Level& L, const double* r, double* c, double dam
 int jacobi_apply_fd_uniform(Ctx* ctx, Level& L, const double* r, double* c, double damping) {
   if (!uniform_supported(ctx, L)) return -1;
   // the bulk copies / bulk stores of the persistent kernel need 16-byte aligned vectors
-  if (uniform_persistent(ctx, L) && ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(c)) & 15) == 0) {
+  if (uniform_persistent(ctx, L, r) && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
     const int rc = launch_q3j(ctx, L, r, c, damping);
     if (rc >= 0) return rc;
   }
-  if (ctx->variant == 50 && L.p_uni == 4 && L.n[0] % 4 == 0 && L.n[1] % 4 == 0 && L.n[2] % 2 == 0 && L.ndof < (1L << 31) &&
+  if (ctx->variant != 40 && L.p_uni == 4 && L.n[0] % 4 == 0 && L.n[1] % 4 == 0 && L.n[2] % 2 == 0 && L.ndof < (1L << 31) &&
       (reinterpret_cast<uintptr_t>(r) & 15) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
     const int rc = launch_q4j(ctx, L, r, c, damping);
     if (rc >= 0) return rc;
@@ -394,14 +378,7 @@ int jacobi_apply_fd_uniform(Ctx* ctx, Level& L, const double* r, double* c, doub
     case 1: return launch_fdu<2, 4, 4, 4, 4>(ctx, L, r, c, damping);
     case 2: return launch_fdu<3, 4, 4, 4, 4>(ctx, L, r, c, damping);
     case 3: return launch_fdu<4, 4, 4, 4, 4>(ctx, L, r, c, damping);
-    case 4:
-      switch (ctx->variant) {
-        case 1: return launch_fdu<5, 3, 3, 3, 3>(ctx, L, r, c, damping);
-        case 2: return launch_fdu<5, 2, 2, 2, 4>(ctx, L, r, c, damping);
-        case 3: return launch_fdu<5, 4, 4, 2, 3>(ctx, L, r, c, damping);
-        case 4: return launch_fdu<5, 4, 4, 2, 2>(ctx, L, r, c, damping);
-        default: return launch_fdu<5, 4, 4, 4, 2>(ctx, L, r, c, damping);
-      }
+    case 4: return launch_fdu<5, 4, 4, 4, 2>(ctx, L, r, c, damping);
     case 5: return launch_fdu<6, 2, 2, 2, 3>(ctx, L, r, c, damping);
     default: return -1;
   }

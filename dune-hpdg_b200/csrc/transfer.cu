@@ -172,56 +172,4 @@ int launch_prolong(Ctx* ctx, Level& fine, Level& coarse, const double* xc, doubl
   return xfer_launch(ctx, fine, coarse, xc, xf, false);
 }
 
-// ---- BLAS-1 on the flat DynamicBlockVector storage (common/dynamicbvector.hh:185-314) ----------
-__global__ void k_axpy(long n, double a, const double* __restrict__ x, double* __restrict__ y) {
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) y[i] += a * x[i];
-}
-__global__ void k_sub(long n, const double* __restrict__ b, const double* __restrict__ ax, double* __restrict__ r) {
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) r[i] = b[i] - ax[i];
-}
-// deterministic two-stage dot product: fixed grid, fixed tree
-constexpr int kDotBlocks = 592, kDotThreads = 256;
-__global__ void k_dot1(long n, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ part) {
-  __shared__ double sh[kDotThreads];
-  double s = 0;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) s = fma(x[i], y[i], s);
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int w = kDotThreads / 2; w > 0; w >>= 1) { if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w]; __syncthreads(); }
-  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
-}
-__global__ void k_dot2(const double* __restrict__ part, double* __restrict__ out) {
-  __shared__ double sh[1024];
-  double s = 0;
-  for (int i = threadIdx.x; i < kDotBlocks; i += blockDim.x) s += part[i];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int w = 512; w > 0; w >>= 1) { if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w]; __syncthreads(); }
-  if (threadIdx.x == 0) out[0] = sh[0];
-}
-
-static int grid_for(long n) { long b = (n + 255) / 256; return (int)(b < 148 * 8 ? (b < 1 ? 1 : b) : 148 * 8); }
-
-int launch_axpy(Ctx* ctx, long n, double a, const double* x, double* y) {
-  k_axpy<<<grid_for(n), 256, 0, ctx->stream>>>(n, a, x, y);
-  ctx->launches++;
-  HPDG_CUDA(cudaGetLastError());
-  return 0;
-}
-int launch_xpay_sub(Ctx* ctx, long n, const double* b, const double* ax, double* r) {
-  k_sub<<<grid_for(n), 256, 0, ctx->stream>>>(n, b, ax, r);
-  ctx->launches++;
-  HPDG_CUDA(cudaGetLastError());
-  return 0;
-}
-int launch_dot(Ctx* ctx, long n, const double* x, const double* y, double* d_result) {
-  static double* d_part = nullptr;
-  if (!d_part) HPDG_CUDA(cudaMalloc(&d_part, kDotBlocks * sizeof(double)));
-  k_dot1<<<kDotBlocks, kDotThreads, 0, ctx->stream>>>(n, x, y, d_part);
-  k_dot2<<<1, 1024, 0, ctx->stream>>>(d_part, d_result);
-  ctx->launches += 2;
-  HPDG_CUDA(cudaGetLastError());
-  return 0;
-}
-
 }  // namespace hpdg

@@ -22,7 +22,9 @@ struct UniParams {
   const double* ghost[6];  // [face elem][node][2] = (der, val) of the remote element at its near side
   const int* ghost_flag[6];  // p2p halo: flag the neighbour raises to ghost_step once its traces for this step have landed
   int ghost_step;
-  int* ghost_err;
+  int* ghost_err;            // p2p halo time-out flag (device, in the halo arena) ...
+  int* ghost_err_host;       // ... and its copy in mapped pinned host memory, which the synchronising entry points read
+  long long ghost_timeout;   // SM clock cycles a rank-boundary tile waits for the neighbour's flag before giving up
   const double* x;
   double* y;
   int accum; // y = y_old + factor * A x
@@ -120,26 +122,58 @@ __device__ __forceinline__ void mass_line(const UniParams<N>& P, double (&a)[N])
   for (int i = 0; i < N; i++) a[i] = o[i];
 }
 
-// Trace (der, val) of the element outside the tile across brick-interior faces: read its DoF line.
+// Traces (der, val) of the two elements just outside a pencil, in two steps so that the global-memory latency is not paid
+// where the loads are issued: halo_issue() only issues the loads (the raw DoF lines of the outside elements across
+// brick-interior faces, or the ghost trace pair on a rank boundary) -- both sides back to back, nothing consumed --
+// and halo_reduce() turns them into traces.  The kernels issue before a barrier and reduce after it.
 template <int N>
-__device__ __forceinline__ void outside_trace(const UniParams<N>& P, const double* __restrict__ line, long stride,
-                                              int side /* near side of that element */, double& der, double& val) {
+struct HaloRaw { double p[N], n[N]; int pm, nm; };  // modes: 0 interior, 1 Dirichlet, 2 natural, 3 ghost (rank boundary)
+
+template <int N>
+__device__ __forceinline__ void halo_load_line(double (&l)[N], const double* __restrict__ line, long stride) {
   if (N == 4 && stride == 1) {  // an x line is 32 contiguous, 32-byte aligned bytes: two 128-bit loads
     const double2 lo = __ldg(reinterpret_cast<const double2*>(line));
     const double2 hi = __ldg(reinterpret_cast<const double2*>(line) + 1);
-    der = fma(P.g[side][0], lo.x, fma(P.g[side][1], lo.y, fma(P.g[side][2], hi.x, P.g[side][3] * hi.y)));
-    val = side ? hi.y : lo.x;
+    l[0] = lo.x; l[1] = lo.y; l[2] = hi.x; l[3] = hi.y;
     return;
   }
-  double d = 0, last = 0, first = 0;
 #pragma unroll
-  for (int m = 0; m < N; m++) {
-    double u = __ldg(line + m * stride);
-    d = fma(P.g[side][m], u, d);
-    if (m == 0) first = u;
-    if (m == N - 1) last = u;
-  }
-  der = d; val = side ? last : first;
+  for (int m = 0; m < N; m++) l[m] = __ldg(line + m * stride);
+}
+
+// pm / nm: boundary mode of the low / high end (0 if the pencil's end is not on a brick face); prev / next: this thread's
+// DoF line in the element before / after the pencil; glo / ghi: this thread's (der, val) pair in the ghost buffers
+template <int N>
+__device__ __forceinline__ HaloRaw<N> halo_issue(int pm, int nm, const double* __restrict__ prev, const double* __restrict__ next,
+                                                 long stride, const double* __restrict__ glo, const double* __restrict__ ghi) {
+  HaloRaw<N> r;
+#pragma unroll
+  for (int m = 0; m < N; m++) r.p[m] = r.n[m] = 0.0;
+  r.pm = pm; r.nm = nm;
+  if (pm == 0) halo_load_line<N>(r.p, prev, stride);
+  else if (pm == 3) { r.p[0] = __ldcg(glo); r.p[1] = __ldcg(glo + 1); }
+  if (nm == 0) halo_load_line<N>(r.n, next, stride);
+  else if (nm == 3) { r.n[0] = __ldcg(ghi); r.n[1] = __ldcg(ghi + 1); }
+  return r;
+}
+
+struct HaloTrace { double pd, pv, nd, nv; int pm, nm; };  // pm / nm in {0 use the trace, 1 Dirichlet, 2 natural}
+template <int N>
+__device__ __forceinline__ HaloTrace halo_reduce(const UniParams<N>& P, const HaloRaw<N>& r) {
+  HaloTrace t; t.pd = t.pv = t.nd = t.nv = 0; t.pm = r.pm; t.nm = r.nm;
+  if (r.pm == 0) {  // the element before the pencil, at its far (s = 1) side
+    double d = P.g[1][0] * r.p[0];
+#pragma unroll
+    for (int m = 1; m < N; m++) d = fma(P.g[1][m], r.p[m], d);
+    t.pd = d; t.pv = r.p[N - 1];
+  } else if (r.pm == 3) { t.pd = r.p[0]; t.pv = r.p[1]; t.pm = 0; }
+  if (r.nm == 0) {  // the element after the pencil, at its near (s = 0) side
+    double d = P.g[0][0] * r.n[0];
+#pragma unroll
+    for (int m = 1; m < N; m++) d = fma(P.g[0][m], r.n[m], d);
+    t.nd = d; t.nv = r.n[0];
+  } else if (r.nm == 3) { t.nd = r.n[0]; t.nv = r.n[1]; t.nm = 0; }
+  return t;
 }
 
 }  // namespace hpdg

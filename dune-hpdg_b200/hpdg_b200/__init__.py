@@ -19,6 +19,9 @@ FINEST = -1
 JACOBI_DENSE = 0
 JACOBI_FD = 1
 SMOOTHER_BLOCKGS = 2
+PRECOND_NONE = 0
+PRECOND_JACOBI = 1
+PRECOND_VCYCLE = 2
 
 _lib = None
 _vp = C.c_void_p
@@ -54,6 +57,9 @@ SIGNATURES = {
     "hpdg_op_apply": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_double]),
     "hpdg_op_apply_device": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_double]),
     "hpdg_op_apply_async": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_double]),
+    "hpdg_op_apply_accum": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_double]),
+    "hpdg_op_apply_accum_device": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_double]),
+    "hpdg_op_apply_accum_async": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_double]),
     "hpdg_jacobi_setup": (C.c_int, [_vp, C.c_int, C.c_int]),
     "hpdg_jacobi_apply": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_double]),
     "hpdg_jacobi_apply_device": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_double]),
@@ -76,7 +82,16 @@ SIGNATURES = {
     "hpdg_vcycle": (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "hpdg_vcycle_device": (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "hpdg_dot_device": (C.c_int, [_vp, C.c_int, _vp, _vp, C.POINTER(C.c_double)]),
+    "hpdg_two_norm_device": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(C.c_double)]),
     "hpdg_axpy_device": (C.c_int, [_vp, C.c_int, C.c_double, _vp, _vp]),
+    "hpdg_scale_device": (C.c_int, [_vp, C.c_int, C.c_double, _vp]),
+    "hpdg_assign_device": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "hpdg_pcg": (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, C.c_double, C.c_int, C.c_int,
+                           C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+    "hpdg_pcg_device": (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, C.c_double, C.c_int, C.c_int,
+                                  C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+    "hpdg_loop_solve_device": (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_double, C.c_int,
+                                         C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "hpdg_launch_count": (C.c_long, [_vp]),
     "hpdg_uses_uniform_kernel": (C.c_int, [_vp, C.c_int]),
     "hpdg_time_apply_device": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.POINTER(C.c_float)]),
@@ -246,15 +261,26 @@ class Context:
     def axpy_device(self, a, dx, dy, level=FINEST):
         self._ck(lib().hpdg_axpy_device(self._h, level, a, dx, dy))
 
+    def two_norm_device(self, dx, level=FINEST):
+        r = C.c_double()
+        self._ck(lib().hpdg_two_norm_device(self._h, level, dx, C.byref(r)))
+        return r.value
+
+    def scale_device(self, a, dx, level=FINEST):
+        self._ck(lib().hpdg_scale_device(self._h, level, a, dx))
+
+    def assign_device(self, dsrc, ddst, level=FINEST):
+        self._ck(lib().hpdg_assign_device(self._h, level, dsrc, ddst))
+
     def time_apply_device(self, dx, dy, reps, level=FINEST):
         ms = C.c_float()
         self._ck(lib().hpdg_time_apply_device(self._h, level, dx, dy, reps, C.byref(ms)))
         return ms.value
 
 
-class Operator:
-    """`Operator::apply(x, Ax)` with a single IPDGOperator local operator and its factor
-    (matrix-free/operator.hh:41-56, matrix-free/localoperators/localoperator.hh:41-49)."""
+class IPDGOperator:
+    """The local operator of the tuple `Operator` iterates over: carries its own factor
+    (matrix-free/localoperators/localoperator.hh:41-49: factor() / setFactor())."""
 
     def __init__(self, ctx, level=FINEST, factor=1.0):
         self.ctx, self.level, self._factor = ctx, level, factor
@@ -265,15 +291,45 @@ class Operator:
     def setFactor(self, f):
         self._factor = f
 
+
+class Operator:
+    """`Operator::apply(x, Ax)` over a tuple of local operators (matrix-free/operator.hh:41-56): Ax is zeroed once and
+    every local operator adds factor_k * (A x).  `Operator(ctx, level, factor)` is the single-operator shorthand;
+    `Operator.from_local_operators([op1, op2, ...])` is the tuple form (matrix-free/test/testoperator.cc:80-98)."""
+
+    def __init__(self, ctx, level=FINEST, factor=1.0):
+        self.ctx, self.level = ctx, level
+        self.local_operators = [IPDGOperator(ctx, level, factor)]
+
+    @classmethod
+    def from_local_operators(cls, ops):
+        self = cls(ops[0].ctx, ops[0].level, ops[0].factor())
+        self.local_operators = list(ops)
+        assert all(o.ctx is self.ctx and o.level == self.level for o in ops), "local operators must share context and level"
+        return self
+
+    def factor(self):
+        return self.local_operators[0].factor()
+
+    def setFactor(self, f):
+        self.local_operators[0].setFactor(f)
+
     def apply(self, x, Ax=None):
         if Ax is None:
             Ax = np.zeros(self.ctx.dimension(self.level))
-        self.ctx._ck(lib().hpdg_op_apply(self.ctx._h, self.level, _hptr(x), _hptr(Ax), self._factor))
+        for k, op in enumerate(self.local_operators):
+            f = lib().hpdg_op_apply if k == 0 else lib().hpdg_op_apply_accum
+            self.ctx._ck(f(self.ctx._h, self.level, _hptr(x), _hptr(Ax), op.factor()))
         return Ax
 
     def apply_device(self, dx, dy, sync=True):
-        f = lib().hpdg_op_apply_device if sync else lib().hpdg_op_apply_async
-        self.ctx._ck(f(self.ctx._h, self.level, dx, dy, self._factor))
+        for k, op in enumerate(self.local_operators):
+            last = k == len(self.local_operators) - 1
+            if k == 0:
+                f = lib().hpdg_op_apply_device if (sync and last) else lib().hpdg_op_apply_async
+            else:
+                f = lib().hpdg_op_apply_accum_device if (sync and last) else lib().hpdg_op_apply_accum_async
+            self.ctx._ck(f(self.ctx._h, self.level, dx, dy, op.factor()))
 
 
 class BlockJacobi:
@@ -405,3 +461,44 @@ class Multigrid:
     def apply_device(self, dx, db):
         self.ctx._ck(lib().hpdg_vcycle_device(self.ctx._h, self.form, self.damping, self.pre, self.post,
                                               self.coarse_its, dx, db))
+
+
+class LoopSolver:
+    """Dune::Solvers::LoopSolver around the multigrid step with the energy norm (buildingblocks/solve.hh:150-166)."""
+
+    def __init__(self, mg, maxIterations=100, tolerance=1e-8):
+        self.mg, self.maxIterations, self.tolerance = mg, maxIterations, tolerance
+        self.iterationCount_, self.error_ = 0, float("nan")
+
+    def solve_device(self, dx, db):
+        it, err = C.c_int(), C.c_double()
+        m = self.mg
+        m.ctx._ck(lib().hpdg_loop_solve_device(m.ctx._h, m.form, m.damping, m.pre, m.post, m.coarse_its, dx, db,
+                                               self.tolerance, self.maxIterations, C.byref(it), C.byref(err)))
+        self.iterationCount_, self.error_ = it.value, err.value
+        return it.value
+
+    def iterationCount(self):
+        return self.iterationCount_
+
+
+class ConjugateGradients:
+    """Preconditioned CG resident on the device (the Krylov loop whose dot products end in the NCCL all-reduce)."""
+
+    def __init__(self, ctx, precond=PRECOND_JACOBI, damping=1.0, smooth=2, coarse_its=5, tol=1e-8, maxit=200, check_every=1):
+        self.ctx, self.precond, self.damping, self.smooth, self.coarse_its = ctx, precond, damping, smooth, coarse_its
+        self.tol, self.maxit, self.check_every = tol, maxit, check_every
+        self.iterations, self.relres = 0, float("nan")
+
+    def _call(self, f, x, b):
+        it, rr = C.c_int(), C.c_double()
+        self.ctx._ck(f(self.ctx._h, self.precond, self.damping, self.smooth, self.coarse_its, x, b, self.tol, self.maxit,
+                       self.check_every, C.byref(it), C.byref(rr)))
+        self.iterations, self.relres = it.value, rr.value
+        return it.value
+
+    def solve(self, x, b):
+        return self._call(lib().hpdg_pcg, _hptr(x), _hptr(b))
+
+    def solve_device(self, dx, db):
+        return self._call(lib().hpdg_pcg_device, dx, db)

@@ -78,23 +78,25 @@ def face_traces(x_local, n, p, f, g_end):
 
 def enable_p2p_halo(ctx, dist, torch, world):
     """all-gather the ranks' halo-arena IPC handles and attach (NVLink peer-memory halo).  HPDG_HALO=nccl keeps NCCL send/recv.
-    If any rank cannot map its neighbours' arenas (no peer access / IPC not permitted) every rank falls back to NCCL."""
+    If any rank cannot map its neighbours' arenas (no peer access / IPC not permitted) every rank falls back to NCCL.
+    Works over any torch.distributed backend (NCCL: CUDA tensors, gloo: host tensors)."""
     import os
     if os.environ.get("HPDG_HALO", "p2p") != "p2p" or world == 1:
         return False
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
     ok = 1
     try:
-        mine = torch.tensor(list(ctx.halo_ipc_handle()), dtype=torch.uint8, device="cuda")
+        mine = torch.tensor(list(ctx.halo_ipc_handle()), dtype=torch.uint8, device=dev)
     except Exception:
-        mine, ok = torch.zeros(64, dtype=torch.uint8, device="cuda"), 0
-    allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        mine, ok = torch.zeros(64, dtype=torch.uint8, device=dev), 0
+    allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
     dist.all_gather(allh, mine)
     if ok:
         try:
             ctx.halo_ipc_attach([bytes(t.cpu().tolist()) for t in allh])
         except Exception:
             ok = 0
-    flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     use = bool(flag.item())
     if ok:

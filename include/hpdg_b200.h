@@ -29,6 +29,9 @@ typedef struct hpdg_ctx hpdg_ctx;
 #define HPDG_JACOBI_DENSE 0       /* precomputed dense per-element inverses, batched by block size */
 #define HPDG_JACOBI_FD 1          /* same inverse in Kronecker (fast diagonalisation) form */
 #define HPDG_SMOOTHER_BLOCKGS 2    /* hpdg_vcycle only: the reference's DynamicBlockGS on assembled level matrices */
+#define HPDG_PRECOND_NONE 0       /* hpdg_pcg: plain CG */
+#define HPDG_PRECOND_JACOBI 1     /* hpdg_pcg: fd block-Jacobi preconditioner */
+#define HPDG_PRECOND_VCYCLE 2     /* hpdg_pcg: one p-multigrid V-cycle with fd block-Jacobi smoothing */
 
 /* -- problem description -------------------------------------------------------------------------
  * Replaces: DynamicDGQkGLBlockBasis(gridView, k | degree map) (functionspacebases/dynamicdgqkglbasis.hh:54-69),
@@ -42,7 +45,8 @@ int hpdg_create(hpdg_ctx** out, int dim, const int* n, const double* L, const in
  * pgrid[1]*pz)); n and L describe the LOCAL brick.  Models the reference's element-wise owner/overlap
  * decomposition (parallel/communicationhpdg.hh:261-263) with a face-trace halo instead of whole ghost
  * blocks.  nccl_id: the 128-byte ncclUniqueId produced by hpdg_nccl_unique_id on rank 0 and broadcast by the
- * caller.  Uniform degree only. */
+ * caller; NULL = no NCCL communicator (then the peer-memory halo below must be attached before the first apply, and the entry
+ * points that need NCCL -- dot products over ranks, NCCL halo, distributed V-cycle -- fail).  Uniform degree only. */
 int hpdg_create_distributed(hpdg_ctx** out, int dim, const int* n, const double* L, int degree, double sigma,
                             int dirichlet, int device, const int* pgrid, int rank, int nranks,
                             const void* nccl_id);
@@ -55,7 +59,7 @@ int hpdg_halo_ipc_handle(hpdg_ctx* ctx, void* out64);
 int hpdg_halo_ipc_attach(hpdg_ctx* ctx, const void* handles_by_rank);
 void hpdg_destroy(hpdg_ctx* ctx);
 const char* hpdg_last_error(const hpdg_ctx* ctx); /* ctx may be NULL after a failed create */
-int hpdg_set_option(hpdg_ctx* ctx, const char* name, long value); /* "force_generic", "halo_p2p", "variant" (tuning) */
+int hpdg_set_option(hpdg_ctx* ctx, const char* name, long value); /* "force_generic", "halo_p2p", "halo_timeout_ms", "variant" (40: no persistent kernels), "q3p_grid" */
 
 /* -- sizes (DynamicBlockVector::dimension(), blockRows(i): dynamicbvector.hh:134-143,282) ---------- */
 int hpdg_num_levels(const hpdg_ctx* ctx);
@@ -86,6 +90,13 @@ void* hpdg_stream(hpdg_ctx* ctx); /* cudaStream_t the context launches on */
 int hpdg_op_apply(hpdg_ctx* ctx, int level, const double* h_x, double* h_y, double factor);
 int hpdg_op_apply_device(hpdg_ctx* ctx, int level, const double* d_x, double* d_y, double factor);
 int hpdg_op_apply_async(hpdg_ctx* ctx, int level, const double* d_x, double* d_y, double factor);
+
+/* Accumulate mode: y += factor * A x.  Operator::apply over a TUPLE of local operators zeroes Ax once and every local operator
+ * adds factor_k * (A_k x) (matrix-free/operator.hh:42-55; matrix-free/test/testoperator.cc:80-98: factors 1 and 2 give 3 A x):
+ * the first operator of a tuple maps to hpdg_op_apply*, each further one to hpdg_op_apply_accum*. */
+int hpdg_op_apply_accum(hpdg_ctx* ctx, int level, const double* h_x, double* h_y, double factor);
+int hpdg_op_apply_accum_device(hpdg_ctx* ctx, int level, const double* d_x, double* d_y, double factor);
+int hpdg_op_apply_accum_async(hpdg_ctx* ctx, int level, const double* d_x, double* d_y, double factor);
 
 /* -- block Jacobi: c = damping * sum_e P_e^T D_e^-1 P_e r -------------------------------------------
  * Replaces IPDGBlockJacobi inside Operator::apply (matrix-free/localoperators/ipdgblockjacobi.hh:58-178) used
@@ -144,7 +155,27 @@ int hpdg_vcycle_device(hpdg_ctx* ctx, int form, double damping, int pre, int pos
 /* -- BLAS-1 used by the Krylov / MG drivers (DynamicBlockVector::operator*, two_norm:
  * common/dynamicbvector.hh:258-264,300-314); sums over all ranks of a distributed context. */
 int hpdg_dot_device(hpdg_ctx* ctx, int level, const double* d_x, const double* d_y, double* h_result);
-int hpdg_axpy_device(hpdg_ctx* ctx, int level, double a, const double* d_x, double* d_y);
+int hpdg_two_norm_device(hpdg_ctx* ctx, int level, const double* d_x, double* h_result);
+int hpdg_axpy_device(hpdg_ctx* ctx, int level, double a, const double* d_x, double* d_y);   /* y += a x  (enqueue only) */
+int hpdg_scale_device(hpdg_ctx* ctx, int level, double a, double* d_x);                     /* x *= a    (enqueue only) */
+int hpdg_assign_device(hpdg_ctx* ctx, int level, const double* d_src, double* d_dst);       /* dst = src (enqueue only) */
+
+/* -- solver loops around the hot path (finest level) ------------------------------------------------------------------------
+ * hpdg_pcg: preconditioned conjugate gradients, everything resident on the device: per iteration one operator apply, one
+ * preconditioner application (HPDG_PRECOND_*: none / fd block Jacobi with `damping` / one V-cycle with fd block-Jacobi smoothing,
+ * pre = post = `smooth`, `coarse_its` coarse iterations), three dot products that each end in a 1-double ncclAllReduce on the
+ * context stream of a distributed context, and two fused updates whose step lengths are read from device memory.  The host only
+ * reads the residual norm every `check_every` iterations.  Stops at ||r|| <= tol ||r_0|| or after maxit iterations; x is the
+ * initial iterate on entry.  iters / relres may be NULL.
+ * hpdg_loop_solve: Dune::Solvers::LoopSolver around the multigrid step with the energy norm, as buildingblocks/solve.hh:150-166
+ * wires it (MultigridWrapper::iterate copies the right-hand side, iterationsteps/mg/mgwrapper.hh:22-27): stops when
+ * ||x_k - x_{k-1}||_A / ||x_{k-1}||_A < tol or after maxit iterations. */
+int hpdg_pcg(hpdg_ctx* ctx, int precond, double damping, int smooth, int coarse_its, double* h_x, const double* h_b, double tol,
+             int maxit, int check_every, int* iters, double* relres);
+int hpdg_pcg_device(hpdg_ctx* ctx, int precond, double damping, int smooth, int coarse_its, double* d_x, const double* d_b,
+                    double tol, int maxit, int check_every, int* iters, double* relres);
+int hpdg_loop_solve_device(hpdg_ctx* ctx, int form, double damping, int pre, int post, int coarse_its, double* d_x,
+                           const double* d_b, double tol, int maxit, int* iters, double* last_error);
 
 /* -- introspection --------------------------------------------------------------------------------- */
 long hpdg_launch_count(const hpdg_ctx* ctx);      /* kernels launched so far by this context */

@@ -104,3 +104,13 @@ def test_two_rank_nccl_parity():
            "--master-port", "29551", os.path.join(ROOT, "tools", "dist_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert "DIST_CHECK PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.gpu
+def test_two_ranks_one_gpu_peer_memory_halo():
+    # runs on a 1-GPU box: two processes share device 0, no NCCL communicator, halo through CUDA IPC peer memory
+    # (tools/dist_check_one_gpu.py); covers pack + flags + waiting rank-boundary tiles of the distributed operator apply
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29561", os.path.join(ROOT, "tools", "dist_check_one_gpu.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert "DIST_CHECK_ONE_GPU PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

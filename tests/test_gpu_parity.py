@@ -53,9 +53,8 @@ def test_q3_persistent_kernel(orc, hp, n, L, dirichlet, grid):
     op = hp.Operator(ctx, factor=-0.75)
     y = op.apply(x)
     assert rel(y, -0.75 * ref) < TOL
-    for variant in (40, 42):  # 40: the one-tile-per-CTA kernel, 42: the persistent kernel with even/odd arithmetic
-        ctx.set_option("variant", variant)
-        assert rel(op.apply(x), y) < TOL
+    ctx.set_option("variant", 40)  # the one-tile-per-CTA kernel
+    assert rel(op.apply(x), y) < TOL
 
 
 def test_q3_persistent_many_tiles(orc, hp):
@@ -169,6 +168,129 @@ def test_device_resident_api(orc, hp):
     ctx.vec_free(dy)
 
 
+def test_operator_tuple_accumulates(orc, hp):
+    # matrix-free/test/testoperator.cc:80-98 restated with the SIPG local operator: a tuple of two local operators with factors
+    # 1 and 2 gives (1 + 2) A x; Ax is zeroed once (operator.hh:42) and every local operator adds its part (:44-55).
+    # Covers the persistent Q3 kernel, the tile kernel (Q4, ragged Q3) and the generic hp kernel, host and device entry points.
+    rng = np.random.default_rng(5)
+    for n, deg in [((8, 4, 4), 3), ((5, 3, 2), 3), ((3, 3, 3), 4), ((4, 3, 2), rng.integers(1, 5, 24).astype(np.int32)), ((6, 5), 2)]:
+        m = orc.Mesh(n, degree=deg)
+        x = orc.fill_random(m.ndof)
+        ref = m.apply_mf(x, threads=orc.max_threads())
+        ctx = hp.Context(n, degree=deg)
+        op = hp.Operator.from_local_operators([hp.IPDGOperator(ctx, factor=1.0), hp.IPDGOperator(ctx, factor=2.0)])
+        Ax = np.full(m.ndof, 7.0)  # garbage on entry: apply() overwrites
+        op.apply(x, Ax)
+        assert rel(Ax, 3.0 * ref) < TOL
+        dx, dy = ctx.upload(x), ctx.upload(Ax)
+        op.apply_device(dx, dy)
+        assert rel(ctx.download(dy), 3.0 * ref) < TOL
+        ctx.close()
+
+
+def test_blas1_device(orc, hp):
+    # DynamicBlockVector BLAS-1 (common/dynamicbvector.hh:185-314): =, *=, axpy, dot, two_norm
+    n = (5, 4, 3)
+    ctx = hp.Context(n, degree=3)
+    nd = ctx.dimension()
+    x, y = orc.fill_random(nd), orc.fill_random(nd, seed=9)
+    dx, dy, dz = ctx.upload(x), ctx.upload(y), ctx.vec_alloc()
+    assert abs(ctx.two_norm_device(dx) - np.linalg.norm(x)) < 1e-12 * np.linalg.norm(x)
+    ctx.assign_device(dx, dz)
+    ctx.scale_device(-0.5, dz)
+    ctx.axpy_device(2.0, dy, dz)
+    ctx.sync()
+    assert rel(ctx.download(dz), -0.5 * x + 2.0 * y) < 1e-15
+    assert abs(ctx.dot_device(dx, dy) - x @ y) < 1e-12 * np.linalg.norm(x) * np.linalg.norm(y)
+    ctx.close()
+
+
+@pytest.mark.parametrize("precond", [0, 1, 2])
+def test_pcg_solves(orc, hp, precond):
+    # the Krylov loop around the hot path: CG / block-Jacobi PCG / V-cycle PCG must all solve A x = b (SPD with Dirichlet faces)
+    n = (4, 4, 4)
+    m = orc.Mesh(n, degree=4, dirichlet=True)
+    xs = orc.fill_random(m.ndof)
+    b = m.apply_mf(xs, threads=orc.max_threads())
+    ctx = hp.Context(n, degree=4, dirichlet=True)
+    ctx.build_p_hierarchy()
+    cg = hp.ConjugateGradients(ctx, precond=precond, damping=0.75 if precond == 2 else 1.0, smooth=2, tol=1e-11,
+                               maxit=2000, check_every=3 if precond == 0 else 1)
+    x = np.zeros(m.ndof)
+    its = cg.solve(x, b)
+    assert cg.relres <= 1e-11 and its < 2000
+    assert rel(m.apply_mf(x, threads=orc.max_threads()), b) < 1e-10
+    if precond == 2:
+        assert its < 40          # multigrid preconditioning: mesh- and degree-robust iteration counts
+    ctx.close()
+
+
+def test_loop_solver_mg(orc, hp):
+    # LoopSolver + energy norm around the multigrid step (buildingblocks/solve.hh:150-166), checked against the same loop run on
+    # the oracle's V-cycle: identical iteration count and iterate
+    n = (4, 4, 4)
+    fine = orc.Mesh(n, degree=4)
+    l1 = fine.coarsen(2)
+    l0 = l1.coarsen(1)
+    b = orc.fill_random(fine.ndof)
+    x = orc.fill_random(fine.ndof, seed=3) * 0.1
+    tol, it_ref = 1e-4, 0
+    A = lambda v: fine.apply_mf(v, threads=orc.max_threads())
+    xr = x.copy()
+    for it_ref in range(1, 31):
+        old = xr.copy()
+        xr, _ = orc.vcycle([l0, l1, fine], None, xr, b.copy(), smoother=1, damping=0.75)
+        c = xr - old
+        if np.sqrt(c @ A(c)) / np.sqrt(old @ A(old)) < tol:
+            break
+    ctx = hp.Context(n, degree=4)
+    ctx.build_p_hierarchy()
+    mg = hp.Multigrid(ctx, form=hp.JACOBI_FD, damping=0.75)
+    solver = hp.LoopSolver(mg, maxIterations=30, tolerance=tol)
+    dx, db = ctx.upload(x), ctx.upload(b)
+    solver.solve_device(dx, db)
+    assert solver.iterationCount() == it_ref
+    assert rel(ctx.download(dx), xr) < 1e-9
+    assert rel(ctx.download(db), b) == 0.0   # the right-hand side is left alone (mgwrapper.hh:23)
+    ctx.close()
+
+
+def test_two_contexts_two_threads(orc, hp):
+    # per-context (= per-device) kernel attributes and scratch: two contexts used from two host threads at once, and -- when the box
+    # has a second GPU -- on two devices of one process
+    import threading
+    import ctypes
+    ndev = ctypes.c_int(0)
+    try:
+        ctypes.CDLL("libcudart.so").cudaGetDeviceCount(ctypes.byref(ndev))
+    except OSError:
+        ndev.value = 1
+    n = (8, 8, 4)
+    m = orc.Mesh(n, degree=3)
+    x = orc.fill_random(m.ndof)
+    ref = m.apply_mf(x, threads=orc.max_threads())
+    jref = m.blockjacobi_apply(x, factor=0.75)
+    errs = []
+
+    def work(dev):
+        try:
+            ctx = hp.Context(n, degree=3, device=dev)
+            for _ in range(5):
+                assert rel(hp.Operator(ctx).apply(x), ref) < TOL
+                assert rel(hp.BlockJacobi(ctx, form=hp.JACOBI_FD, damping=0.75)(x), jref) < TOL
+                dx = ctx.upload(x)
+                assert abs(ctx.dot_device(dx, dx) - x @ x) < 1e-10 * (x @ x)
+                ctx.vec_free(dx)
+            ctx.close()
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    ths = [threading.Thread(target=work, args=(d % max(ndev.value, 1),)) for d in range(2)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errs, errs
+
+
 @pytest.mark.parametrize("form", [0, 1])
 def test_block_jacobi_vs_oracle(orc, hp, form):
     rng = np.random.default_rng(2)
@@ -205,17 +327,18 @@ def test_fd_jacobi_persistent_q3(orc, hp):
             ctx.close()
 
 
-@pytest.mark.skipif(not os.environ.get("HPDG_EXPERIMENTAL"), reason="experimental kernel (variant 50), not yet validated on a GPU: set HPDG_EXPERIMENTAL=1")
-def test_fd_jacobi_persistent_q4_experimental(orc, hp):
-    # jacobi_uniform_q4p.cuh: uniform Q4 bricks with extents multiple of (4, 4, 2); must match the oracle and the default kernel
+def test_fd_jacobi_persistent_q4(orc, hp):
+    # jacobi_uniform_q4p.cuh: uniform Q4 bricks with extents multiple of (4, 4, 2) run the persistent kernel; variant 40 keeps the
+    # one-tile-per-CTA kernel: both must match the oracle's exact block solve
     for n, L, dirichlet in [((4, 4, 2), None, True), ((8, 4, 6), [1.0, 1.5, 0.5], True), ((8, 8, 4), None, False), ((4, 12, 2), None, False)]:
         m = orc.Mesh(n, L=L, degree=4, dirichlet=dirichlet)
         r = orc.fill_random(m.ndof)
         ref = m.blockjacobi_apply(r, factor=0.75)
-        ctx = hp.Context(n, L=L, degree=4, dirichlet=dirichlet)
-        ctx.set_option("variant", 50)
-        assert rel(hp.BlockJacobi(ctx, form=hp.JACOBI_FD, damping=0.75)(r), ref) < 1e-12
-        ctx.close()
+        for variant in (0, 40):
+            ctx = hp.Context(n, L=L, degree=4, dirichlet=dirichlet)
+            ctx.set_option("variant", variant)
+            assert rel(hp.BlockJacobi(ctx, form=hp.JACOBI_FD, damping=0.75)(r), ref) < 1e-12
+            ctx.close()
 
 
 def test_transfer_vs_oracle(orc, hp):
