@@ -1037,6 +1037,25 @@ int hpdg_loop_solve_device(hpdg_ctx* ctx, int form, double damping, int pre, int
   return 0;
 }
 
+// host-only introspection (no device work): the 1-D tables of degree p the kernels are built from, n = p + 1, row-major n x n
+int hpdg_tables_1d(int degree, double* nodes, double* mass, double* stiffness, double* end_values, double* end_derivatives) {
+  if (degree < 0 || degree > kMaxP) { g_create_err = "polynomial degree out of range 0..13"; return 1; }
+  const DegTable& T = host_tables().deg[degree];
+  const int n = degree + 1;
+  for (int i = 0; i < n; i++) {
+    if (nodes) nodes[i] = T.nodes[i];
+    for (int j = 0; j < n; j++) {
+      if (mass) mass[i * n + j] = T.M[i * kMaxN + j];
+      if (stiffness) stiffness[i * n + j] = T.S[i * kMaxN + j];
+    }
+    for (int s = 0; s < 2; s++) {
+      if (end_values) end_values[s * n + i] = T.t[s][i];
+      if (end_derivatives) end_derivatives[s * n + i] = T.g[s][i];
+    }
+  }
+  return 0;
+}
+
 long hpdg_launch_count(const hpdg_ctx* ctx) { return ctx->launches; }
 int hpdg_uses_uniform_kernel(const hpdg_ctx* ctx, int level) {
   Level* L = get_level(const_cast<hpdg_ctx*>(ctx), level);

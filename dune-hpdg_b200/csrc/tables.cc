@@ -10,57 +10,85 @@ namespace {
 typedef long double ld;
 constexpr int kQ = 20;  // Gauss points: exact to degree 39
 
-void legendre(int n, ld x, ld& P, ld& dP) {
-  if (n == 0) { P = 1; dP = 0; return; }
-  ld p0 = 1, p1 = x, d0 = 0, d1 = 1;
-  for (int k = 2; k <= n; k++) {
-    ld p2 = ((2 * k - 1) * x * p1 - (k - 1) * p0) / k;
-    ld d2 = d0 + (2 * k - 1) * p1;
-    p0 = p1; p1 = p2; d0 = d1; d1 = d2;
+// Node and quadrature generation.  Deliberately NOT the Newton-on-Legendre code of the test oracle (oracle/hpdg_oracle.c):
+// nodes and weights come from the eigen-decomposition of the Jacobi matrices of the orthogonal polynomials (Golub-Welsch), the
+// Lagrange basis is evaluated in barycentric form.  A mistake in either generator then shows up as a product/oracle mismatch.
+
+// cyclic Jacobi rotations on a symmetric n x n matrix (row-major, stride n): A -> diagonal, Q's columns -> eigenvectors
+void jacobi_eig(int n, ld* A, ld* Q) {
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) Q[i * n + j] = (i == j);
+  for (int sweep = 0; sweep < 200; sweep++) {
+    ld offd = 0;
+    for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) offd += A[i * n + j] * A[i * n + j];
+    if (offd < 1e-70L) break;
+    for (int p = 0; p < n; p++) for (int q = p + 1; q < n; q++) {
+      const ld apq = A[p * n + q];
+      if (fabsl(apq) < 1e-300L) continue;
+      const ld theta = (A[q * n + q] - A[p * n + p]) / (2 * apq);
+      const ld t = (theta >= 0 ? 1 : -1) / (fabsl(theta) + sqrtl(theta * theta + 1));
+      const ld c = 1 / sqrtl(t * t + 1), sn = t * c;
+      for (int k = 0; k < n; k++) { ld akp = A[k * n + p], akq = A[k * n + q]; A[k * n + p] = c * akp - sn * akq; A[k * n + q] = sn * akp + c * akq; }
+      for (int k = 0; k < n; k++) { ld apk = A[p * n + k], aqk = A[q * n + k]; A[p * n + k] = c * apk - sn * aqk; A[q * n + k] = sn * apk + c * aqk; }
+      for (int k = 0; k < n; k++) { ld qkp = Q[k * n + p], qkq = Q[k * n + q]; Q[k * n + p] = c * qkp - sn * qkq; Q[k * n + q] = sn * qkp + c * qkq; }
+    }
   }
-  P = p1; dP = d1;
 }
 
+// eigenvalues (ascending) of the symmetric tridiagonal matrix with zero diagonal and off-diagonal entries off[0..n-2];
+// z0[i] = first component of the i-th normalised eigenvector
+void tridiag_eig(int n, const ld* off, ld* ev, ld* z0) {
+  static thread_local ld A[kQ * kQ], Q[kQ * kQ];
+  for (int i = 0; i < n * n; i++) A[i] = 0;
+  for (int i = 0; i + 1 < n; i++) A[i * n + i + 1] = A[(i + 1) * n + i] = off[i];
+  jacobi_eig(n, A, Q);
+  int idx[kQ];
+  for (int i = 0; i < n; i++) idx[i] = i;
+  for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) if (A[idx[j] * n + idx[j]] < A[idx[i] * n + idx[i]]) std::swap(idx[i], idx[j]);
+  for (int i = 0; i < n; i++) { ev[i] = A[idx[i] * n + idx[i]]; z0[i] = Q[0 * n + idx[i]]; }
+}
+
+// Gauss-Lobatto nodes on [0,1] (qkgllocalbasis.hh:222-234): the end points and the zeros of P'_p, i.e. of the Jacobi polynomial
+// P^(1,1)_{p-1}, whose Jacobi matrix has zero diagonal and off-diagonal entries sqrt(k (k+2) / ((2k+1)(2k+3))), k = 1..p-2
 void gl_nodes(int p, ld* x) {
   if (p == 0) { x[0] = 0.5L; return; }
   x[0] = 0; x[p] = 1;
-  const ld pi = acosl(-1.0L);
-  for (int i = 1; i < p; i++) {
-    ld t = -cosl(pi * i / p);
-    for (int it = 0; it < 200; it++) {
-      ld P, dP; legendre(p, t, P, dP);
-      ld ddP = (2 * t * dP - (ld)p * (p + 1) * P) / (1 - t * t);
-      ld dt = dP / ddP; t -= dt;
-      if (fabsl(dt) < 1e-21L) break;
-    }
-    x[i] = (t + 1) / 2;
+  if (p >= 2) {
+    ld off[kMaxN], ev[kMaxN], z0[kMaxN];
+    for (int k = 1; k <= p - 2; k++) off[k - 1] = sqrtl((ld)k * (k + 2) / ((ld)(2 * k + 1) * (2 * k + 3)));
+    tridiag_eig(p - 1, off, ev, z0);
+    for (int i = 1; i < p; i++) x[i] = (ev[i - 1] + 1) / 2;
   }
-  for (int i = 0; i <= p / 2; i++) { ld a = (x[i] + (1 - x[p - i])) / 2; x[i] = a; x[p - i] = 1 - a; }
+  for (int i = 0; i <= p / 2; i++) { ld a = (x[i] + (1 - x[p - i])) / 2; x[i] = a; x[p - i] = 1 - a; }  // exact mirror symmetry
 }
 
+// m-point Gauss-Legendre rule on [0,1] (Golub-Welsch): off-diagonal entries k / sqrt(4 k^2 - 1), weights = first components squared
 void gauss(int m, ld* x, ld* w) {
-  const ld pi = acosl(-1.0L);
-  for (int i = 0; i < m; i++) {
-    ld t = -cosl(pi * (i + 0.75L) / (m + 0.5L)), P, dP;
-    for (int it = 0; it < 200; it++) { legendre(m, t, P, dP); ld dt = P / dP; t -= dt; if (fabsl(dt) < 1e-21L) break; }
-    legendre(m, t, P, dP);
-    x[i] = (t + 1) / 2; w[i] = 1 / ((1 - t * t) * dP * dP);
-  }
+  ld off[kQ], ev[kQ], z0[kQ];
+  for (int k = 1; k < m; k++) off[k - 1] = (ld)k / sqrtl(4 * (ld)k * k - 1);
+  tridiag_eig(m, off, ev, z0);
+  for (int i = 0; i < m; i++) { x[i] = (ev[i] + 1) / 2; w[i] = z0[i] * z0[i]; }
 }
 
-ld lag(int p, const ld* nd, int i, ld x) {
-  ld r = 1;
-  for (int j = 0; j <= p; j++) if (j != i) r *= (x - nd[j]) / (nd[i] - nd[j]);
-  return r;
+// Lagrange basis on the nodes nd[0..p] in barycentric form: l_i(x) = (b_i / (x - x_i)) / sum_j b_j / (x - x_j)
+void bary_weights(int p, const ld* nd, ld* b) {
+  for (int i = 0; i <= p; i++) { ld d = 1; for (int j = 0; j <= p; j++) if (j != i) d *= (nd[i] - nd[j]); b[i] = 1 / d; }
 }
+ld lag(int p, const ld* nd, int i, ld x) {
+  ld b[kMaxN];
+  bary_weights(p, nd, b);
+  for (int j = 0; j <= p; j++) if (x == nd[j]) return i == j ? 1 : 0;
+  ld den = 0;
+  for (int j = 0; j <= p; j++) den += b[j] / (x - nd[j]);
+  return b[i] / (x - nd[i]) / den;
+}
+// l_i'(x): at a node x_k != x_i it is (b_i / b_k) / (x_k - x_i); otherwise l_i(x) * sum_{j != i} 1 / (x - x_j)
 ld dlag(int p, const ld* nd, int i, ld x) {
-  ld r = 0;
-  for (int j = 0; j <= p; j++) if (j != i) {
-    ld prod = 1 / (nd[i] - nd[j]);
-    for (int l = 0; l <= p; l++) if (l != i && l != j) prod *= (x - nd[l]) / (nd[i] - nd[l]);
-    r += prod;
-  }
-  return r;
+  ld b[kMaxN];
+  bary_weights(p, nd, b);
+  for (int k = 0; k <= p; k++) if (x == nd[k] && k != i) return b[i] / b[k] / (nd[k] - nd[i]);
+  ld sum = 0;
+  for (int j = 0; j <= p; j++) if (j != i) sum += 1 / (x - nd[j]);
+  return lag(p, nd, i, x) * sum;
 }
 
 // in-place inverse by Gauss-Jordan with partial pivoting, n x n, stride n

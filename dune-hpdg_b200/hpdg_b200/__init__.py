@@ -92,11 +92,21 @@ SIGNATURES = {
                                   C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "hpdg_loop_solve_device": (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_double, C.c_int,
                                          C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+    "hpdg_tables_1d": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "hpdg_launch_count": (C.c_long, [_vp]),
     "hpdg_uses_uniform_kernel": (C.c_int, [_vp, C.c_int]),
     "hpdg_time_apply_device": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.POINTER(C.c_float)]),
     "hpdg_time_jacobi_device": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_double, C.c_int, C.POINTER(C.c_float)]),
 }
+
+
+def tables_1d(p):
+    """(nodes, M, S, t, g) of degree p as the kernels use them (host-only introspection)"""
+    n = p + 1
+    nodes, M, S, t, g = np.zeros(n), np.zeros((n, n)), np.zeros((n, n)), np.zeros((2, n)), np.zeros((2, n))
+    if lib().hpdg_tables_1d(p, nodes.ctypes.data, M.ctypes.data, S.ctypes.data, t.ctypes.data, g.ctypes.data):
+        raise HpdgError(lib().hpdg_last_error(None).decode())
+    return nodes, M, S, t, g
 
 
 class HpdgError(RuntimeError):

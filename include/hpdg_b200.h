@@ -178,6 +178,10 @@ int hpdg_loop_solve_device(hpdg_ctx* ctx, int form, double damping, int pre, int
                            const double* d_b, double tol, int maxit, int* iters, double* last_error);
 
 /* -- introspection --------------------------------------------------------------------------------- */
+/* Host-only (no device work): the 1-D tables of degree p the kernels are built from -- GL nodes on [0,1] ascending
+ * (qkgllocalbasis.hh:222-234), exact mass int l_i l_j and stiffness int l_i' l_j' (n x n row-major, n = p + 1), l_i(s) and l_i'(s)
+ * at the end points s = 0, 1 ([2][n]).  Any output may be NULL. */
+int hpdg_tables_1d(int degree, double* nodes, double* mass, double* stiffness, double* end_values, double* end_derivatives);
 long hpdg_launch_count(const hpdg_ctx* ctx);      /* kernels launched so far by this context */
 int hpdg_uses_uniform_kernel(const hpdg_ctx* ctx, int level);
 /* time `reps` back-to-back operator applies with CUDA events on the context stream; ms per apply */
