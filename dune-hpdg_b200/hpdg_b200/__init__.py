@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libhpdg_b200.so")
+# HPDG_B200_LIB: load another build of the same library (kernel A/B experiments of tools/, e.g. `make EXTRA=-DQ3P_...`)
+LIB_PATH = os.environ.get("HPDG_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libhpdg_b200.so")
 
 FINEST = -1
 JACOBI_DENSE = 0
