@@ -114,13 +114,17 @@ int setup_level(Ctx* ctx, Level& L, int dim, const int* n, const double* h, cons
 }
 
 void free_level(Level& L) {
-  cudaFree(L.d_deg); cudaFree(L.d_pdeg); cudaFree(L.d_off); cudaFree(L.d_elist);
+  cudaFree(L.d_deg); cudaFree(L.d_pdeg); cudaFree(L.d_off); cudaFree(L.d_elist); cudaFree(L.d_troff); cudaFree(L.d_tr);
   cudaFree(L.jd.d_inv); cudaFree(L.jf.d_fac); cudaFree(L.jf.d_idx);
   cudaFree(L.mg_x); cudaFree(L.mg_r); cudaFree(L.mg_t1); cudaFree(L.mg_t2);
   cudaFree(L.d_tiles_int); cudaFree(L.d_tiles_bnd); cudaFree(L.d_tiles_all); cudaFree(L.d_tile_desc); cudaFree(L.d_jinv);
   cudaFree(L.bcrs.d_rowptr); cudaFree(L.bcrs.d_col); cudaFree(L.bcrs.d_brow); cudaFree(L.bcrs.d_boff); cudaFree(L.bcrs.d_val);
   cudaFree(L.bcrs.d_wave); cudaFree(L.bcrs.d_res); cudaFree(L.bcrs.d_l1reg);
-  for (int f = 0; f < 6; f++) { cudaFree(L.cg.d_send[f]); cudaFree(L.cg.d_recv[f]); }
+  for (int f = 0; f < 6; f++) {
+    cudaFree(L.cg.d_send[f]); cudaFree(L.cg.d_recv[f]);
+    cudaFree(L.hpg.d_deg[f]); cudaFree(L.hpg.d_pdeg[f]); cudaFree(L.hpg.d_troff[f]); cudaFree(L.hpg.d_recv[f]); cudaFree(L.hpg.d_send[f]);
+    cudaFree(L.hpg.d_send_src[f]); cudaFree(L.hpg.d_send_dst[f]);
+  }
 }
 
 int create_common(Ctx* ctx, int dim, const int* n, const double* Lx, const std::vector<int>& deg, double sigma,
@@ -222,12 +226,9 @@ int op_apply_distributed(Ctx* ctx, Level& L, const double* d_x, double* d_y, dou
 }
 
 int op_apply_async(Ctx* ctx, Level& L, const double* d_x, double* d_y, double factor) {
-  if (ctx->nranks > 1) {
-    if (!uniform_supported(ctx, L)) { ctx->err = "distributed apply needs a level with a uniform-degree 3-D kernel"; return 1; }
-    return op_apply_distributed(ctx, L, d_x, d_y, factor);
-  }
-  if (uniform_supported(ctx, L)) return launch_apply_uniform(ctx, L, d_x, d_y, factor, 0);
-  return launch_apply_generic(ctx, L, d_x, d_y, factor);
+  if (ctx->nranks > 1 && uniform_supported(ctx, L) && !ctx->hp_distributed) return op_apply_distributed(ctx, L, d_x, d_y, factor);
+  if (ctx->nranks == 1 && uniform_supported(ctx, L)) return launch_apply_uniform(ctx, L, d_x, d_y, factor, 0);
+  return launch_apply_generic(ctx, L, d_x, d_y, factor);   // any degree map; distributed: hp face-trace halo over NCCL
 }
 
 int jacobi_async(Ctx* ctx, Level& L, int form, const double* r, double* c, double damping) {
@@ -236,6 +237,107 @@ int jacobi_async(Ctx* ctx, Level& L, int form, const double* r, double* c, doubl
   ctx->err = "unknown block-Jacobi form"; return 1;
 }
 
+// ---- distributed hp: ghost degrees (once per level) and face-trace halo (per apply) over NCCL -------------------------------------
+// boundary elements of brick face f in face-element order (lower tangential direction fastest)
+std::vector<long> face_elements(const Level& L, int f) {
+  const int d = f / 2, s = f % 2, ta = d == 0 ? 1 : 0, tb = d == 2 ? 1 : 2;
+  const long stride[3] = {1, L.n[0], (long)L.n[0] * L.n[1]};
+  std::vector<long> out;
+  for (int b = 0; b < (L.dim == 3 ? L.n[tb] : 1); b++)
+    for (int a = 0; a < L.n[ta]; a++)
+      out.push_back((s ? L.n[d] - 1 : 0) * stride[d] + a * stride[ta] + (L.dim == 3 ? b * stride[tb] : 0));
+  return out;
+}
+
+}  // namespace
+namespace hpdg {
+int hp_ghost_setup(Ctx* ctx, Level& L) {
+  HpGhost& G = L.hpg;
+  if (G.ready) return 0;
+  if (!ctx->nccl) { ctx->err = "the distributed hp apply needs the NCCL communicator (context created with nccl_id = NULL)"; return 1; }
+  ncclComm_t comm = (ncclComm_t)ctx->nccl;
+  if (generic_trace_setup(ctx, L)) return 1;
+  // 1. exchange the finest-level degrees of the boundary elements (the analogue of parallel/updatedegrees.hh:11-46)
+  int* d_sdeg[6] = {};
+  std::vector<long> fel[6];
+  for (int f = 0; f < 6; f++) {
+    if (!ctx->ghost.active[f]) continue;
+    fel[f] = face_elements(L, f);
+    G.nface[f] = (long)fel[f].size();
+    std::vector<int> pd(fel[f].size());
+    for (size_t i = 0; i < fel[f].size(); i++) pd[i] = L.pdeg[fel[f][i]];
+    HPDG_CUDA(cudaMalloc(&d_sdeg[f], sizeof(int) * pd.size()));
+    HPDG_CUDA(cudaMemcpy(d_sdeg[f], pd.data(), sizeof(int) * pd.size(), cudaMemcpyHostToDevice));
+    HPDG_CUDA(cudaMalloc(&G.d_pdeg[f], sizeof(int) * pd.size()));
+    HPDG_CUDA(cudaMalloc(&G.d_deg[f], sizeof(int) * pd.size()));
+  }
+  HPDG_NCCL(g_nccl.GroupStart());
+  for (int f = 0; f < 6; f++) {
+    if (!ctx->ghost.active[f]) continue;
+    HPDG_NCCL(g_nccl.Send(d_sdeg[f], (size_t)G.nface[f], ncclInt32, ctx->ghost.peer[f], comm, ctx->stream));
+    HPDG_NCCL(g_nccl.Recv(G.d_pdeg[f], (size_t)G.nface[f], ncclInt32, ctx->ghost.peer[f], comm, ctx->stream));
+  }
+  HPDG_NCCL(g_nccl.GroupEnd());
+  HPDG_CUDA(cudaStreamSynchronize(ctx->stream));
+  // 2. this level's ghost degrees (the level's cap applied, ordertransfer.hh:62-67), receive offsets, send gather lists
+  G.maxp = 0;
+  for (int f = 0; f < 6; f++) {
+    if (!ctx->ghost.active[f]) continue;
+    cudaFree(d_sdeg[f]);
+    const long nfc = G.nface[f];
+    G.h_pdeg[f].resize(nfc); G.h_deg[f].resize(nfc);
+    HPDG_CUDA(cudaMemcpy(G.h_pdeg[f].data(), G.d_pdeg[f], sizeof(int) * nfc, cudaMemcpyDeviceToHost));
+    std::vector<long> roff(nfc), src(nfc), dst(nfc + 1, 0);
+    long rp = 0;
+    for (long i = 0; i < nfc; i++) {
+      if (G.h_pdeg[f][i] < 0 || G.h_pdeg[f][i] > kMaxP) { ctx->err = "ghost degree out of range (neighbour rank sent garbage?)"; return 1; }
+      G.h_deg[f][i] = L.cap >= 0 ? std::min(G.h_pdeg[f][i], L.cap) : G.h_pdeg[f][i];
+      G.maxp = std::max(G.maxp, G.h_deg[f][i]);
+      roff[i] = rp; rp += ipow_h(G.h_deg[f][i] + 1, L.dim - 1);
+      const long e = fel[f][i];
+      const long nfe = ipow_h(L.deg[e] + 1, L.dim - 1);
+      long tro = 0;  // offset of element e's traces: prefix over the elements' 2 dim N^(dim-1) pairs
+      (void)tro;
+      src[i] = -1; dst[i + 1] = dst[i] + nfe;
+    }
+    // element trace offsets (host prefix, as generic_trace_setup builds them)
+    {
+      std::vector<long> troff(L.nelem + 1, 0);
+      for (long e = 0; e < L.nelem; e++) troff[e + 1] = troff[e] + 2 * L.dim * ipow_h(L.deg[e] + 1, L.dim - 1);
+      for (long i = 0; i < nfc; i++) { const long e = fel[f][i]; src[i] = troff[e] + (long)f * ipow_h(L.deg[e] + 1, L.dim - 1); }
+    }
+    G.recv_pairs[f] = rp; G.send_pairs[f] = dst[nfc];
+    HPDG_CUDA(cudaMemcpy(G.d_deg[f], G.h_deg[f].data(), sizeof(int) * nfc, cudaMemcpyHostToDevice));
+    HPDG_CUDA(cudaMalloc(&G.d_troff[f], sizeof(long) * nfc));
+    HPDG_CUDA(cudaMemcpy(G.d_troff[f], roff.data(), sizeof(long) * nfc, cudaMemcpyHostToDevice));
+    HPDG_CUDA(cudaMalloc(&G.d_send_src[f], sizeof(long) * nfc));
+    HPDG_CUDA(cudaMemcpy(G.d_send_src[f], src.data(), sizeof(long) * nfc, cudaMemcpyHostToDevice));
+    HPDG_CUDA(cudaMalloc(&G.d_send_dst[f], sizeof(long) * (nfc + 1)));
+    HPDG_CUDA(cudaMemcpy(G.d_send_dst[f], dst.data(), sizeof(long) * (nfc + 1), cudaMemcpyHostToDevice));
+    HPDG_CUDA(cudaMalloc(&G.d_recv[f], sizeof(double) * 2 * std::max<long>(rp, 1)));
+    HPDG_CUDA(cudaMalloc(&G.d_send[f], sizeof(double) * 2 * std::max<long>(dst[nfc], 1)));
+  }
+  G.ready = true;
+  return 0;
+}
+// Per apply (after k_face_traces): gather this rank's boundary traces, one grouped ncclSend/ncclRecv with the <= 6 face neighbours
+// (variable-size blocks per element: parallel/communicationhpdg.hh:387-418), all on the context stream.
+int hp_halo_exchange(Ctx* ctx, Level& L) {
+  if (hp_ghost_setup(ctx, L)) return 1;
+  if (launch_hp_pack(ctx, L, ctx->stream)) return 1;
+  ncclComm_t comm = (ncclComm_t)ctx->nccl;
+  HPDG_NCCL(g_nccl.GroupStart());
+  for (int f = 0; f < 6; f++) {
+    if (!ctx->ghost.active[f]) continue;
+    HPDG_NCCL(g_nccl.Send(L.hpg.d_send[f], (size_t)L.hpg.send_pairs[f] * 2, ncclDouble, ctx->ghost.peer[f], comm, ctx->stream));
+    HPDG_NCCL(g_nccl.Recv(L.hpg.d_recv[f], (size_t)L.hpg.recv_pairs[f] * 2, ncclDouble, ctx->ghost.peer[f], comm, ctx->stream));
+  }
+  HPDG_NCCL(g_nccl.GroupEnd());
+  return 0;
+}
+}  // namespace hpdg
+
+namespace {
 // ---- V-cycle (iterationsteps/mg/multigrid_impl.hh:16-117) -----------------------------------------
 struct VC { int form; double damping; int pre, post, coarse_its; };
 
@@ -395,30 +497,18 @@ int hpdg_nccl_unique_id(void* out128) {
   return 0;
 }
 
-int hpdg_create_distributed(hpdg_ctx** out, int dim, const int* n, const double* L, int degree, double sigma,
-                            int dirichlet, int device, const int* pgrid, int rank, int nranks, const void* nccl_id) {
-  *out = nullptr;
-  if (dim != 3) { g_create_err = "distributed bricks are 3-D"; return 1; }
-  if (!n || !L || !pgrid) { g_create_err = "null argument"; return 1; }
-  for (int d = 0; d < 3; d++) {
-    if (n[d] < 1) { g_create_err = "mesh extents must be positive"; return 1; }
-    if (pgrid[d] < 1) { g_create_err = "pgrid entries must be positive"; return 1; }
-  }
-  if (nranks < 1 || pgrid[0] * pgrid[1] * pgrid[2] != nranks) { g_create_err = "pgrid does not match nranks"; return 1; }
-  if (rank < 0 || rank >= nranks) { g_create_err = "rank out of range"; return 1; }
-  if (degree < 0 || degree > kMaxP) { g_create_err = "polynomial degree out of range 0..13"; return 1; }
-  if (nranks > 1 && (degree < 1 || degree > 5)) { g_create_err = "distributed path needs a degree with a specialised uniform kernel (1..5)"; return 1; }
-  long nelem = (long)n[0] * n[1] * n[2];
-  std::vector<int> deg(nelem, degree);
+// common part of the distributed creators: `deg` holds one degree per local element; hp = per-element degree map (generic path)
+static int create_distributed_common(hpdg_ctx** out, int dim, const int* n, const double* L, const std::vector<int>& deg, bool hp,
+                                     double sigma, int dirichlet, int device, const int* pgrid, int rank, int nranks,
+                                     const void* nccl_id) {
+  const long nelem = (long)n[0] * n[1] * n[2];
   hpdg_ctx* ctx = new hpdg_ctx();
   if (create_common(ctx, dim, n, L, deg, sigma, dirichlet, device)) { g_create_err = ctx->err; delete ctx; return 1; }
-  ctx->rank = rank; ctx->nranks = nranks;
+  ctx->rank = rank; ctx->nranks = nranks; ctx->hp_distributed = hp;
   for (int d = 0; d < 3; d++) ctx->pgrid[d] = pgrid[d];
   ctx->pcoord[0] = rank % pgrid[0]; ctx->pcoord[1] = (rank / pgrid[0]) % pgrid[1]; ctx->pcoord[2] = rank / (pgrid[0] * pgrid[1]);
   auto fail = [&](const std::string& e) { g_create_err = e; hpdg_destroy(ctx); return 1; };
   if (nranks > 1) {
-    Level& Lv = ctx->levels.back();
-    if (!uniform_supported(ctx, Lv)) return fail("distributed path needs a degree with a specialised uniform kernel (1..5)");
     if (nccl_id) {  // nccl_id == NULL: no NCCL communicator (peer-memory halo only; entry points that need NCCL then fail)
       std::string err;
       if (!load_nccl(err)) return fail(err);
@@ -429,7 +519,6 @@ int hpdg_create_distributed(hpdg_ctx** out, int dim, const int* n, const double*
       if (r != ncclSuccess) return fail(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
       ctx->nccl = comm;
     }
-    const int N2 = (degree + 1) * (degree + 1);
     const int pstride[3] = {1, pgrid[0], pgrid[0] * pgrid[1]};
     for (int f = 0; f < 6; f++) {
       const int d = f / 2, s = f % 2;
@@ -438,30 +527,74 @@ int hpdg_create_distributed(hpdg_ctx** out, int dim, const int* n, const double*
       ctx->bnd_is_rank[f] = true;
       ctx->ghost.active[f] = true;
       ctx->ghost.peer[f] = rank + (s ? pstride[d] : -pstride[d]);
-      size_t felems = (size_t)nelem / n[d];
-      ctx->ghost.count[f] = felems * N2 * 2;
-      if (cudaMalloc(&ctx->ghost.d_send[f], ctx->ghost.count[f] * sizeof(double)) != cudaSuccess ||
-          cudaMalloc(&ctx->ghost.d_recv[f], ctx->ghost.count[f] * sizeof(double)) != cudaSuccess)
-        return fail("cudaMalloc of halo buffers failed");
     }
-    // arena for the peer-to-peer mode: identical layout on every rank (all six faces, sized from the brick shape)
-    size_t offb = 0;
-    for (int f = 0; f < 6; f++) {
-      const size_t bytes = ((size_t)nelem / n[f / 2]) * N2 * 2 * sizeof(double);
-      for (int par = 0; par < 2; par++) { ctx->ghost.recv_off[f][par] = offb; offb += (bytes + 255) / 256 * 256; }
+    if (!hp) {
+      // uniform degree: fixed-size trace buffers for the NCCL transport and the arena of the peer-memory transport
+      const int N2 = (deg[0] + 1) * (deg[0] + 1);
+      for (int f = 0; f < 6; f++) {
+        if (!ctx->ghost.active[f]) continue;
+        size_t felems = (size_t)nelem / n[f / 2];
+        ctx->ghost.count[f] = felems * N2 * 2;
+        if (cudaMalloc(&ctx->ghost.d_send[f], ctx->ghost.count[f] * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&ctx->ghost.d_recv[f], ctx->ghost.count[f] * sizeof(double)) != cudaSuccess)
+          return fail("cudaMalloc of halo buffers failed");
+      }
+      // arena for the peer-to-peer mode: identical layout on every rank (all six faces, sized from the brick shape)
+      size_t offb = 0;
+      for (int f = 0; f < 6; f++) {
+        const size_t bytes = ((size_t)nelem / n[f / 2]) * N2 * 2 * sizeof(double);
+        for (int par = 0; par < 2; par++) { ctx->ghost.recv_off[f][par] = offb; offb += (bytes + 255) / 256 * 256; }
+      }
+      ctx->ghost.flag_off = offb; offb += 256;
+      ctx->ghost.arena_bytes = offb;
+      if (cudaMalloc(&ctx->ghost.arena, offb) != cudaSuccess || cudaMemset(ctx->ghost.arena, 0, offb) != cudaSuccess)
+        return fail("cudaMalloc of the halo arena failed");
+      int* herr = nullptr;
+      if (cudaHostAlloc(&herr, sizeof(int), cudaHostAllocMapped) != cudaSuccess) return fail("cudaHostAlloc of the halo time-out flag failed");
+      *herr = 0;
+      ctx->h_ghost_err = herr;
+      if (cudaHostGetDevicePointer(&ctx->d_ghost_err, herr, 0) != cudaSuccess) return fail("cudaHostGetDevicePointer failed");
     }
-    ctx->ghost.flag_off = offb; offb += 256;
-    ctx->ghost.arena_bytes = offb;
-    if (cudaMalloc(&ctx->ghost.arena, offb) != cudaSuccess || cudaMemset(ctx->ghost.arena, 0, offb) != cudaSuccess)
-      return fail("cudaMalloc of the halo arena failed");
-    int* herr = nullptr;
-    if (cudaHostAlloc(&herr, sizeof(int), cudaHostAllocMapped) != cudaSuccess) return fail("cudaHostAlloc of the halo time-out flag failed");
-    *herr = 0;
-    ctx->h_ghost_err = herr;
-    if (cudaHostGetDevicePointer(&ctx->d_ghost_err, herr, 0) != cudaSuccess) return fail("cudaHostGetDevicePointer failed");
   }
   *out = ctx;
   return 0;
+}
+
+static int check_distributed_args(int dim, const int* n, const double* L, const int* pgrid, int rank, int nranks) {
+  if (dim != 3) { g_create_err = "distributed bricks are 3-D"; return 1; }
+  if (!n || !L || !pgrid) { g_create_err = "null argument"; return 1; }
+  for (int d = 0; d < 3; d++) {
+    if (n[d] < 1) { g_create_err = "mesh extents must be positive"; return 1; }
+    if (pgrid[d] < 1) { g_create_err = "pgrid entries must be positive"; return 1; }
+  }
+  if (nranks < 1 || pgrid[0] * pgrid[1] * pgrid[2] != nranks) { g_create_err = "pgrid does not match nranks"; return 1; }
+  if (rank < 0 || rank >= nranks) { g_create_err = "rank out of range"; return 1; }
+  return 0;
+}
+
+int hpdg_create_distributed(hpdg_ctx** out, int dim, const int* n, const double* L, int degree, double sigma,
+                            int dirichlet, int device, const int* pgrid, int rank, int nranks, const void* nccl_id) {
+  *out = nullptr;
+  if (check_distributed_args(dim, n, L, pgrid, rank, nranks)) return 1;
+  if (degree < 0 || degree > kMaxP) { g_create_err = "polynomial degree out of range 0..13"; return 1; }
+  if (nranks > 1 && (degree < 1 || degree > 5)) { g_create_err = "the uniform distributed path needs a degree with a specialised kernel (1..5); use hpdg_create_distributed_hp"; return 1; }
+  std::vector<int> deg((size_t)n[0] * n[1] * n[2], degree);
+  return create_distributed_common(out, dim, n, L, deg, false, sigma, dirichlet, device, pgrid, rank, nranks, nccl_id);
+}
+
+int hpdg_create_distributed_hp(hpdg_ctx** out, int dim, const int* n, const double* L, const int* degree, double sigma,
+                               int dirichlet, int device, const int* pgrid, int rank, int nranks, const void* nccl_id) {
+  *out = nullptr;
+  if (check_distributed_args(dim, n, L, pgrid, rank, nranks)) return 1;
+  if (!degree) { g_create_err = "degree array is null"; return 1; }
+  if (nranks > 1 && !nccl_id) { g_create_err = "the distributed hp path exchanges its halo over NCCL: nccl_id must not be null"; return 1; }
+  const long nelem = (long)n[0] * n[1] * n[2];
+  std::vector<int> deg(nelem);
+  for (long e = 0; e < nelem; e++) {
+    deg[e] = degree[e];
+    if (deg[e] < 0 || deg[e] > kMaxP) { g_create_err = "polynomial degree out of range 0..13"; return 1; }
+  }
+  return create_distributed_common(out, dim, n, L, deg, true, sigma, dirichlet, device, pgrid, rank, nranks, nccl_id);
 }
 
 void hpdg_destroy(hpdg_ctx* ctx) {
@@ -535,6 +668,7 @@ int hpdg_build_p_hierarchy(hpdg_ctx* ctx) {
     std::vector<int> deg(fine.nelem);
     for (long e = 0; e < fine.nelem; e++) deg[e] = std::min(lv[idx + 1].deg[e], cap);  // ordertransfer.hh:62-67
     Level L;
+    L.cap = cap;
     if (setup_level(ctx, L, fine.dim, fine.n, fine.h, deg, fine.pdeg)) {  // leave the context as it was: one level
       free_level(L);
       for (int k = idx + 1; k < pLevels; k++) free_level(lv[k]);

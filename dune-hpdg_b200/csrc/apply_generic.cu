@@ -1,8 +1,8 @@
-// Generic hp SIPG operator apply: one CTA per element, elements bucketed by degree.
+// Generic hp SIPG operator apply: elements bucketed by degree, any per-element degree 0..13, 2-D and 3-D.
 //
 // Replaces, for any per-element degree map, the reference's Operator::apply over an IPDGOperator
 // (matrix-free/operator.hh:41-56, matrix-free/localoperators/ipdgoperator.hh:80-390) and equally the
-// assembled DynamicBCRSMatrix::mv (common/matrixwindow.hh:196-209).  Formulation (DESIGN.md §3):
+// assembled DynamicBCRSMatrix::mv (common/matrixwindow.hh:196-209).  Formulation (DESIGN.md section 3):
 // element-centric "pull" -- each element computes its own rows from its own block and the face
 // traces of its neighbours, so there is no scatter into neighbour rows (the reference's
 // "not thread-safe" write, ipdgoperator.hh:233-243) and the summation order is fixed.
@@ -12,6 +12,17 @@
 //
 // with, per face node, alpha/beta built from the own trace (der_s, val_s) and -- through the
 // L2 projection P = (M^{ee})^-1 M^{eo} in the tangential directions -- the neighbour's trace.
+//
+// Two kernels per apply:
+//  * k_face_traces (ONE launch for the whole level): every element writes its OWN face traces once -- per face node the pair
+//    (der, val) = (g_s . line, t_s . line) of the DoF line normal to the face -- into the level's trace array.
+//  * k_apply_generic<DIM, N1> (one launch per degree bucket, buckets concurrent on side streams): a CTA takes several
+//    elements of the bucket, N1^(DIM-1) threads per element (one per DoF line).  Neighbour traces are PULLED from the trace
+//    array (N_o^(DIM-1) coalesced 16-byte loads per face) instead of being re-derived from the neighbour's full block; for
+//    mixed-degree faces the tangential projection runs in two separable stages through shared memory.  Then, per direction,
+//    a thread holds its DoF line in registers: own traces, alpha/beta of its two face nodes, T~_d sweep; finally the three
+//    mass sweeps.  All index arithmetic on the element's own block is compile-time (DIM, N1 template parameters).
+// The trace array is also exactly what crosses a rank boundary in the distributed hp path (csrc/api.cu).
 #include <algorithm>
 #include <cstdio>
 
@@ -36,126 +47,128 @@ struct GenericParams {
   double* y;
   double factor;
   int accum;
+  const long* troff;     // per element: offset (in pairs) of its face traces, face f at troff[e] + f * N_e^(dim-1)
+  const double2* tr;     // face traces (der, val) of every element (k_face_traces)
+  // distributed hp (rank-local brick): faces on a rank boundary take the neighbour's degree and traces from the ghost layer
+  int bnd_is_rank[6];
+  const int* ghost_deg[6];      // [face element] degree of the remote element across brick face f
+  const int* ghost_pdeg[6];     // [face element] its finest-level degree (face penalty)
+  const long* ghost_troff[6];   // [face element] offset (pairs) of its traces in ghost_tr[f]
+  const double2* ghost_tr[6];
 };
 
-__device__ __forceinline__ int ipow_d(int b, int e) { int r = 1; for (int i = 0; i < e; i++) r *= b; return r; }
-
-// Per-face metadata of the element a CTA works on (computed once by 2*dim threads, read by all).
-struct FaceInfo {
-  int has_nb;      // neighbour element exists
-  int skip;        // natural boundary: no face term at all (ipdgoperator.hh:97-105)
-  int po;          // neighbour degree
-  long uo;         // offset of the neighbour's block
-  double w_nu_k;   // w * nu * kappa   (w = 1/2 interior, 1 Dirichlet: ipdgoperator.hh:186,357)
-  double cpen;     // sigma * max(p-,p+)^2 (ipdgoperator.hh:129-131) or sigma p^2 on the boundary (:310)
-  double A1, A2, A3;
-};
-
-// base offset (inside a block of n1^dim doubles) of the DoF line normal to direction d through face node `node`
-__device__ __forceinline__ int line_base(int dim, int n1, int d, int node) {
-  int rem = node, base = 0, st = 1;
-  for (int dd = 0; dd < dim; dd++) {
-    if (dd != d) { base += (rem % n1) * st; rem /= n1; }
-    st *= n1;
-  }
-  return base;
-}
-
-
-// sum_k a[k*sa] * b[k*sb] for k < n, n compile-time for the common degrees so the loads pipeline
-template <int NN>
-__device__ __forceinline__ void dot2_n(const double* __restrict__ c0, const double* __restrict__ c1, int sc, const double* __restrict__ v,
-                                       int sv, double& r0, double& r1) {
-  double a = 0, b = 0;
-#pragma unroll
-  for (int k = 0; k < NN; k++) { const double x = v[k * sv]; a = fma(c0[k * sc], x, a); b = fma(c1[k * sc], x, b); }
-  r0 = a; r1 = b;
-}
-__device__ __forceinline__ void dot2(int n, const double* __restrict__ c0, const double* __restrict__ c1, int sc,
-                                     const double* __restrict__ v, int sv, double& r0, double& r1) {
-  switch (n) {
-    case 1: dot2_n<1>(c0, c1, sc, v, sv, r0, r1); break;
-    case 2: dot2_n<2>(c0, c1, sc, v, sv, r0, r1); break;
-    case 3: dot2_n<3>(c0, c1, sc, v, sv, r0, r1); break;
-    case 4: dot2_n<4>(c0, c1, sc, v, sv, r0, r1); break;
-    case 5: dot2_n<5>(c0, c1, sc, v, sv, r0, r1); break;
-    case 6: dot2_n<6>(c0, c1, sc, v, sv, r0, r1); break;
-    case 7: dot2_n<7>(c0, c1, sc, v, sv, r0, r1); break;
-    case 8: dot2_n<8>(c0, c1, sc, v, sv, r0, r1); break;
-    default: {
-      double a = 0, b = 0;
-      for (int k = 0; k < n; k++) { const double x = v[k * sv]; a = fma(c0[k * sc], x, a); b = fma(c1[k * sc], x, b); }
-      r0 = a; r1 = b;
-    }
-  }
-}
-// one coefficient row applied to two vectors
-template <int NN>
-__device__ __forceinline__ void dotp_n(const double* __restrict__ c, const double* __restrict__ v0, const double* __restrict__ v1, int sv,
-                                       double& r0, double& r1) {
-  double a = 0, b = 0;
-#pragma unroll
-  for (int k = 0; k < NN; k++) { const double pv = c[k]; a = fma(pv, v0[k * sv], a); b = fma(pv, v1[k * sv], b); }
-  r0 = a; r1 = b;
-}
-__device__ __forceinline__ void dotp(int n, const double* __restrict__ c, const double* __restrict__ v0, const double* __restrict__ v1,
-                                     int sv, double& r0, double& r1) {
-  switch (n) {
-    case 1: dotp_n<1>(c, v0, v1, sv, r0, r1); break;
-    case 2: dotp_n<2>(c, v0, v1, sv, r0, r1); break;
-    case 3: dotp_n<3>(c, v0, v1, sv, r0, r1); break;
-    case 4: dotp_n<4>(c, v0, v1, sv, r0, r1); break;
-    case 5: dotp_n<5>(c, v0, v1, sv, r0, r1); break;
-    case 6: dotp_n<6>(c, v0, v1, sv, r0, r1); break;
-    case 7: dotp_n<7>(c, v0, v1, sv, r0, r1); break;
-    case 8: dotp_n<8>(c, v0, v1, sv, r0, r1); break;
-    default: {
-      double a = 0, b = 0;
-      for (int k = 0; k < n; k++) { const double pv = c[k]; a = fma(pv, v0[k * sv], a); b = fma(pv, v1[k * sv], b); }
-      r0 = a; r1 = b;
-    }
-  }
-}
+__host__ __device__ __forceinline__ int ipow_d(int b, int e) { int r = 1; for (int i = 0; i < e; i++) r *= b; return r; }
 
 template <int B, int E> struct CPow { static constexpr int v = B * CPow<B, E - 1>::v; };
 template <int B> struct CPow<B, 0> { static constexpr int v = 1; };
 
-// 1-D tables of the bucket's degree, passed by value (constant bank)
-template <int N1> struct GenTab { double MinvS[N1 * N1], M[N1 * N1], mt[2][N1], mg[2][N1], g[2][N1], t[2][N1]; };
-
-// One CTA handles `epc` elements of one degree bucket.  DIM and N1 = p + 1 are compile-time, so all index arithmetic on the
-// elements' own blocks folds to constants; only the neighbours' degrees are run-time.
-//   face phases : per face node, own trace and neighbour trace (tangentially L2-projected when the degrees differ) -> alpha, beta
-//   line passes : one thread per DoF line (N1^(DIM-1) threads per element), the line in registers:
-//                 X: w = T~_x u   Y: w += T~_y u   Z: w += T~_z u, w = M_z w   then M_y, then M_x -> global
+// Base offset and stride (inside a block of N1^DIM doubles, x-fastest) of DoF line `line` along direction d.  The line index
+// is also the face-node index of the line's end points on the two faces normal to d (tangential coordinates, lower
+// direction fastest): line = j + N1 k (d = 0), i + N1 k (d = 1), i + N1 j (d = 2).
 template <int DIM, int N1>
-__global__ void k_apply_generic(GenericParams P, GenTab<N1> T, int maxno1, long cnt, int epc, int per_elem) {
+__device__ __forceinline__ int line_base_c(int d, int line) {
+  if (d == 0) return N1 * line;
+  if (DIM == 2) return line;
+  return d == 1 ? (line % N1) + N1 * N1 * (line / N1) : line;
+}
+template <int N1> __device__ __forceinline__ int line_stride_c(int d) { return d == 0 ? 1 : (d == 1 ? N1 : N1 * N1); }
+
+// ---- pass 1: own face traces of every element, one launch for all degree buckets --------------------------------------------
+constexpr int kTraceThreads = 128;
+struct TraceParams {
+  int nb;                     // degree buckets
+  int bucket_n1[kMaxN];
+  long bucket_ebegin[kMaxN + 1];   // bucket ranges in elist
+  long cta_begin[kMaxN + 1];       // first CTA of every bucket
+  const int* elist; const long* off; const long* troff;
+  const double* x; double2* tr;
+};
+// 1-D end-point tables (l_i'(s), l_i(s)) of all degrees, stride kMaxN, in constant memory
+__constant__ double c_end_g[kMaxN][2][kMaxN];
+__constant__ double c_end_t[kMaxN][2][kMaxN];
+
+template <int DIM, int N1>
+__device__ __forceinline__ void face_traces_body(const TraceParams& P, long ebegin, long cnt, long cta) {
+  constexpr int nf = CPow<N1, DIM - 1>::v;
+  constexpr int epc = nf >= kTraceThreads ? 1 : kTraceThreads / nf;
+  for (int t = threadIdx.x; t < epc * nf; t += kTraceThreads) {
+    const int lel = t / nf, line = t % nf;
+    const long idx = cta * epc + lel;
+    if (idx >= cnt) continue;
+    const long e = P.elist[ebegin + idx];
+    const double* __restrict__ xe = P.x + P.off[e];
+    double2* __restrict__ out = P.tr + P.troff[e];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      const int base = line_base_c<DIM, N1>(d, line), sd = line_stride_c<N1>(d);
+      double v[N1];
+#pragma unroll
+      for (int k = 0; k < N1; k++) v[k] = __ldg(xe + base + k * sd);
+      double d0 = 0, d1 = 0, v0 = 0, v1 = 0;
+#pragma unroll
+      for (int k = 0; k < N1; k++) {
+        d0 = fma(c_end_g[N1 - 1][0][k], v[k], d0); d1 = fma(c_end_g[N1 - 1][1][k], v[k], d1);
+        v0 = fma(c_end_t[N1 - 1][0][k], v[k], v0); v1 = fma(c_end_t[N1 - 1][1][k], v[k], v1);
+      }
+      out[(2 * d) * nf + line] = make_double2(d0, v0);
+      out[(2 * d + 1) * nf + line] = make_double2(d1, v1);
+    }
+  }
+}
+template <int DIM>
+__global__ void __launch_bounds__(kTraceThreads) k_face_traces(const __grid_constant__ TraceParams P) {
+  int b = 0;
+  while (b + 1 < P.nb && (long)blockIdx.x >= P.cta_begin[b + 1]) b++;
+  const long cta = blockIdx.x - P.cta_begin[b], eb = P.bucket_ebegin[b], cnt = P.bucket_ebegin[b + 1] - eb;
+  switch (P.bucket_n1[b]) {
+#define HPDG_TR_CASE(NN) case NN: face_traces_body<DIM, NN>(P, eb, cnt, cta); break;
+    HPDG_TR_CASE(1) HPDG_TR_CASE(2) HPDG_TR_CASE(3) HPDG_TR_CASE(4) HPDG_TR_CASE(5) HPDG_TR_CASE(6) HPDG_TR_CASE(7)
+    HPDG_TR_CASE(8) HPDG_TR_CASE(9) HPDG_TR_CASE(10) HPDG_TR_CASE(11) HPDG_TR_CASE(12) HPDG_TR_CASE(13) HPDG_TR_CASE(14)
+#undef HPDG_TR_CASE
+  }
+}
+
+// ---- pass 2: the element kernel ------------------------------------------------------------------------------------------------
+// Per-face metadata of an element (computed once by 2*DIM threads per element, read by all its threads).
+struct FaceInfo {
+  double nuk;    // nu * kappa_d: outward normal sign of the face times prod_{d' != d} h_d' / h_d
+  double cpen;   // sigma * max(p-,p+)^2 (ipdgoperator.hh:129-131) or sigma p^2 on a Dirichlet face (:310)
+  long tro;      // offset (pairs) of the neighbour's traces on the shared face
+  short mode;    // 0 natural boundary: no face term (ipdgoperator.hh:97-105); 1 Dirichlet boundary (weight 1, :357);
+                 // 2 neighbour of the same degree; 3 neighbour of another degree (tangential L2 projection)
+  short po;      // neighbour degree
+  short ghost;   // neighbour lives on another rank: traces from the ghost layer of brick face f
+  short pad;
+};
+static_assert(sizeof(FaceInfo) == 32, "FaceInfo layout");
+
+// 1-D tables of the bucket's degree, passed by value (constant bank)
+template <int N1> struct GenTab { double MinvS[N1 * N1], M[N1 * N1], mt[2][N1], mg[2][N1], g[2][N1]; };
+
+template <int DIM, int N1>
+__global__ void k_apply_generic(const __grid_constant__ GenericParams P, const __grid_constant__ GenTab<N1> T, const int maxno1,
+                                const long cnt, const int epc, const int per_elem, const int mixed) {
   extern __shared__ double sm_all[];
-  constexpr int dim = DIM, nfaces = 2 * DIM;
-  constexpr int pe = N1 - 1, n1 = N1;
+  constexpr int nfaces = 2 * DIM;
+  constexpr int pe = N1 - 1;
   constexpr int ne = CPow<N1, DIM>::v;
-  constexpr int nf = CPow<N1, DIM - 1>::v;   // face nodes == DoF lines per direction
-  const int maxnfo = ipow_d(maxno1, dim - 1);
-  const int maxtmp = n1 * maxno1;
+  constexpr int nf = CPow<N1, DIM - 1>::v;   // face nodes == DoF lines per direction == threads per element
+  const int maxtmp = N1 * maxno1;            // stage-1 projection results per face (3-D)
   const int tid = threadIdx.x, nthr = blockDim.x;
   const long first = (long)blockIdx.x * epc;
   const int nel = (int)min((long)epc, cnt - first);   // elements of this CTA
-  // per-element shared memory: su, sw, alpha, beta, rawD, rawV, tmpA, tmpB, face info
+  // per-element shared memory: su (block), sw (accumulator), face info, stage-1 projections (der / val) of the mixed faces
   auto SU = [&](int el) { return sm_all + (size_t)el * per_elem; };
   auto SW = [&](int el) { return SU(el) + ne; };
-  auto AL = [&](int el) { return SW(el) + ne; };
-  auto BE = [&](int el) { return AL(el) + nfaces * nf; };
-  auto RD = [&](int el) { return BE(el) + nfaces * nf; };
-  auto RV = [&](int el) { return RD(el) + nfaces * maxnfo; };
-  auto TA = [&](int el) { return RV(el) + nfaces * maxnfo; };
-  auto TB = [&](int el) { return TA(el) + nfaces * maxtmp; };
-  auto FI = [&](int el) { return reinterpret_cast<FaceInfo*>(TB(el) + nfaces * maxtmp); };
+  auto FI = [&](int el) { return reinterpret_cast<FaceInfo*>(SW(el) + ne); };
+  auto TD = [&](int el, int f) { return SW(el) + ne + 4 * nfaces + (size_t)(2 * f) * maxtmp; };
+  auto TV = [&](int el, int f) { return TD(el, f) + maxtmp; };
 
-  // ---- phase 0: load the blocks, face metadata ------------------------------------------------------------------
+  // ---- phase 0: load the blocks (coalesced), face metadata -------------------------------------------------------------
   for (int t = tid; t < nel * ne; t += nthr) {
     const int el = t / ne, i = t % ne;
     const long e = P.elist[P.ebegin + first + el];
-    SU(el)[i] = P.x[P.off[e] + i];
+    SU(el)[i] = __ldg(P.x + P.off[e] + i);
   }
   for (int t = tid; t < nel * nfaces; t += nthr) {
     const int el = t / nfaces, f = t % nfaces, d = f / 2, s = f % 2;
@@ -164,181 +177,163 @@ __global__ void k_apply_generic(GenericParams P, GenTab<N1> T, int maxno1, long 
     ijk[0] = (int)(r % P.n[0]); r /= P.n[0]; ijk[1] = (int)(r % P.n[1]); r /= P.n[1]; ijk[2] = (int)r;
     const int c = ijk[d] + (s ? 1 : -1);
     FaceInfo F;
-    F.has_nb = (c >= 0 && c < P.n[d]);
-    F.skip = (!F.has_nb && !P.dirichlet);
     double kappa = 1.0 / P.h[d];
-    for (int dd = 0; dd < dim; dd++) if (dd != d) kappa *= P.h[dd];
-    const double nu = s ? 1.0 : -1.0;
-    F.po = pe; F.uo = 0;
-    double w = 1.0;
-    if (F.has_nb) {
+    for (int dd = 0; dd < DIM; dd++) if (dd != d) kappa *= P.h[dd];
+    F.nuk = s ? kappa : -kappa;
+    F.po = pe; F.tro = 0; F.ghost = 0; F.pad = 0;
+    if (c >= 0 && c < P.n[d]) {
       const long stride = d == 0 ? 1 : d == 1 ? P.n[0] : (long)P.n[0] * P.n[1];
       const long o = e + (s ? stride : -stride);
-      F.po = P.deg[o]; F.uo = P.off[o];
+      F.po = (short)P.deg[o];
+      F.tro = P.troff[o] + (long)(2 * d + (1 - s)) * ipow_d(F.po + 1, DIM - 1);
       const int pm = max(P.pdeg[e], P.pdeg[o]);
-      F.cpen = P.sigma * (double)pm * pm; w = 0.5;
-    } else F.cpen = P.sigma * (double)P.pdeg[e] * P.pdeg[e];
-    F.w_nu_k = w * nu * kappa;
-    F.A1 = -0.5 * nu * kappa; F.A2 = -F.cpen; F.A3 = 0.5 * nu * kappa;
+      F.cpen = P.sigma * (double)pm * pm;
+      F.mode = F.po == pe ? 2 : 3;
+    } else if (P.bnd_is_rank[f]) {
+      // face elements of a brick face are numbered with the lower tangential direction fastest
+      const int ta = d == 0 ? 1 : 0, tb = d == 2 ? 1 : 2;
+      const long fe = ijk[ta] + (long)P.n[ta] * (DIM == 3 ? ijk[tb] : 0);
+      F.ghost = 1;
+      F.po = (short)P.ghost_deg[f][fe]; F.tro = P.ghost_troff[f][fe];
+      const int pm = max(P.pdeg[e], P.ghost_pdeg[f][fe]);
+      F.cpen = P.sigma * (double)pm * pm;
+      F.mode = F.po == pe ? 2 : 3;
+    } else {
+      F.cpen = P.sigma * (double)P.pdeg[e] * P.pdeg[e];
+      F.mode = P.dirichlet ? 1 : 0;
+    }
     FI(el)[f] = F;
   }
   __syncthreads();
 
-  // ---- phase 1: own traces -> alpha/beta, raw neighbour traces; all elements and faces in parallel -----------------
-  for (int t = tid; t < nel * nfaces * nf; t += nthr) {
-    const int el = t / (nfaces * nf), rem = t % (nfaces * nf);
-    const int f = rem / nf, node = rem % nf, d = f / 2, s = f % 2;
-    const FaceInfo& F = FI(el)[f];
-    const double* su = SU(el);
-    double a = 0, b = 0;
-    if (!F.skip) {
-      const int base = line_base(dim, n1, d, node), sd = d == 0 ? 1 : d == 1 ? n1 : n1 * n1;
-      double der = 0, val = 0;
-#pragma unroll
-      for (int k = 0; k < n1; k++) { const double v = su[base + k * sd]; der += T.g[s][k] * v; val += T.t[s][k] * v; }
-      a = -F.w_nu_k * der + F.cpen * val;
-      b = -F.w_nu_k * val;
-    }
-    AL(el)[f * nf + node] = a; BE(el)[f * nf + node] = b;
-  }
-  for (int t = tid; t < nel * nfaces * maxnfo; t += nthr) {
-    const int el = t / (nfaces * maxnfo), rem = t % (nfaces * maxnfo);
-    const int f = rem / maxnfo, node = rem % maxnfo, d = f / 2, s = f % 2;
-    const FaceInfo& F = FI(el)[f];
-    if (!F.has_nb) continue;
-    const int no1 = F.po + 1, nfo = ipow_d(no1, dim - 1);
-    if (node >= nfo) continue;
-    const DegTable& To = P.tab[F.po];
-    const double* uo = P.x + F.uo;
-    const int base = line_base(dim, no1, d, node), sd = ipow_d(no1, d);
-    double der, val;
-    dot2(no1, To.g[1 - s], To.t[1 - s], 1, uo + base, sd, der, val);
-    RD(el)[f * maxnfo + node] = der; RV(el)[f * maxnfo + node] = val;
-  }
-  __syncthreads();
-  // ---- phase 2: same-degree faces add directly; mixed-degree faces: tangential L2 projection ---------------------
-  if constexpr (DIM == 2) {
-    for (int t = tid; t < nel * nfaces * nf; t += nthr) {
-      const int el = t / (nfaces * nf), rem = t % (nfaces * nf), f = rem / nf, i = rem % nf;
-      const FaceInfo& F = FI(el)[f];
-      if (!F.has_nb) continue;
-      const double* rawD = RD(el) + f * maxnfo; const double* rawV = RV(el) + f * maxnfo;
-      double a, b;
-      if (F.po == pe) { a = rawD[i]; b = rawV[i]; }
-      else {
-        const double* Pm = P.P + ((size_t)pe * (kMaxP + 1) + F.po) * kMaxN * kMaxN;
-        a = 0; b = 0;
-        for (int k = 0; k <= F.po; k++) { const double pv = Pm[i * kMaxN + k]; a += pv * rawD[k]; b += pv * rawV[k]; }
-      }
-      AL(el)[f * nf + i] += F.A1 * a + F.A2 * b;
-      BE(el)[f * nf + i] += F.A3 * b;
-    }
-  } else {
-    const int slots = max(nf, maxtmp);
-    for (int t = tid; t < nel * nfaces * slots; t += nthr) {
-      const int el = t / (nfaces * slots), rem = t % (nfaces * slots), f = rem / slots, q = rem % slots;
-      const FaceInfo& F = FI(el)[f];
-      if (!F.has_nb) continue;
-      const double* rawD = RD(el) + f * maxnfo; const double* rawV = RV(el) + f * maxnfo;
-      if (F.po == pe) {
-        if (q < nf) {
-          AL(el)[f * nf + q] += F.A1 * rawD[q] + F.A2 * rawV[q];
-          BE(el)[f * nf + q] += F.A3 * rawV[q];
-        }
-      } else {
+  const int lel = tid / nf, line = tid % nf;       // (element in CTA, DoF line / face node)
+  const bool lact = lel < nel;
+
+  // ---- phase 1 (3-D, mixed-degree faces): stage 1 of the tangential projection, tmp[i + N1 b] = sum_a P[i][a] raw[a + No b] ----
+  if (DIM == 3 && mixed) {
+    if (lact) {
+#pragma unroll 1
+      for (int f = 0; f < nfaces; f++) {
+        const FaceInfo F = FI(lel)[f];
+        if (F.mode != 3) continue;
         const int no1 = F.po + 1;
-        if (q < n1 * no1) {  // tmp[i + n1*b] = sum_a P[i,a] raw[a + no1*b]
-          const double* Pm = P.P + ((size_t)pe * (kMaxP + 1) + F.po) * kMaxN * kMaxN;
-          const int i = q % n1, b = q / n1;
-          double a0, a1;
-          dotp(no1, Pm + i * kMaxN, rawD + no1 * b, rawV + no1 * b, 1, a0, a1);
-          TA(el)[f * maxtmp + q] = a0; TB(el)[f * maxtmp + q] = a1;
+        const double* __restrict__ Pm = P.P + ((size_t)pe * (kMaxP + 1) + F.po) * kMaxN * kMaxN;
+        const double2* __restrict__ raw = (F.ghost ? P.ghost_tr[f] : P.tr) + F.tro;
+        double* __restrict__ td = TD(lel, f); double* __restrict__ tv = TV(lel, f);
+        for (int q = line; q < N1 * no1; q += nf) {
+          const int i = q % N1, b = q / N1;
+          double a0 = 0, a1 = 0;
+          for (int a = 0; a < no1; a++) {
+            const double pv = __ldg(Pm + i * kMaxN + a);
+            const double2 rv = F.ghost ? __ldcg(raw + a + no1 * b) : __ldg(raw + a + no1 * b);
+            a0 = fma(pv, rv.x, a0); a1 = fma(pv, rv.y, a1);
+          }
+          td[q] = a0; tv[q] = a1;
         }
       }
     }
     __syncthreads();
-    for (int t = tid; t < nel * nfaces * nf; t += nthr) {
-      const int el = t / (nfaces * nf), rem = t % (nfaces * nf), f = rem / nf, q = rem % nf;
-      const FaceInfo& F = FI(el)[f];
-      if (!F.has_nb || F.po == pe) continue;
-      const int no1 = F.po + 1;
-      const double* Pm = P.P + ((size_t)pe * (kMaxP + 1) + F.po) * kMaxN * kMaxN;
-      const int i = q % n1, j = q / n1;
-      double a0, a1;
-      dotp(no1, Pm + j * kMaxN, TA(el) + f * maxtmp + i, TB(el) + f * maxtmp + i, n1, a0, a1);
-      AL(el)[f * nf + q] += F.A1 * a0 + F.A2 * a1;
-      BE(el)[f * nf + q] += F.A3 * a1;
-    }
   }
-  __syncthreads();
 
-  // ---- line passes ------------------------------------------------------------------------------------------------
-  double kap[3] = {1, 1, 1};
+  // ---- line passes: X: w = T~_x u   Y: w += T~_y u   Z: w += T~_z u, w = M_z w   then M_y, then M_x -> global ---------------
 #pragma unroll
-  for (int d = 0; d < dim; d++) {
-    double k = 1.0 / P.h[d];
-    for (int dd = 0; dd < dim; dd++) if (dd != d) k *= P.h[dd];
-    kap[d] = k;
-  }
-  const int lel = tid / nf, line = tid % nf;       // (element in CTA, line)
-  const bool lact = lel < nel;
-  // base offset and stride of line `line` along direction d (x-fastest local index)
-  auto lbase = [&](int d) { return d == 0 ? n1 * line : (DIM == 2 ? line : (d == 1 ? (line % n1) + n1 * n1 * (line / n1) : line)); };
-  auto lstride = [&](int d) { return d == 0 ? 1 : (d == 1 ? n1 : n1 * n1); };
-#pragma unroll
-  for (int d = 0; d < dim; d++) {
+  for (int d = 0; d < DIM; d++) {
     if (lact) {
       const double* su = SU(lel); double* sw = SW(lel);
-      const int base = lbase(d), sd = lstride(d);
+      const int base = line_base_c<DIM, N1>(d, line), sd = line_stride_c<N1>(d);
       double v[N1], w[N1];
 #pragma unroll
-      for (int k = 0; k < n1; k++) v[k] = su[base + k * sd];
-      const double a0 = AL(lel)[(2 * d) * nf + line], b0 = BE(lel)[(2 * d) * nf + line];
-      const double a1 = AL(lel)[(2 * d + 1) * nf + line], b1 = BE(lel)[(2 * d + 1) * nf + line];
+      for (int k = 0; k < N1; k++) v[k] = su[base + k * sd];
+      double al[2], be[2];
 #pragma unroll
-      for (int i = 0; i < n1; i++) {
+      for (int s = 0; s < 2; s++) {
+        const int f = 2 * d + s;
+        const FaceInfo F = FI(lel)[f];
+        double a = 0, b = 0;
+        if (F.mode != 0) {
+          double der = 0;
+#pragma unroll
+          for (int k = 0; k < N1; k++) der = fma(T.g[s][k], v[k], der);
+          const double val = v[s ? N1 - 1 : 0];   // GL nodes include the end points (p = 0: the constant)
+          const double wnk = (F.mode == 1 ? 1.0 : 0.5) * F.nuk;
+          a = fma(-wnk, der, F.cpen * val);
+          b = -wnk * val;
+          if (F.mode >= 2) {
+            double nd, nv;
+            const double2* __restrict__ raw = (F.ghost ? P.ghost_tr[f] : P.tr) + F.tro;
+            if (F.mode == 2) {
+              const double2 rv = F.ghost ? __ldcg(raw + line) : __ldg(raw + line);
+              nd = rv.x; nv = rv.y;
+            } else {
+              const int no1 = F.po + 1;
+              const double* __restrict__ Pm = P.P + ((size_t)pe * (kMaxP + 1) + F.po) * kMaxN * kMaxN;
+              nd = 0; nv = 0;
+              if (DIM == 2) {
+                for (int a2 = 0; a2 < no1; a2++) {
+                  const double pv = __ldg(Pm + line * kMaxN + a2);
+                  const double2 rv = F.ghost ? __ldcg(raw + a2) : __ldg(raw + a2);
+                  nd = fma(pv, rv.x, nd); nv = fma(pv, rv.y, nv);
+                }
+              } else {
+                const int i = line % N1, j = line / N1;
+                const double* __restrict__ td = TD(lel, f); const double* __restrict__ tv = TV(lel, f);
+                for (int b2 = 0; b2 < no1; b2++) {
+                  const double pv = __ldg(Pm + j * kMaxN + b2);
+                  nd = fma(pv, td[i + N1 * b2], nd); nv = fma(pv, tv[i + N1 * b2], nv);
+                }
+              }
+            }
+            a = fma(-0.5 * F.nuk, nd, a); a = fma(-F.cpen, nv, a);
+            b = fma(0.5 * F.nuk, nv, b);
+          }
+        }
+        al[s] = a; be[s] = b;
+      }
+      double kap = 1.0 / P.h[d];
+#pragma unroll
+      for (int dd = 0; dd < DIM; dd++) if (dd != d) kap *= P.h[dd];
+#pragma unroll
+      for (int i = 0; i < N1; i++) {
         double s = 0;
 #pragma unroll
-        for (int k = 0; k < n1; k++) s = fma(T.MinvS[i * n1 + k], v[k], s);
-        s *= kap[d];
-        s = fma(T.mt[0][i], a0, s); s = fma(T.mg[0][i], b0, s);
-        s = fma(T.mt[1][i], a1, s); s = fma(T.mg[1][i], b1, s);
+        for (int k = 0; k < N1; k++) s = fma(T.MinvS[i * N1 + k], v[k], s);
+        s *= kap;
+        s = fma(T.mt[0][i], al[0], s); s = fma(T.mg[0][i], be[0], s);
+        s = fma(T.mt[1][i], al[1], s); s = fma(T.mg[1][i], be[1], s);
         w[i] = (d == 0) ? s : s + sw[base + i * sd];
       }
-      if (d == dim - 1) {  // last direction: its mass sweep acts on the same line
+      if (d == DIM - 1) {  // last direction: its mass sweep acts on the same line
         double o[N1];
 #pragma unroll
-        for (int i = 0; i < n1; i++) {
+        for (int i = 0; i < N1; i++) {
           double s = 0;
 #pragma unroll
-          for (int k = 0; k < n1; k++) s = fma(T.M[i * n1 + k], w[k], s);
+          for (int k = 0; k < N1; k++) s = fma(T.M[i * N1 + k], w[k], s);
           o[i] = s;
         }
 #pragma unroll
-        for (int i = 0; i < n1; i++) w[i] = o[i];
+        for (int i = 0; i < N1; i++) w[i] = o[i];
       }
-      if (dim == 1) { /* unreachable */ }
 #pragma unroll
-      for (int i = 0; i < n1; i++) sw[base + i * sd] = w[i];
+      for (int i = 0; i < N1; i++) sw[base + i * sd] = w[i];
     }
     __syncthreads();
   }
-  // remaining mass sweeps, directions dim-2 .. 0; the last one (x lines, contiguous) writes to global
+  // remaining mass sweeps, directions DIM-2 .. 0; the last one (x lines, contiguous) writes to global
 #pragma unroll
-  for (int d = dim - 2; d >= 0; d--) {
+  for (int d = DIM - 2; d >= 0; d--) {
     if (lact) {
       double* sw = SW(lel);
-      const int base = lbase(d), sd = lstride(d);
+      const int base = line_base_c<DIM, N1>(d, line), sd = line_stride_c<N1>(d);
       double w[N1];
 #pragma unroll
-      for (int k = 0; k < n1; k++) w[k] = sw[base + k * sd];
-      const long e = P.elist[P.ebegin + first + lel];
-      double* yo = P.y + P.off[e];
+      for (int k = 0; k < N1; k++) w[k] = sw[base + k * sd];
+      double* yo = d == 0 ? P.y + P.off[P.elist[P.ebegin + first + lel]] : nullptr;
 #pragma unroll
-      for (int i = 0; i < n1; i++) {
+      for (int i = 0; i < N1; i++) {
         double s = 0;
 #pragma unroll
-        for (int k = 0; k < n1; k++) s = fma(T.M[i * n1 + k], w[k], s);
+        for (int k = 0; k < N1; k++) s = fma(T.M[i * N1 + k], w[k], s);
         if (d == 0) yo[base + i] = P.accum ? yo[base + i] + P.factor * s : P.factor * s;
         else sw[base + i * sd] = s;
       }
@@ -347,14 +342,100 @@ __global__ void k_apply_generic(GenericParams P, GenTab<N1> T, int maxno1, long 
   }
 }
 
+// the level's trace array (allocated on first use) and the offsets of every element's traces
+int generic_trace_setup(Ctx* ctx, Level& L) {
+  if (L.d_troff) return 0;
+  std::vector<long> troff(L.nelem + 1, 0);
+  for (long e = 0; e < L.nelem; e++) troff[e + 1] = troff[e] + 2 * L.dim * ipow_d(L.deg[e] + 1, L.dim - 1);
+  L.tr_pairs = troff[L.nelem];
+  HPDG_CUDA(cudaMalloc(&L.d_troff, sizeof(long) * (L.nelem + 1)));
+  HPDG_CUDA(cudaMemcpy(L.d_troff, troff.data(), sizeof(long) * (L.nelem + 1), cudaMemcpyHostToDevice));
+  HPDG_CUDA(cudaMalloc(&L.d_tr, sizeof(double) * 2 * std::max<long>(L.tr_pairs, 1)));
+  if (!ctx->end_tables_set) {  // once per context (= device): the end-point tables of all degrees in constant memory
+    static thread_local double g[kMaxN][2][kMaxN], t[kMaxN][2][kMaxN];
+    for (int p = 0; p <= kMaxP; p++) for (int s = 0; s < 2; s++) for (int k = 0; k < kMaxN; k++) {
+      g[p][s][k] = k <= p ? host_tables().deg[p].g[s][k] : 0.0; t[p][s][k] = k <= p ? host_tables().deg[p].t[s][k] : 0.0;
+    }
+    HPDG_CUDA(cudaMemcpyToSymbol(c_end_g, g, sizeof(g)));
+    HPDG_CUDA(cudaMemcpyToSymbol(c_end_t, t, sizeof(t)));
+    ctx->end_tables_set = true;
+  }
+  return 0;
+}
+
+// pass 1 of the hp apply (also the first step of the distributed hp halo): own face traces of every element of the level
+int launch_face_traces(Ctx* ctx, Level& L, const double* x, cudaStream_t stream) {
+  if (generic_trace_setup(ctx, L)) return 1;
+  static thread_local TraceParams TP;
+  TP.nb = (int)L.bucket_p.size();
+  long ctas = 0;
+  for (int b = 0; b < TP.nb; b++) {
+    const int n1 = L.bucket_p[b] + 1, nf = ipow_d(n1, L.dim - 1);
+    const int epc = nf >= kTraceThreads ? 1 : kTraceThreads / nf;
+    TP.bucket_n1[b] = n1; TP.bucket_ebegin[b] = L.bucket_begin[b]; TP.cta_begin[b] = ctas;
+    ctas += (L.bucket_begin[b + 1] - L.bucket_begin[b] + epc - 1) / epc;
+  }
+  TP.bucket_ebegin[TP.nb] = L.bucket_begin[TP.nb]; TP.cta_begin[TP.nb] = ctas;
+  TP.elist = L.d_elist; TP.off = L.d_off; TP.troff = L.d_troff; TP.x = x; TP.tr = reinterpret_cast<double2*>(L.d_tr);
+  if (ctas == 0) return 0;
+  if (L.dim == 2) k_face_traces<2><<<(unsigned)ctas, kTraceThreads, 0, stream>>>(TP);
+  else k_face_traces<3><<<(unsigned)ctas, kTraceThreads, 0, stream>>>(TP);
+  ctx->launches++;
+  HPDG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// distributed hp: gather the face-f traces of this rank's boundary elements into the contiguous send buffer of brick face f
+struct HpPackParams { const double2* tr; double2* send[6]; const long* src[6]; const long* dst[6]; long nface[6]; };
+__global__ void k_hp_pack(const __grid_constant__ HpPackParams P) {
+  const int f = blockIdx.y;
+  if (!P.send[f]) return;
+  const int lane = threadIdx.x & 31;
+  const long warp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = (long)gridDim.x * (blockDim.x >> 5);
+  for (long fe = warp; fe < P.nface[f]; fe += nw) {
+    const long s0 = P.src[f][fe], d0 = P.dst[f][fe], n = P.dst[f][fe + 1] - d0;
+    for (long i = lane; i < n; i += 32) P.send[f][d0 + i] = P.tr[s0 + i];
+  }
+}
+int launch_hp_pack(Ctx* ctx, Level& L, cudaStream_t stream) {
+  HpPackParams PK;
+  long mx = 0;
+  for (int f = 0; f < 6; f++) {
+    PK.send[f] = reinterpret_cast<double2*>(L.hpg.d_send[f]); PK.src[f] = L.hpg.d_send_src[f]; PK.dst[f] = L.hpg.d_send_dst[f];
+    PK.nface[f] = L.hpg.nface[f];
+    if (PK.send[f]) mx = std::max(mx, PK.nface[f]);
+  }
+  PK.tr = reinterpret_cast<const double2*>(L.d_tr);
+  if (mx == 0) return 0;
+  k_hp_pack<<<dim3((unsigned)std::min<long>((mx + 7) / 8, 1024), 6), 256, 0, stream>>>(PK);
+  ctx->launches++;
+  HPDG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double factor) {
-  GenericParams P;
+  static thread_local GenericParams P;
   P.dim = L.dim;
   for (int d = 0; d < 3; d++) { P.n[d] = L.n[d]; P.h[d] = L.h[d]; }
   P.sigma = ctx->sigma; P.dirichlet = ctx->dirichlet;
   P.deg = L.d_deg; P.pdeg = L.d_pdeg; P.off = L.d_off; P.elist = L.d_elist;
   P.tab = ctx->d_tab; P.P = ctx->d_P; P.x = x; P.y = y; P.factor = factor; P.accum = ctx->fuse_accum;
-  // the degree buckets write disjoint rows of y: launch them on side streams so that small buckets overlap the large ones
+  // ---- pass 1: every element's own face traces (one launch); distributed hp: exchange the rank-boundary traces ----
+  if (launch_face_traces(ctx, L, x, ctx->stream)) return 1;
+  P.troff = L.d_troff; P.tr = reinterpret_cast<const double2*>(L.d_tr);
+  int maxno1 = L.maxp + 1;
+  for (int f = 0; f < 6; f++) { P.bnd_is_rank[f] = 0; P.ghost_deg[f] = P.ghost_pdeg[f] = nullptr; P.ghost_troff[f] = nullptr; P.ghost_tr[f] = nullptr; }
+  if (ctx->nranks > 1) {
+    if (hp_halo_exchange(ctx, L)) return 1;
+    for (int f = 0; f < 6; f++) {
+      if (!ctx->bnd_is_rank[f]) continue;
+      P.bnd_is_rank[f] = 1; P.ghost_deg[f] = L.hpg.d_deg[f]; P.ghost_pdeg[f] = L.hpg.d_pdeg[f]; P.ghost_troff[f] = L.hpg.d_troff[f];
+      P.ghost_tr[f] = reinterpret_cast<const double2*>(L.hpg.d_recv[f]);
+    }
+    maxno1 = std::max(maxno1, L.hpg.maxp + 1);
+  }
+  const int mixed = (!L.uniform || ctx->nranks > 1) ? 1 : 0;
+  // ---- pass 2: the degree buckets write disjoint rows of y: side streams, so that small buckets overlap the large ones ----
   const size_t nb = L.bucket_p.size();
   const bool fork = nb > 1;
   if (fork) {
@@ -365,39 +446,39 @@ int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double 
     HPDG_CUDA(cudaEventRecord(ctx->bucket_ev[4], ctx->stream));
     for (int k = 0; k < 4; k++) HPDG_CUDA(cudaStreamWaitEvent(ctx->bucket_stream[k], ctx->bucket_ev[4], 0));
   }
-  for (size_t b = 0; b < nb; b++) {
+  // largest buckets first (they determine the critical path)
+  std::vector<size_t> order(nb);
+  for (size_t b = 0; b < nb; b++) order[b] = b;
+  auto work = [&](size_t k) { return (double)(L.bucket_begin[k + 1] - L.bucket_begin[k]) * ipow_d(L.bucket_p[k] + 1, L.dim + 1); };
+  std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return work(a) > work(b); });
+  for (size_t bi = 0; bi < nb; bi++) {
+    const size_t b = order[bi];
     long cnt = L.bucket_begin[b + 1] - L.bucket_begin[b];
     if (cnt == 0) continue;
-    cudaStream_t lstream = fork ? ctx->bucket_stream[b % 4] : ctx->stream;
-    int p = L.bucket_p[b], n1 = p + 1;
-    int ne = 1, nf = 1;
-    for (int d = 0; d < L.dim; d++) ne *= n1;
-    for (int d = 0; d < L.dim - 1; d++) nf *= n1;
-    const int maxno1 = L.maxp + 1;
-    int maxnfo = 1;
-    for (int d = 0; d < L.dim - 1; d++) maxnfo *= maxno1;
+    cudaStream_t lstream = fork ? ctx->bucket_stream[bi % 4] : ctx->stream;
+    const int p = L.bucket_p[b], n1 = p + 1;
+    const int ne = ipow_d(n1, L.dim), nf = ipow_d(n1, L.dim - 1);
     const int nfaces = 2 * L.dim;
-    const int per_elem = 2 * ne + 2 * nfaces * nf + 2 * nfaces * maxnfo + 2 * nfaces * n1 * maxno1 +
-                         (int)((nfaces * sizeof(FaceInfo) + 7) / 8);
+    const int per_elem = 2 * ne + 4 * nfaces + ((mixed && L.dim == 3) ? 2 * nfaces * n1 * maxno1 : 0);
     P.ebegin = L.bucket_begin[b];
-    // elements per CTA: aim at ~128 line threads, bounded by 96 KB of shared memory
-    int epc = nf >= 64 ? 1 : (L.uniform ? 128 / nf : std::max(1, 64 / nf));  // mixed-degree meshes: face work dominates, fewer elements per CTA
-    epc = (int)std::max<long>(1, std::min<long>(epc, (96 * 1024) / ((long)per_elem * 8)));
+    // elements per CTA: ~128 line threads, at most 48 KB of shared memory
+    int epc = nf >= 128 ? 1 : 128 / nf;
+    epc = (int)std::max<long>(1, std::min<long>(epc, (48 * 1024) / ((long)per_elem * 8)));
     epc = (int)std::min<long>(epc, cnt);
     const size_t smem_l = (size_t)epc * per_elem * sizeof(double);
     const unsigned grid = (unsigned)((cnt + epc - 1) / epc);
-    const int threads = std::max(L.uniform ? 128 : 256, (epc * nf + 31) / 32 * 32);  // line passes use epc*nf threads, the face phases all of them
+    const int threads = std::max(32, (epc * nf + 31) / 32 * 32);
     const DegTable& HT = host_tables().deg[p];
 #define HPDG_GEN_LAUNCH(D, NN)                                                                                            \
   do {                                                                                                                    \
-    GenTab<NN> T;                                                                                                         \
+    static thread_local GenTab<NN> T;                                                                                     \
     for (int i = 0; i < NN; i++) {                                                                                        \
       for (int j = 0; j < NN; j++) { T.MinvS[i * NN + j] = HT.MinvS[i * kMaxN + j]; T.M[i * NN + j] = HT.M[i * kMaxN + j]; } \
-      for (int sd = 0; sd < 2; sd++) { T.mt[sd][i] = HT.mt[sd][i]; T.mg[sd][i] = HT.mg[sd][i]; T.g[sd][i] = HT.g[sd][i]; T.t[sd][i] = HT.t[sd][i]; } \
+      for (int sd = 0; sd < 2; sd++) { T.mt[sd][i] = HT.mt[sd][i]; T.mg[sd][i] = HT.mg[sd][i]; T.g[sd][i] = HT.g[sd][i]; } \
     }                                                                                                                     \
-    if (smem_l + 1024 > 48 * 1024)                                                                                        \
+    if (smem_l > 48 * 1024)                                                                                               \
       HPDG_CUDA(cudaFuncSetAttribute(k_apply_generic<D, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));  \
-    k_apply_generic<D, NN><<<grid, threads, smem_l, lstream>>>(P, T, maxno1, cnt, epc, per_elem);                     \
+    k_apply_generic<D, NN><<<grid, threads, smem_l, lstream>>>(P, T, maxno1, cnt, epc, per_elem, mixed);                  \
   } while (0)
 #define HPDG_GEN_CASE(NN)                                                      \
   case NN:                                                                     \

@@ -35,6 +35,24 @@ struct Ghost {
   int step = 0;
 };
 
+// Distributed hp: ghost layer of one level.  The degrees of the remote elements across every rank-boundary face are exchanged once
+// (the analogue of parallel/updatedegrees.hh:11-46); their face traces -- variable-size blocks per element, like the reference's
+// ghost copy (parallel/communicationhpdg.hh:309-326,387-418), but N^(dim-1) (der, val) pairs instead of whole blocks -- per apply.
+struct HpGhost {
+  bool ready = false;
+  int maxp = 0;                  // largest ghost degree
+  long nface[6] = {};            // face elements of brick face f
+  int* d_deg[6] = {};            // [nface] degree of the remote element on this level
+  int* d_pdeg[6] = {};           // [nface] its degree on the finest level (enters the face penalty on Galerkin coarse levels)
+  long* d_troff[6] = {};         // [nface] offset (pairs) of the remote element's traces in d_recv[f]
+  double* d_recv[6] = {};        // received traces (pairs)
+  double* d_send[6] = {};        // packed traces of this rank's boundary elements on face f
+  long* d_send_src[6] = {};      // [nface] offset (pairs) of the element's face-f traces in the level's trace array
+  long* d_send_dst[6] = {};      // [nface + 1] offsets (pairs) in d_send[f]
+  long send_pairs[6] = {}, recv_pairs[6] = {};
+  std::vector<int> h_deg[6], h_pdeg[6];   // host copies of the ghost degrees (block-Jacobi setup)
+};
+
 struct JacobiDense {
   bool ready = false;
   double* d_inv = nullptr;      // all inverses, bucket by bucket, element-major inside a bucket
@@ -78,6 +96,12 @@ struct Level {
   std::vector<long> bucket_begin;  // size buckets+1
   int* d_elist = nullptr;
   int maxp = 0;
+  int cap = -1;   // p-hierarchy: degree cap of this level (-1: finest level, no cap)
+  HpGhost hpg;    // distributed hp: ghost degrees / trace buffers of this level
+  // hp apply: face traces (der, val) of every element, written once per apply by k_face_traces (apply_generic.cu)
+  long* d_troff = nullptr;      // [nelem+1] offset (in pairs) of an element's traces; face f at troff[e] + f * N_e^(dim-1)
+  double* d_tr = nullptr;       // [2 * tr_pairs]
+  long tr_pairs = 0;
   JacobiDense jd;
   JacobiFD jf;
   Bcrs bcrs;
@@ -110,6 +134,7 @@ struct Ctx {
   std::string err;
   // distributed brick
   int rank = 0, nranks = 1;
+  bool hp_distributed = false;   // created with a per-element degree array: every level takes the generic hp path
   int pgrid[3] = {1, 1, 1}, pcoord[3] = {0, 0, 0};
   bool bnd_is_rank[6] = {false, false, false, false, false, false};
   Ghost ghost;           // finest level only
@@ -137,6 +162,7 @@ struct Ctx {
   int* d_ghost_err = nullptr;          // its device alias
   long long halo_timeout_cycles = 40000000000LL;  // ~20 s of SM clock; option "halo_timeout_ms"
   double *cg_p = nullptr, *cg_q = nullptr, *cg_r = nullptr, *cg_z = nullptr;  // work vectors of the solver loops (finest level)
+  bool end_tables_set = false;  // apply_generic.cu: end-point tables of all degrees copied to this device's constant memory
   long launches = 0;  // kernels launched by this context (bench.py's gpu_launches)
 };
 
@@ -151,6 +177,11 @@ struct Ctx {
 
 // ---- kernel launchers (defined in the .cu files) -----------------------------------------------
 int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double factor);
+int launch_face_traces(Ctx* ctx, Level& L, const double* x, cudaStream_t stream);  // every element's own face traces -> L.d_tr
+int launch_hp_pack(Ctx* ctx, Level& L, cudaStream_t stream);   // rank-boundary traces of L.d_tr -> L.hpg.d_send[f]
+int generic_trace_setup(Ctx* ctx, Level& L);                   // allocates L.d_troff / L.d_tr on first use
+int hp_ghost_setup(Ctx* ctx, Level& L);                        // (api.cu) one-time exchange of the neighbour degrees across rank boundaries
+int hp_halo_exchange(Ctx* ctx, Level& L);                      // (api.cu) pack + NCCL send/recv of the rank-boundary face traces
 // returns -1 if (dim, degree) has no specialised kernel
 int launch_apply_uniform(Ctx* ctx, Level& L, const double* x, double* y, double factor, int part, cudaStream_t stream = nullptr);
 int uniform_supported(const Ctx* ctx, const Level& L);

@@ -318,6 +318,7 @@ int jacobi_setup_fd(Ctx* ctx, Level& L) {
 
 static int jacobi_build_fd_generic(Ctx* ctx, Level& L) {
   if (L.jf.d_fac) return 0;
+  if (ctx->hp_distributed && ctx->nranks > 1 && hp_ghost_setup(ctx, L)) return 1;   // neighbour degrees across rank boundaries
   const HostTables& H = host_tables();
   typedef std::tuple<int, int, long long, long long, int, int> Key;  // dir-kappa id, p, c0, c1 (bits), w0, w1 (x2)
   std::map<Key, int> seen;
@@ -338,7 +339,16 @@ static int jacobi_build_fd_generic(Ctx* ctx, Level& L) {
           long o = e + (s ? stride : -stride);
           int pm = std::max(L.pdeg[e], L.pdeg[o]);
           w[s] = 0.5; c[s] = ctx->sigma * (double)pm * pm;
-        } else if (ctx->bnd_is_rank[2 * d + s]) { w[s] = 0.5; c[s] = ctx->sigma * (double)L.pdeg[e] * L.pdeg[e]; }
+        } else if (ctx->bnd_is_rank[2 * d + s]) {
+          // rank boundary = interior face; the neighbour's degree comes from the ghost layer on hp bricks
+          int pm = L.pdeg[e];
+          if (ctx->hp_distributed) {
+            const int f = 2 * d + s, ta = d == 0 ? 1 : 0, tb = d == 2 ? 1 : 2;
+            const long fe = ijk[ta] + (long)L.n[ta] * (L.dim == 3 ? ijk[tb] : 0);
+            pm = std::max(pm, L.hpg.h_pdeg[f][fe]);
+          }
+          w[s] = 0.5; c[s] = ctx->sigma * (double)pm * pm;
+        }
         else if (ctx->dirichlet) { w[s] = 1.0; c[s] = ctx->sigma * (double)L.pdeg[e] * L.pdeg[e]; }
         else { w[s] = 0.0; c[s] = 0.0; }
       }

@@ -10,7 +10,7 @@ namespace {
 typedef long double ld;
 constexpr int kQ = 20;  // Gauss points: exact to degree 39
 
-// Node and quadrature generation.  Deliberately NOT the Newton-on-Legendre code of the test oracle (oracle/hpdg_oracle.c):
+// Node and quadrature generation.  Deliberately NOT the Newton-on-Legendre iteration the CPU test oracle uses:
 // nodes and weights come from the eigen-decomposition of the Jacobi matrices of the orthogonal polynomials (Golub-Welsch), the
 // Lagrange basis is evaluated in barycentric form.  A mistake in either generator then shows up as a product/oracle mismatch.
 

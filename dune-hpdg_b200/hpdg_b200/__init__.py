@@ -35,6 +35,8 @@ SIGNATURES = {
     "hpdg_create": (C.c_int, [C.POINTER(_vp), C.c_int, _ip, _dp, _ip, C.c_long, C.c_double, C.c_int, C.c_int]),
     "hpdg_create_distributed": (C.c_int, [C.POINTER(_vp), C.c_int, _ip, _dp, C.c_int, C.c_double, C.c_int, C.c_int,
                                           _ip, C.c_int, C.c_int, C.c_void_p]),
+    "hpdg_create_distributed_hp": (C.c_int, [C.POINTER(_vp), C.c_int, _ip, _dp, _ip, C.c_double, C.c_int, C.c_int,
+                                             _ip, C.c_int, C.c_int, C.c_void_p]),
     "hpdg_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "hpdg_halo_ipc_handle": (C.c_int, [_vp, C.c_void_p]),
     "hpdg_halo_ipc_attach": (C.c_int, [_vp, C.c_void_p]),
@@ -153,8 +155,12 @@ class Context:
         else:
             pg = np.ascontiguousarray(pgrid, dtype=np.int32)
             idp = C.c_char_p(nccl_id) if nccl_id is not None else None
-            rc = lib().hpdg_create_distributed(C.byref(self._h), self.dim, n, L, int(deg[0]), sigma, int(dirichlet),
-                                               device, pg, rank, nranks, idp)
+            if deg.size == 1:
+                rc = lib().hpdg_create_distributed(C.byref(self._h), self.dim, n, L, int(deg[0]), sigma, int(dirichlet),
+                                                   device, pg, rank, nranks, idp)
+            else:  # per-element degree map of the local brick: distributed hp
+                rc = lib().hpdg_create_distributed_hp(C.byref(self._h), self.dim, n, L, deg, sigma, int(dirichlet),
+                                                      device, pg, rank, nranks, idp)
         if rc:
             msg = lib().hpdg_last_error(None).decode()
             self._h = None

@@ -54,6 +54,12 @@ def scatter_global_vector(xg, rank, pgrid, n, ndof_per_elem):
     return np.ascontiguousarray(xg.reshape(-1, ndof_per_elem)[g].reshape(-1))
 
 
+def scatter_global_blocks(xg, offsets, gl):
+    """rank-local DynamicBlockVector slice of a global vector with per-element block sizes (hp): `offsets` are the global
+    block offsets, `gl` the global indices of the rank's elements in local order"""
+    return np.ascontiguousarray(np.concatenate([xg[offsets[g]:offsets[g + 1]] for g in gl]))
+
+
 def face_traces(x_local, n, p, f, g_end):
     """(der, val) traces the rank SENDS across brick face f = 2*dir+side, in the layout the receiving kernel expects:
     [face element (lower tangential direction fastest)][face node (lower fastest)][2].

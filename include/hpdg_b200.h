@@ -50,6 +50,12 @@ int hpdg_create(hpdg_ctx** out, int dim, const int* n, const double* L, const in
 int hpdg_create_distributed(hpdg_ctx** out, int dim, const int* n, const double* L, int degree, double sigma,
                             int dirichlet, int device, const int* pgrid, int rank, int nranks,
                             const void* nccl_id);
+/* The same with a per-element degree map of the LOCAL brick (x-fastest element order): the hp mesh partitioned element-wise over the
+ * ranks.  The degrees of the elements across every rank-boundary face are exchanged once (parallel/updatedegrees.hh:11-46); per
+ * apply the rank-boundary face traces -- variable-size blocks per element, cf. parallel/communicationhpdg.hh:309-326,387-418 --
+ * travel by one grouped ncclSend/ncclRecv.  nccl_id must not be NULL when nranks > 1. */
+int hpdg_create_distributed_hp(hpdg_ctx** out, int dim, const int* n, const double* L, const int* degree, double sigma,
+                               int dirichlet, int device, const int* pgrid, int rank, int nranks, const void* nccl_id);
 int hpdg_nccl_unique_id(void* out128);
 /* Optional NVLink peer-memory halo (one process per GPU, same node): every rank exports the 64-byte cudaIpcMemHandle_t of its
  * halo arena, the caller all-gathers them (indexed by rank) and every rank attaches.  After that the operator apply stores the

@@ -79,6 +79,40 @@ for p, n in [(3, (8, 8, 8)), (3, (6, 5, 7)), (4, (4, 6, 4)), (1, (8, 4, 4)), (2,
     ok &= good
     print(f"rank {rank}/{world} p={p} brick={n}: halo={'p2p' if p2p else 'nccl'} apply {err:.2e} twice {err2:.2e} dot {derr:.2e} jacobi {jerr:.2e} vcycle {verr:.2e} {'OK' if good else 'FAIL'}", flush=True)
     ctx.close()
+# ---- distributed hp: the hp mesh partitioned element-wise over the ranks (per-element degree map, variable-size halo blocks) ----
+for n, pmax, dirichlet in [((4, 3, 5), 4, True), ((6, 6, 4), 6, False), ((3, 4, 4), 3, True)]:
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        buf = ctypes.create_string_buffer(128)
+        assert hp.lib().hpdg_nccl_unique_id(buf) == 0
+        idt = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
+    dist.broadcast(idt, 0)
+    N = [n[d] * pgrid[d] for d in range(3)]
+    degg = np.random.default_rng(7).integers(1, pmax + 1, int(np.prod(N))).astype(np.int32)   # same on every rank
+    m = orc.Mesh(N, L=[float(pgrid[d]) for d in range(3)], degree=degg, sigma=2.0, dirichlet=dirichlet)
+    xg = orc.fill_random(m.ndof)
+    ref = m.apply_mf(xg, threads=orc.max_threads())
+    ref2 = m.apply_mf(ref, threads=orc.max_threads())
+    jref = m.blockjacobi_apply(xg, factor=0.75)
+    gl = part.local_to_global_elements(rank, pgrid, n)
+    sc = lambda v: part.scatter_global_blocks(v, m.offsets, gl)
+    ctx = hp.Context(n, L=[1.0, 1.0, 1.0], degree=degg[gl], sigma=2.0, dirichlet=dirichlet, device=lr, pgrid=pgrid, rank=rank,
+                     nranks=world, nccl_id=bytes(idt.cpu().tolist()))
+    dx, dy = ctx.upload(sc(xg)), ctx.vec_alloc()
+    op = hp.Operator(ctx)
+    op.apply_device(dx, dy)
+    e1 = np.linalg.norm(ctx.download(dy) - sc(ref)) / np.linalg.norm(sc(ref))
+    op.apply_device(dy, dx)
+    e2 = np.linalg.norm(ctx.download(dx) - sc(ref2)) / np.linalg.norm(sc(ref2))
+    ctx.upload(sc(xg), dx)
+    derr = abs(ctx.dot_device(dx, dx) - xg @ xg) / (xg @ xg)
+    jac = hp.BlockJacobi(ctx, form=hp.JACOBI_FD, damping=0.75)
+    jac.apply_device(dx, dy)
+    jerr = np.linalg.norm(ctx.download(dy) - sc(jref)) / np.linalg.norm(sc(jref))
+    good = e1 < 1e-12 and e2 < 1e-12 and derr < 1e-12 and jerr < 1e-11
+    ok &= good
+    print(f"rank {rank}/{world} hp p=1..{pmax} brick={n} dirichlet={dirichlet}: apply {e1:.2e} twice {e2:.2e} dot {derr:.2e} jacobi {jerr:.2e} {'OK' if good else 'FAIL'}", flush=True)
+    ctx.close()
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()

@@ -1,5 +1,5 @@
 import sys
-sys.path.insert(0, '/root/repo/dune-hpdg_b200')
+import os; sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'dune-hpdg_b200'))
 import numpy as np, hpdg_b200 as hp
 rng = np.random.default_rng(1887)
 deg = rng.integers(1, 7, 32 ** 3).astype(np.int32)

@@ -22,4 +22,4 @@ except Exception as e:
     print(sys.argv[1], 'NO LINE', e)
 PY
 done
-tail -3 $O/r2_bench_cfg2_n${N}.err $O/r2_bench_cfg5_n${N}.err
+tail -q -n 3 $O/r2_bench_cfg2_n${N}.err $O/r2_bench_cfg5_n${N}.err; true
