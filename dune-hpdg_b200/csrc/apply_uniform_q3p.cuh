@@ -371,6 +371,53 @@ hpdg_k_apply_q3_persist(const __grid_constant__ hpdg::UniParams<4> P, const int4
       }
     }
 
+#ifndef Q3P_NO_FUSE45
+    // ---------------- P4+5: factor * M_z M_x on (x,z)-planes, 256-bit stores ----------------
+    // plane role: x-z plane j of one element of this half; a quarter warp = 4 j x 2 element layers (the x-role's lanes, with
+    // the x-role's k bits selecting the element of the row instead).  The 16 values of a plane cross shared memory once
+    // (8 128-bit loads), both mass sweeps run in registers, and every lane stores whole 32-byte sectors: the four j lanes
+    // of an element together write one full 128-byte line per z-plane.
+    {
+      const int tid = q3p_tid();
+      const int pj = tid & 3, pez = ((tid >> 2) & 1) | ((tid >> 6) & 2), pex = (tid >> 3) & 3, pey = (tid >> 5) & 3;
+      const int pbase = (pex + 4 * pey + 16 * pez) * N3;
+      double b[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int q = 2 * (pj ^ k) + (pez & 1);
+        const double2 lo = *reinterpret_cast<const double2*>(sw + pbase + 16 * k + 2 * (q & 7));
+        const double2 hi = *reinterpret_cast<const double2*>(sw + pbase + 16 * k + 2 * ((q + 1) & 7));
+        double a[4] = {lo.x, lo.y, hi.x, hi.y};
+        q3p_mass<false>(a);
+#pragma unroll
+        for (int i = 0; i < 4; i++) b[k][i] = a[i];
+      }
+      double o[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        double c[4] = {b[0][i], b[1][i], b[2][i], b[3][i]};
+        q3p_mass<true>(c);
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k][i] = c[k];
+      }
+      double* __restrict__ yo_p = P.y + (long)(e0 + pex + n0 * pey + n01 * pez) * N3 + N * pj;
+      if (P.accum) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          double y0, y1, y2, y3;
+          asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];\n" : "=d"(y0), "=d"(y1), "=d"(y2), "=d"(y3) : "l"(yo_p + N2 * k));
+          o[k][0] += y0; o[k][1] += y1; o[k][2] += y2; o[k][3] += y3;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};\n" ::"l"(yo_p + N2 * k), "d"(o[k][0]), "d"(o[k][1]), "d"(o[k][2]), "d"(o[k][3]) : "memory");
+    }
+    if (!has_next) break;
+    __syncthreads();  // the plane role's reads of w precede the next tile's first-pass writes (different thread -> DoF mapping)
+    t = tn;
+    continue;
+#else
     // ---------------- P4: M_x ----------------
     {
       const int tid = q3p_tid();
@@ -410,6 +457,7 @@ hpdg_k_apply_q3_persist(const __grid_constant__ hpdg::UniParams<4> P, const int4
       };
       if (P.accum) tile_out(std::true_type{}); else tile_out(std::false_type{});
     }
+#endif
     if (!has_next) break;
     t = tn;
   }
