@@ -114,7 +114,7 @@ int setup_level(Ctx* ctx, Level& L, int dim, const int* n, const double* h, cons
 }
 
 void free_level(Level& L) {
-  cudaFree(L.d_deg); cudaFree(L.d_pdeg); cudaFree(L.d_off); cudaFree(L.d_elist); cudaFree(L.d_troff); cudaFree(L.d_tr);
+  cudaFree(L.d_deg); cudaFree(L.d_pdeg); cudaFree(L.d_off); cudaFree(L.d_elist); cudaFree(L.d_troff); cudaFree(L.d_tr); cudaFree(L.d_gs_elist);
   cudaFree(L.jd.d_inv); cudaFree(L.jf.d_fac); cudaFree(L.jf.d_idx);
   cudaFree(L.mg_x); cudaFree(L.mg_r); cudaFree(L.mg_t1); cudaFree(L.mg_t2);
   cudaFree(L.d_tiles_int); cudaFree(L.d_tiles_bnd); cudaFree(L.d_tiles_all); cudaFree(L.d_tile_desc); cudaFree(L.d_jinv);
@@ -343,13 +343,13 @@ struct VC { int form; double damping; int pre, post, coarse_its; };
 
 int mg_smooth(Ctx* ctx, int l, const VC& v, int steps, double* x, double* r) {
   Level& L = ctx->levels[l];
-  if (v.form == HPDG_SMOOTHER_BLOCKGS) {
+  if (v.form == HPDG_SMOOTHER_BLOCKGS || v.form == HPDG_SMOOTHER_BLOCKGS_MF) {
     // the reference's default: smootherFromIterationStep2 around DynamicBlockGS on the level's assembled (Galerkin) matrix
     // (solversetup.hh:139-145, multigrid.hh:96-107).  tmp1 is zeroed once per applySmoother (multigrid_impl.hh:73) and NOT between
     // steps: iterate() continues from the previous tmp1, exactly as the reference does.
     HPDG_CUDA(cudaMemsetAsync(L.mg_t1, 0, sizeof(double) * L.ndof, ctx->stream));
     for (int i = 0; i < steps; i++) {
-      if (blockgs_iterate(ctx, L, r, L.mg_t1)) return 1;
+      if (v.form == HPDG_SMOOTHER_BLOCKGS ? blockgs_iterate(ctx, L, r, L.mg_t1) : blockgs_mf_iterate(ctx, L, r, L.mg_t1)) return 1;
       if (v.damping != 1.0) { if (launch_axpy(ctx, L.ndof, v.damping - 1.0, L.mg_t1, L.mg_t1)) return 1; }
       if (launch_axpy(ctx, L.ndof, 1.0, L.mg_t1, x)) return 1;
       ctx->fuse_accum = 1;
@@ -377,8 +377,9 @@ int mg_smooth(Ctx* ctx, int l, const VC& v, int steps, double* x, double* r) {
 int mg_level(Ctx* ctx, int l, const VC& v) {
   Level& L = ctx->levels[l];
   double* x = L.mg_x; double* r = L.mg_r;
-  if (l == 0 && v.form == HPDG_SMOOTHER_BLOCKGS) {  // coarse solver of the reference: coarse_its block-GS iterations (solversetup.hh:198-215)
-    for (int i = 0; i < v.coarse_its; i++) if (blockgs_iterate(ctx, L, r, x)) return 1;
+  if (l == 0 && (v.form == HPDG_SMOOTHER_BLOCKGS || v.form == HPDG_SMOOTHER_BLOCKGS_MF)) {  // coarse solver of the reference: coarse_its block-GS iterations (solversetup.hh:198-215)
+    for (int i = 0; i < v.coarse_its; i++)
+      if (v.form == HPDG_SMOOTHER_BLOCKGS ? blockgs_iterate(ctx, L, r, x) : blockgs_mf_iterate(ctx, L, r, x)) return 1;
     return 0;
   }
   if (l == 0) {  // coarse solver: coarse_its damped block-Jacobi iterations from x = 0 (cf. solversetup.hh:198-215)
@@ -416,6 +417,7 @@ int vcycle_device(Ctx* ctx, const VC& v, double* d_x, double* d_b) {
       HPDG_CUDA(cudaMalloc(&L.mg_t2, sizeof(double) * L.ndof));
     }
     if (v.form == HPDG_SMOOTHER_BLOCKGS) { if (bcrs_build(ctx, L)) return 1; }
+    else if (v.form == HPDG_SMOOTHER_BLOCKGS_MF) {}
     else if (v.form == HPDG_JACOBI_DENSE ? !L.jd.ready : !L.jf.ready) {
       if (v.form == HPDG_JACOBI_DENSE ? jacobi_setup_dense(ctx, L) : jacobi_setup_fd(ctx, L)) return 1;
     }
@@ -899,6 +901,23 @@ int hpdg_blockgs_iterate(hpdg_ctx* ctx, int level, const double* h_b, double* h_
   HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_b, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
   HPDG_CUDA(cudaMemcpyAsync(ctx->d_out, h_x, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
   if (blockgs_iterate(ctx, *L, ctx->d_in, ctx->d_out)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(h_x, ctx->d_out, sizeof(double) * L->ndof, cudaMemcpyDeviceToHost, ctx->stream));
+  return sync_check(ctx);
+}
+
+int hpdg_blockgs_mf_iterate_device(hpdg_ctx* ctx, int level, const double* d_b, double* d_x) {
+  HPDG_ENTER(ctx);
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  if (blockgs_mf_iterate(ctx, *L, d_b, d_x)) return 1;
+  return sync_check(ctx);
+}
+int hpdg_blockgs_mf_iterate(hpdg_ctx* ctx, int level, const double* h_b, double* h_x) {
+  HPDG_ENTER(ctx);
+  Level* L = get_level(ctx, level); if (!L) return 1;
+  if (ensure_stage(ctx, L->ndof)) return 1;
+  HPDG_CUDA(cudaMemcpyAsync(ctx->d_in, h_b, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
+  HPDG_CUDA(cudaMemcpyAsync(ctx->d_out, h_x, sizeof(double) * L->ndof, cudaMemcpyHostToDevice, ctx->stream));
+  if (blockgs_mf_iterate(ctx, *L, ctx->d_in, ctx->d_out)) return 1;
   HPDG_CUDA(cudaMemcpyAsync(h_x, ctx->d_out, sizeof(double) * L->ndof, cudaMemcpyDeviceToHost, ctx->stream));
   return sync_check(ctx);
 }

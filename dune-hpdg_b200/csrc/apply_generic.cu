@@ -145,9 +145,20 @@ static_assert(sizeof(FaceInfo) == 32, "FaceInfo layout");
 // 1-D tables of the bucket's degree, passed by value (constant bank)
 template <int N1> struct GenTab { double MinvS[N1 * N1], M[N1 * N1], mt[2][N1], mg[2][N1], g[2][N1]; };
 
-template <int DIM, int N1>
-__global__ void k_apply_generic(const __grid_constant__ GenericParams P, const __grid_constant__ GenTab<N1> T, const int maxno1,
-                                const long cnt, const int epc, const int per_elem, const int mixed) {
+// Matrix-free block Gauss-Seidel (MODE 1): what the element pass needs beyond the operator apply
+struct GsParams {
+  const double* b;   // right-hand side
+  double* x;         // iterate (== GenericParams::x), updated in place
+  double2* tr;       // the level's trace array (== GenericParams::tr), the updated elements' traces are rewritten
+};
+
+// MODE 0: y_e = factor * (A x)_e.  MODE 1: one DynamicBlockGS row update of every element of the launch (the elements of one
+// hyperplane and degree bucket, mutually independent): r_e = b_e - (A x)_e with the current x, x_e += (L_ee + D_ee)^-1 r_e
+// (GSCore), then the element's own face traces are recomputed (blockgs_mf.cu).
+template <int DIM, int N1, int MODE>
+__device__ __forceinline__ void generic_element_pass(const GenericParams& P, const GenTab<N1>& T, const int maxno1,
+                                                     const long cnt, const int epc, const int per_elem, const int mixed,
+                                                     const GsParams& G) {
   extern __shared__ double sm_all[];
   constexpr int nfaces = 2 * DIM;
   constexpr int pe = N1 - 1;
@@ -334,12 +345,113 @@ __global__ void k_apply_generic(const __grid_constant__ GenericParams P, const _
         double s = 0;
 #pragma unroll
         for (int k = 0; k < N1; k++) s = fma(T.M[i * N1 + k], w[k], s);
-        if (d == 0) yo[base + i] = P.accum ? yo[base + i] + P.factor * s : P.factor * s;
+        if (d == 0 && MODE == 0) yo[base + i] = P.accum ? yo[base + i] + P.factor * s : P.factor * s;
         else sw[base + i * sd] = s;
       }
     }
-    if (d > 0) __syncthreads();
+    if (d > 0 || MODE == 1) __syncthreads();
   }
+  if (MODE == 0) return;
+
+  // ---- block Gauss-Seidel epilogue (iterationsteps/dynamicblockgs.hh:94-126 with GSCore, :17-40) -------------------------
+  // sw holds (A x)_e.  The diagonal block is never stored: A_ee = sum_d M x..x D_d x..x M with the 1-D factors D_d of the
+  // element (own-face terms folded in, the same factors the block-Jacobi setup builds: jacobi.cu build_dir_matrix), so
+  // entry (j, a) costs a handful of shared-memory reads.  GSCore from zero is the forward substitution (L + D) c = r.
+  {
+    constexpr int n2 = N1 * N1;
+    double* sM = sm_all + (size_t)epc * per_elem;                                // [n2] 1-D mass (one copy per CTA)
+    auto SD = [&](int el, int d) { return SW(el) + ne + 4 * nfaces + (mixed && DIM == 3 ? 2 * nfaces * maxtmp : 0) + d * n2; };
+    auto SC = [&](int el) { return SD(el, DIM); };                               // [ne] correction
+    for (int t = tid; t < n2; t += nthr) sM[t] = T.M[t];
+    for (int t = tid; t < nel * DIM * n2; t += nthr) {
+      const int el = t / (DIM * n2), d = (t / n2) % DIM, i = (t % n2) / N1, j = t % N1;
+      const DegTable& DT = P.tab[pe];
+      double kap = 1.0 / P.h[d];
+      for (int dd = 0; dd < DIM; dd++) if (dd != d) kap *= P.h[dd];
+      double v = kap * DT.S[i * kMaxN + j];
+      for (int s = 0; s < 2; s++) {
+        const FaceInfo F = FI(el)[2 * d + s];
+        if (F.mode == 0) continue;
+        const double wgt = F.mode == 1 ? 1.0 : 0.5;
+        v += -wgt * F.nuk * (DT.t[s][i] * DT.g[s][j] + DT.g[s][i] * DT.t[s][j]) + F.cpen * DT.t[s][i] * DT.t[s][j];
+      }
+      SD(el, d)[i * N1 + j] = v;
+    }
+    long e_own = 0;
+    if (lact) {
+      e_own = P.elist[P.ebegin + first + lel];
+      double* sw = SW(lel);
+      const double* __restrict__ be = G.b + P.off[e_own];
+#pragma unroll
+      for (int k = 0; k < N1; k++) { const int j = line + nf * k; sw[j] = be[j] - sw[j]; }   // r_e = b_e - (A x)_e
+    }
+    const int j0 = line % N1, j1 = DIM == 3 ? line / N1 : 0;
+    for (int a = 0; a < ne; a++) {
+      __syncthreads();
+      if (lact) {
+        double* sw = SW(lel);
+        const double* Dx = SD(lel, 0); const double* Dy = SD(lel, 1); const double* Dz = SD(lel, DIM - 1);
+        const int a0 = a % N1, a1 = (a / N1) % N1, a2 = a / n2;
+        double maa, c1, c2;
+        if (DIM == 3) {
+          maa = Dx[a0 * N1 + a0] * sM[a1 * N1 + a1] * sM[a2 * N1 + a2] + sM[a0 * N1 + a0] * Dy[a1 * N1 + a1] * sM[a2 * N1 + a2] +
+                sM[a0 * N1 + a0] * sM[a1 * N1 + a1] * Dz[a2 * N1 + a2];
+          c1 = Dx[j0 * N1 + a0] * sM[j1 * N1 + a1] + sM[j0 * N1 + a0] * Dy[j1 * N1 + a1];
+          c2 = sM[j0 * N1 + a0] * sM[j1 * N1 + a1];
+        } else {
+          maa = Dx[a0 * N1 + a0] * sM[a1 * N1 + a1] + sM[a0 * N1 + a0] * Dy[a1 * N1 + a1];
+          c1 = Dx[j0 * N1 + a0]; c2 = sM[j0 * N1 + a0];
+        }
+        const double xa = (fabs(maa) == 0.) ? 0.0 : sw[a] / maa;               // dynamicblockgs.hh:26-27,36
+        if (a % nf == line) SC(lel)[a] = xa;
+        const int ak = DIM == 3 ? a2 : a1;                                       // the column's index in the owned direction
+#pragma unroll
+        for (int k = 0; k < N1; k++) {
+          const int j = line + nf * k;
+          if (j > a) {
+            const double mja = DIM == 3 ? sM[k * N1 + ak] * c1 + Dz[k * N1 + ak] * c2 : sM[k * N1 + ak] * c1 + Dy[k * N1 + ak] * c2;
+            sw[j] = fma(-mja, xa, sw[j]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (lact) {
+      double* su = SU(lel); const double* sc = SC(lel);
+      double* __restrict__ xe = G.x + P.off[e_own];
+#pragma unroll
+      for (int k = 0; k < N1; k++) { const int j = line + nf * k; const double xn = su[j] + sc[j]; su[j] = xn; xe[j] = xn; }
+    }
+    __syncthreads();
+    if (lact) {   // the element's own face traces follow its new values (the later hyperplanes pull them)
+      const double* su = SU(lel);
+      double2* __restrict__ out = G.tr + P.troff[e_own];
+#pragma unroll
+      for (int d = 0; d < DIM; d++) {
+        const int base = line_base_c<DIM, N1>(d, line), sd = line_stride_c<N1>(d);
+        double d0 = 0, d1 = 0, v0 = 0, v1 = 0;
+#pragma unroll
+        for (int k = 0; k < N1; k++) {
+          const double v = su[base + k * sd];
+          d0 = fma(c_end_g[N1 - 1][0][k], v, d0); d1 = fma(c_end_g[N1 - 1][1][k], v, d1);
+          v0 = fma(c_end_t[N1 - 1][0][k], v, v0); v1 = fma(c_end_t[N1 - 1][1][k], v, v1);
+        }
+        out[(2 * d) * nf + line] = make_double2(d0, v0);
+        out[(2 * d + 1) * nf + line] = make_double2(d1, v1);
+      }
+    }
+  }
+}
+
+template <int DIM, int N1>
+__global__ void k_apply_generic(const __grid_constant__ GenericParams P, const __grid_constant__ GenTab<N1> T, const int maxno1,
+                                const long cnt, const int epc, const int per_elem, const int mixed) {
+  generic_element_pass<DIM, N1, 0>(P, T, maxno1, cnt, epc, per_elem, mixed, GsParams());
+}
+template <int DIM, int N1>
+__global__ void k_blockgs_generic(const __grid_constant__ GenericParams P, const __grid_constant__ GenTab<N1> T, const int maxno1,
+                                  const long cnt, const int epc, const int per_elem, const int mixed, const GsParams G) {
+  generic_element_pass<DIM, N1, 1>(P, T, maxno1, cnt, epc, per_elem, mixed, G);
 }
 
 // the level's trace array (allocated on first use) and the offsets of every element's traces
@@ -500,6 +612,102 @@ int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double 
       HPDG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->bucket_ev[k], 0));
     }
   }
+  return 0;
+}
+
+// ---- matrix-free block Gauss-Seidel: DynamicBlockGS::iterate (iterationsteps/dynamicblockgs.hh:94-126) without a matrix ----------
+// The reference sweeps the block rows in ascending element order: r_i = b_i - sum_j A_ij x_j with the current x, then
+// x_i += GSCore(A_ii, r_i).  Elements on a hyperplane ix + iy + iz = const are never face neighbours and depend only on lower
+// hyperplanes, so sweeping hyperplane by hyperplane (elements of one hyperplane in parallel) reproduces the sequential sweep
+// with the same operands for every row -- as the assembled hpdg_blockgs_iterate does (assemble.cu), but (A x)_i comes from the
+// element pass of the operator kernel (own block + the neighbours' current face traces) and A_ii from its Kronecker factors:
+// no matrix, so the reference's default smoother runs at the named mesh sizes (the assembled one needs 229 KB per Q3 element).
+static int blockgs_mf_setup(Ctx* ctx, Level& L) {
+  if (L.d_gs_elist) return 0;
+  const int nb = (int)L.bucket_p.size();
+  const int nw = L.n[0] + L.n[1] + (L.dim == 3 ? L.n[2] : 1) - 2;
+  std::vector<int> bucket_of(kMaxP + 1, -1);
+  for (int b = 0; b < nb; b++) bucket_of[L.bucket_p[b]] = b;
+  std::vector<long> cntv((size_t)nw * nb + 1, 0);
+  auto seg = [&](long e) {
+    long r = e; const int i0 = (int)(r % L.n[0]); r /= L.n[0]; const int i1 = (int)(r % L.n[1]); r /= L.n[1];
+    return (size_t)(i0 + i1 + (int)r) * nb + bucket_of[L.deg[e]];
+  };
+  for (long e = 0; e < L.nelem; e++) cntv[seg(e) + 1]++;
+  for (size_t k = 0; k < (size_t)nw * nb; k++) cntv[k + 1] += cntv[k];
+  L.gs_seg = cntv;
+  std::vector<int> list(L.nelem);
+  std::vector<long> pos(cntv.begin(), cntv.end() - 1);
+  for (long e = 0; e < L.nelem; e++) list[pos[seg(e)]++] = (int)e;   // ascending element index inside a segment
+  HPDG_CUDA(cudaMalloc(&L.d_gs_elist, sizeof(int) * std::max<long>(L.nelem, 1)));
+  HPDG_CUDA(cudaMemcpy(L.d_gs_elist, list.data(), sizeof(int) * L.nelem, cudaMemcpyHostToDevice));
+  L.gs_nw = nw;
+  return 0;
+}
+
+template <int NN>
+static void fill_gentab(GenTab<NN>& T, const DegTable& HT) {
+  for (int i = 0; i < NN; i++) {
+    for (int j = 0; j < NN; j++) { T.MinvS[i * NN + j] = HT.MinvS[i * kMaxN + j]; T.M[i * NN + j] = HT.M[i * kMaxN + j]; }
+    for (int sd = 0; sd < 2; sd++) { T.mt[sd][i] = HT.mt[sd][i]; T.mg[sd][i] = HT.mg[sd][i]; T.g[sd][i] = HT.g[sd][i]; }
+  }
+}
+
+int blockgs_mf_iterate(Ctx* ctx, Level& L, const double* b, double* x) {
+  if (ctx->nranks > 1) { ctx->err = "matrix-free block Gauss-Seidel is rank-local (use the L1 smoother or block Jacobi across ranks)"; return 1; }
+  if (blockgs_mf_setup(ctx, L)) return 1;
+  static thread_local GenericParams P;
+  P.dim = L.dim;
+  for (int d = 0; d < 3; d++) { P.n[d] = L.n[d]; P.h[d] = L.h[d]; }
+  P.sigma = ctx->sigma; P.dirichlet = ctx->dirichlet;
+  P.deg = L.d_deg; P.pdeg = L.d_pdeg; P.off = L.d_off; P.elist = L.d_gs_elist;
+  P.tab = ctx->d_tab; P.P = ctx->d_P; P.x = x; P.y = nullptr; P.factor = 1.0; P.accum = 0;
+  if (launch_face_traces(ctx, L, x, ctx->stream)) return 1;   // traces of the incoming iterate; the sweep keeps them current
+  P.troff = L.d_troff; P.tr = reinterpret_cast<const double2*>(L.d_tr);
+  for (int f = 0; f < 6; f++) { P.bnd_is_rank[f] = 0; P.ghost_deg[f] = P.ghost_pdeg[f] = nullptr; P.ghost_troff[f] = nullptr; P.ghost_tr[f] = nullptr; }
+  GsParams G; G.b = b; G.x = x; G.tr = reinterpret_cast<double2*>(L.d_tr);
+  const int maxno1 = L.maxp + 1;
+  const int mixed = L.uniform ? 0 : 1;
+  const int nb = (int)L.bucket_p.size();
+  for (int w = 0; w < L.gs_nw; w++) {
+    for (int bk = 0; bk < nb; bk++) {
+      const long begin = L.gs_seg[(size_t)w * nb + bk], cnt = L.gs_seg[(size_t)w * nb + bk + 1] - begin;
+      if (cnt == 0) continue;
+      const int p = L.bucket_p[bk], n1 = p + 1;
+      const int ne = ipow_d(n1, L.dim), nf = ipow_d(n1, L.dim - 1), nfaces = 2 * L.dim;
+      const int per_elem = 2 * ne + 4 * nfaces + ((mixed && L.dim == 3) ? 2 * nfaces * n1 * maxno1 : 0);
+      const int per_elem_gs = per_elem + L.dim * n1 * n1 + ne;
+      P.ebegin = begin;
+      int epc = nf >= 128 ? 1 : 128 / nf;
+      epc = (int)std::max<long>(1, std::min<long>(epc, (48 * 1024) / ((long)per_elem_gs * 8)));
+      epc = (int)std::min<long>(epc, cnt);
+      const size_t smem_l = ((size_t)epc * per_elem_gs + n1 * n1) * sizeof(double);
+      const unsigned grid = (unsigned)((cnt + epc - 1) / epc);
+      const int threads = std::max(32, (epc * nf + 31) / 32 * 32);
+      if (threads > 1024) { ctx->err = "matrix-free block Gauss-Seidel: degree too high for one CTA per element"; return 1; }
+      const DegTable& HT = host_tables().deg[p];
+#define HPDG_GS_LAUNCH(D, NN)                                                                                             \
+  do {                                                                                                                    \
+    static thread_local GenTab<NN> T;                                                                                     \
+    fill_gentab<NN>(T, HT);                                                                                               \
+    if (kernel_slots(ctx, reinterpret_cast<const void*>(k_blockgs_generic<D, NN>), threads, 200 * 1024, nullptr)) return 1; \
+    k_blockgs_generic<D, NN><<<grid, threads, smem_l, ctx->stream>>>(P, T, maxno1, cnt, epc, per_elem_gs, mixed, G);      \
+  } while (0)
+#define HPDG_GS_CASE(NN)                                                     \
+  case NN:                                                                   \
+    if (L.dim == 2) HPDG_GS_LAUNCH(2, NN); else HPDG_GS_LAUNCH(3, NN);       \
+    break;
+      switch (n1) {
+        HPDG_GS_CASE(1) HPDG_GS_CASE(2) HPDG_GS_CASE(3) HPDG_GS_CASE(4) HPDG_GS_CASE(5) HPDG_GS_CASE(6) HPDG_GS_CASE(7)
+        HPDG_GS_CASE(8) HPDG_GS_CASE(9) HPDG_GS_CASE(10) HPDG_GS_CASE(11) HPDG_GS_CASE(12) HPDG_GS_CASE(13) HPDG_GS_CASE(14)
+        default: ctx->err = "degree out of range"; return 1;
+      }
+#undef HPDG_GS_CASE
+#undef HPDG_GS_LAUNCH
+      ctx->launches++;
+    }
+  }
+  HPDG_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -102,6 +102,8 @@ struct Level {
   long* d_troff = nullptr;      // [nelem+1] offset (in pairs) of an element's traces; face f at troff[e] + f * N_e^(dim-1)
   double* d_tr = nullptr;       // [2 * tr_pairs]
   long tr_pairs = 0;
+  // matrix-free block Gauss-Seidel: elements sorted by (hyperplane ix+iy+iz, degree bucket); segment k = w * buckets + b
+  int* d_gs_elist = nullptr; std::vector<long> gs_seg; int gs_nw = 0;
   JacobiDense jd;
   JacobiFD jf;
   Bcrs bcrs;
@@ -206,6 +208,7 @@ int diag_block_device(Ctx* ctx, Level& L, long e, double* d_out);
 int bcrs_build(Ctx* ctx, Level& L);
 int bcrs_mv(Ctx* ctx, Level& L, const double* x, double* y);
 int blockgs_iterate(Ctx* ctx, Level& L, const double* b, double* x, int l1 = 0);
+int blockgs_mf_iterate(Ctx* ctx, Level& L, const double* b, double* x);   // (apply_generic.cu) the same sweep without a matrix
 int l1_setup(Ctx* ctx, Level& L, const long* ghosts, long nghost);
 
 int launch_restrict(Ctx* ctx, Level& fine, Level& coarse, const double* xf, double* xc);

@@ -20,6 +20,7 @@ FINEST = -1
 JACOBI_DENSE = 0
 JACOBI_FD = 1
 SMOOTHER_BLOCKGS = 2
+SMOOTHER_BLOCKGS_MF = 3
 PRECOND_NONE = 0
 PRECOND_JACOBI = 1
 PRECOND_VCYCLE = 2
@@ -75,6 +76,8 @@ SIGNATURES = {
     "hpdg_bcrs_mv_device": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "hpdg_blockgs_iterate": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "hpdg_blockgs_iterate_device": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "hpdg_blockgs_mf_iterate": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "hpdg_blockgs_mf_iterate_device": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "hpdg_l1_setup": (C.c_int, [_vp, C.c_int, _vp, C.c_long]),
     "hpdg_l1_iterate": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "hpdg_l1_iterate_device": (C.c_int, [_vp, C.c_int, _vp, _vp]),
@@ -422,6 +425,27 @@ class DynamicBlockGS:
     def iterate(self):
         c = self.mat_.ctx
         c._ck(lib().hpdg_blockgs_iterate(c._h, self.mat_.level, _hptr(self.rhs_), _hptr(self.x_)))
+
+
+class MatrixFreeBlockGS:
+    """The same iteration step without an assembled matrix (hpdg_blockgs_mf_iterate): setProblem(x, rhs); iterate().
+    `ctx` takes the place of the matrix; works at any mesh size the vectors fit."""
+
+    def __init__(self, ctx, level=FINEST):
+        self.ctx, self.level = ctx, level
+        self.x_ = self.rhs_ = None
+
+    def setProblem(self, x, rhs):
+        self.x_, self.rhs_ = x, rhs
+
+    def preprocess(self):
+        pass
+
+    def iterate(self):
+        self.ctx._ck(lib().hpdg_blockgs_mf_iterate(self.ctx._h, self.level, _hptr(self.rhs_), _hptr(self.x_)))
+
+    def iterate_device(self, d_x, d_rhs):
+        self.ctx._ck(lib().hpdg_blockgs_mf_iterate_device(self.ctx._h, self.level, d_rhs, d_x))
 
 
 class L1Smoother:

@@ -29,6 +29,7 @@ typedef struct hpdg_ctx hpdg_ctx;
 #define HPDG_JACOBI_DENSE 0       /* precomputed dense per-element inverses, batched by block size */
 #define HPDG_JACOBI_FD 1          /* same inverse in Kronecker (fast diagonalisation) form */
 #define HPDG_SMOOTHER_BLOCKGS 2    /* hpdg_vcycle only: the reference's DynamicBlockGS on assembled level matrices */
+#define HPDG_SMOOTHER_BLOCKGS_MF 3 /* hpdg_vcycle only: the same DynamicBlockGS sweeps without a matrix (any mesh size) */
 #define HPDG_PRECOND_NONE 0       /* hpdg_pcg: plain CG */
 #define HPDG_PRECOND_JACOBI 1     /* hpdg_pcg: fd block-Jacobi preconditioner */
 #define HPDG_PRECOND_VCYCLE 2     /* hpdg_pcg: one p-multigrid V-cycle with fd block-Jacobi smoothing */
@@ -134,6 +135,12 @@ int hpdg_bcrs_mv_device(hpdg_ctx* ctx, int level, const double* d_x, double* d_y
  * ascending order, inner forward scalar GS sweep from zero.  x is updated in place. */
 int hpdg_blockgs_iterate(hpdg_ctx* ctx, int level, const double* h_b, double* h_x);
 int hpdg_blockgs_iterate_device(hpdg_ctx* ctx, int level, const double* d_b, double* d_x);
+/* the same DynamicBlockGS::iterate() WITHOUT an assembled matrix: per hyperplane of independent block rows, (A x)_i comes from
+ * the operator kernel's element pass (own block + the neighbours' current face traces) and the diagonal block A_ii from its
+ * Kronecker factors, so the reference's default smoother (solversetup.hh:139-145) runs at any mesh size the vectors fit.
+ * No hpdg_assemble_bcrs needed; single rank. */
+int hpdg_blockgs_mf_iterate(hpdg_ctx* ctx, int level, const double* h_b, double* h_x);
+int hpdg_blockgs_mf_iterate_device(hpdg_ctx* ctx, int level, const double* d_b, double* d_x);
 /* L1Smoother (iterationsteps/l1smoother.hh:20-145), the reference's smoother for MPI runs: block Gauss-Seidel whose local solver
  * (a forward scalar GS sweep from zero, :127-145) divides by D_aa + reg_a, where reg is the l1 norm of the rows of the blocks
  * that couple an owned block row to a ghost block (preprocess(), :31-57).  hpdg_l1_setup = L1Smoother(ghosts) + preprocess():
@@ -152,7 +159,8 @@ int hpdg_prolong_device(hpdg_ctx* ctx, int fine_level, const double* d_coarse, d
 /* -- one multigrid cycle: Multigrid<Vector>::apply(x, b) (iterationsteps/mg/multigrid_impl.hh:16-117) with the
  * block-Jacobi smoother on every level and `coarse_its` damped Jacobi iterations as coarse solver, or -- with form =
  * HPDG_SMOOTHER_BLOCKGS -- the reference's own configuration: DynamicBlockGS on the assembled Galerkin level matrices as
- * smoother and `coarse_its` block-GS iterations as coarse solver (solversetup.hh:139-145,198-215; small/medium meshes).  On return x += correction and
+ * smoother and `coarse_its` block-GS iterations as coarse solver (solversetup.hh:139-145,198-215; small/medium meshes), or --
+ * form = HPDG_SMOOTHER_BLOCKGS_MF -- the same cycle with the matrix-free block-GS sweeps (no matrices).  On return x += correction and
  * b holds the residual (multigrid_impl.hh:60-61). */
 int hpdg_vcycle(hpdg_ctx* ctx, int form, double damping, int pre, int post, int coarse_its, double* h_x, double* h_b);
 int hpdg_vcycle_device(hpdg_ctx* ctx, int form, double damping, int pre, int post, int coarse_its, double* d_x,

@@ -169,6 +169,22 @@ class DynamicBlockGS {
   const V* rhs_ = nullptr;
 };
 
+// The same iteration step without an assembled matrix (hpdg_blockgs_mf_iterate): the context takes the matrix's place in
+// setProblem; the sweeps are those of DynamicBlockGS::iterate (dynamicblockgs.hh:94-126) at any mesh size.
+template <class V>
+class MatrixFreeBlockGS {
+ public:
+  explicit MatrixFreeBlockGS(std::shared_ptr<Context> c, int level = HPDG_FINEST) : c_(std::move(c)), level_(level) {}
+  void setProblem(V& x, const V& rhs) { x_ = &x; rhs_ = &rhs; }
+  void preprocess() {}
+  void iterate() { c_->check(hpdg_blockgs_mf_iterate(c_->handle(), level_, rhs_->data(), x_->data())); }
+  V* x_ = nullptr;
+  const V* rhs_ = nullptr;
+ private:
+  std::shared_ptr<Context> c_;
+  int level_;
+};
+
 // Dune::HPDG::L1Smoother<Matrix, Vector> (iterationsteps/l1smoother.hh:20-145): L1Smoother(ghosts); setProblem(mat, x, rhs);
 // preprocess(); iterate()
 template <class V>

@@ -557,6 +557,66 @@ def test_vcycle_with_reference_default_smoother(orc, hp):
     assert np.linalg.norm(bb) < 0.2 * np.linalg.norm(b - Af.mv(x0))
 
 
+@pytest.mark.parametrize("dim,n,pmax,uniform", [(2, (16, 16), 2, True), (2, (5, 4), 4, False), (3, (3, 4, 2), 4, False),
+                                                (3, (8, 4, 4), 3, True), (3, (1, 3, 1), 5, False), (3, (4, 4, 4), 4, True)])
+def test_matrix_free_blockgs(orc, hp, dim, n, pmax, uniform):
+    # DynamicBlockGS::iterate (iterationsteps/dynamicblockgs.hh:94-126, GSCore :17-40) WITHOUT an assembled matrix, against the
+    # oracle's sweep on the assembled matrix: cfg1 (10 sweeps from x = 1, b = 1: test_dynamicblockgs.cc:31-32), hp meshes, 3-D
+    rng = np.random.default_rng(13)
+    deg = pmax if uniform else rng.integers(1, pmax + 1, int(np.prod(n))).astype(np.int32)
+    for dirichlet in (True, False):
+        m = orc.Mesh(n, L=[1.0, 1.5, 0.75][:dim], degree=deg, sigma=2.0, dirichlet=dirichlet)
+        A = m.assemble()
+        ctx = hp.Context(n, L=[1.0, 1.5, 0.75][:dim], degree=deg, sigma=2.0, dirichlet=dirichlet)
+        b = np.ones(m.ndof) if uniform else orc.fill_random(m.ndof, 5)
+        xr = np.ones(m.ndof) if uniform else orc.fill_random(m.ndof)
+        xg = xr.copy()
+        gs = hp.MatrixFreeBlockGS(ctx)
+        gs.setProblem(xg, b)
+        for _ in range(10 if dim == 2 else 3):
+            A.blockgs_iterate(b, xr)
+            gs.iterate()
+        assert rel(xg, xr) < TOL
+        ctx.close()
+
+
+def test_vcycle_with_matrix_free_blockgs(orc, hp):
+    # the reference's p-MG configuration (solversetup.hh:139-145,198-215) with the matrix-free DynamicBlockGS sweeps on every
+    # level, against the oracle's cycle on the assembled Galerkin matrices
+    n = (3, 3, 3)
+    fine = orc.Mesh(n, degree=4)
+    l1 = fine.coarsen(2)
+    l0 = l1.coarsen(1)
+    Af = fine.assemble()
+    A1 = fine.galerkin_restrict(l1, Af)
+    A0 = l1.galerkin_restrict(l0, A1)
+    b = orc.fill_random(fine.ndof)
+    x0 = orc.fill_random(fine.ndof, seed=3) * 0.1
+    xr, rr = orc.vcycle([l0, l1, fine], [A0, A1, Af], x0, b, smoother=0, damping=1.0)
+    ctx = hp.Context(n, degree=4)
+    ctx.build_p_hierarchy()
+    x, bb = x0.copy(), b.copy()
+    hp.Multigrid(ctx, form=hp.SMOOTHER_BLOCKGS_MF, damping=1.0).apply(x, bb)
+    assert rel(x, xr) < 1e-11 and rel(bb, rr) < 1e-10
+
+
+def test_matrix_free_blockgs_at_size(hp):
+    # a mesh whose assembled matrix would not be built (32^3 Q3: 7.5 GB): the sweeps run and reduce the residual of A x = b
+    n = (32, 32, 32)
+    ctx = hp.Context(n, degree=3, dirichlet=True)
+    nd = ctx.dimension()
+    b = np.random.default_rng(3).standard_normal(nd)
+    dx, db, dr = ctx.upload(np.zeros(nd)), ctx.upload(b), ctx.vec_alloc()
+    gs = hp.MatrixFreeBlockGS(ctx)
+    res = []
+    for _ in range(3):
+        gs.iterate_device(dx, db)
+        hp.Operator(ctx).apply_device(dx, dr)
+        res.append(np.linalg.norm(b - ctx.download(dr)))
+    assert res[0] < np.linalg.norm(b) and res[2] < res[1] < res[0]
+    ctx.close()
+
+
 def test_cfg5_full_size_properties(hp):
     # BASELINE config 5 brick: 128^3 elements, Q4 (262 144 000 DoF, 2.1 GB per vector) -- too large for the CPU oracle, so the
     # size-independent properties of the operator are checked on the device: symmetry, linearity, positivity.
