@@ -84,6 +84,22 @@ def test_cfg1_2d_q2_testdg(orc, hp):
     assert rel(Ax, A.mv(x)) < TOL
 
 
+@pytest.mark.parametrize("dirichlet", [True, False])
+def test_2d_against_gauss_lobatto_sumfactorised_formulation(orc, hp, dirichlet):
+    # the CUDA 2-D path against the oracle's THIRD formulation (oracle/sf2d.py: restatement of SumFactIPDGOperator,
+    # matrix-free/localoperators/sfipdg.hh, Gauss-Lobatto quadrature, own node generator): cfg1's mesh and an hp mesh
+    from oracle import sf2d
+    x = orc.Mesh((16, 16), degree=2).interpolate_normsq()
+    y = hp.Operator(hp.Context((16, 16), degree=2, sigma=2.0, dirichlet=dirichlet), factor=0.5).apply(x)
+    assert rel(y, sf2d.SumFactIPDG2D((16, 16), (1.0, 1.0), 2, 2.0, dirichlet).apply(x, 0.5)) < TOL
+    rng = np.random.default_rng(5)
+    deg = rng.integers(1, 7, 42).astype(np.int32)
+    s = sf2d.SumFactIPDG2D((7, 6), (1.0, 2.0), deg, 2.0, dirichlet)
+    x = orc.fill_random(s.ndof)
+    y = hp.Operator(hp.Context((7, 6), L=[1.0, 2.0], degree=deg, sigma=2.0, dirichlet=dirichlet)).apply(x)
+    assert rel(y, s.apply(x)) < TOL
+
+
 @pytest.mark.parametrize("dim,n", [(2, (7, 5)), (3, (4, 3, 5))])
 @pytest.mark.parametrize("dirichlet", [True, False])
 def test_hp_random_degrees(orc, hp, dim, n, dirichlet):
