@@ -114,7 +114,7 @@ int setup_level(Ctx* ctx, Level& L, int dim, const int* n, const double* h, cons
 }
 
 void free_level(Level& L) {
-  cudaFree(L.d_deg); cudaFree(L.d_pdeg); cudaFree(L.d_off); cudaFree(L.d_elist); cudaFree(L.d_troff); cudaFree(L.d_tr); cudaFree(L.d_gs_elist);
+  cudaFree(L.d_deg); cudaFree(L.d_pdeg); cudaFree(L.d_off); cudaFree(L.d_elist); cudaFree(L.d_troff); cudaFree(L.d_tr); cudaFree(L.d_gs_elist); cudaFree(L.d_finfo);
   cudaFree(L.jd.d_inv); cudaFree(L.jf.d_fac); cudaFree(L.jf.d_idx);
   cudaFree(L.mg_x); cudaFree(L.mg_r); cudaFree(L.mg_t1); cudaFree(L.mg_t2);
   cudaFree(L.d_tiles_int); cudaFree(L.d_tiles_bnd); cudaFree(L.d_tiles_all); cudaFree(L.d_tile_desc); cudaFree(L.d_jinv);
@@ -288,6 +288,7 @@ int hp_ghost_setup(Ctx* ctx, Level& L) {
     G.h_pdeg[f].resize(nfc); G.h_deg[f].resize(nfc);
     HPDG_CUDA(cudaMemcpy(G.h_pdeg[f].data(), G.d_pdeg[f], sizeof(int) * nfc, cudaMemcpyDeviceToHost));
     std::vector<long> roff(nfc), src(nfc), dst(nfc + 1, 0);
+    // (roff is kept as G.h_troff[f] for the level's face table)
     long rp = 0;
     for (long i = 0; i < nfc; i++) {
       if (G.h_pdeg[f][i] < 0 || G.h_pdeg[f][i] > kMaxP) { ctx->err = "ghost degree out of range (neighbour rank sent garbage?)"; return 1; }
@@ -310,6 +311,7 @@ int hp_ghost_setup(Ctx* ctx, Level& L) {
     HPDG_CUDA(cudaMemcpy(G.d_deg[f], G.h_deg[f].data(), sizeof(int) * nfc, cudaMemcpyHostToDevice));
     HPDG_CUDA(cudaMalloc(&G.d_troff[f], sizeof(long) * nfc));
     HPDG_CUDA(cudaMemcpy(G.d_troff[f], roff.data(), sizeof(long) * nfc, cudaMemcpyHostToDevice));
+    G.h_troff[f] = roff;
     HPDG_CUDA(cudaMalloc(&G.d_send_src[f], sizeof(long) * nfc));
     HPDG_CUDA(cudaMemcpy(G.d_send_src[f], src.data(), sizeof(long) * nfc, cudaMemcpyHostToDevice));
     HPDG_CUDA(cudaMalloc(&G.d_send_dst[f], sizeof(long) * (nfc + 1)));
@@ -611,7 +613,7 @@ void hpdg_destroy(hpdg_ctx* ctx) {
   if (ctx->h_ghost_err) cudaFreeHost(const_cast<int*>(ctx->h_ghost_err));
   cudaFree(ctx->d_scalar); cudaFree(ctx->d_partial);
   if (ctx->cg_p) { cudaFree(ctx->cg_p); cudaFree(ctx->cg_q); cudaFree(ctx->cg_r); cudaFree(ctx->cg_z); }
-  cudaFree(ctx->d_tab); cudaFree(ctx->d_sched); cudaFree(ctx->d_P); cudaFree(ctx->d_T); cudaFree(ctx->d_Mab); cudaFree(ctx->d_in); cudaFree(ctx->d_out);
+  cudaFree(ctx->d_tab); cudaFree(ctx->d_sched); cudaFree(ctx->d_P); cudaFree(ctx->d_T); cudaFree(ctx->d_Mab); cudaFree(ctx->d_Pnc_eo); cudaFree(ctx->d_Pnc_ee); cudaFree(ctx->d_in); cudaFree(ctx->d_out);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -55,6 +55,12 @@ struct GenericParams {
   const int* ghost_pdeg[6];     // [face element] its finest-level degree (face penalty)
   const long* ghost_troff[6];   // [face element] offset (pairs) of its traces in ghost_tr[f]
   const double2* ghost_tr[6];
+  // face metadata of every element (generic_face_table): [element][2 dim][fslots]; non-conforming 2-D meshes: two intersections per
+  // side (fslots = 2) and the sub-face couplings of the tangential bases (tables.hpp: Pnc_eo, Pnc_ee)
+  const FaceInfo* finfo;
+  int fslots;
+  const double* Pnc_eo;
+  const double* Pnc_ee;
 };
 
 __host__ __device__ __forceinline__ int ipow_d(int b, int e) { int r = 1; for (int i = 0; i < e; i++) r *= b; return r; }
@@ -129,19 +135,6 @@ __global__ void __launch_bounds__(kTraceThreads) k_face_traces(const __grid_cons
 }
 
 // ---- pass 2: the element kernel ------------------------------------------------------------------------------------------------
-// Per-face metadata of an element (computed once by 2*DIM threads per element, read by all its threads).
-struct FaceInfo {
-  double nuk;    // nu * kappa_d: outward normal sign of the face times prod_{d' != d} h_d' / h_d
-  double cpen;   // sigma * max(p-,p+)^2 (ipdgoperator.hh:129-131) or sigma p^2 on a Dirichlet face (:310)
-  long tro;      // offset (pairs) of the neighbour's traces on the shared face
-  short mode;    // 0 natural boundary: no face term (ipdgoperator.hh:97-105); 1 Dirichlet boundary (weight 1, :357);
-                 // 2 neighbour of the same degree; 3 neighbour of another degree (tangential L2 projection)
-  short po;      // neighbour degree
-  short ghost;   // neighbour lives on another rank: traces from the ghost layer of brick face f
-  short pad;
-};
-static_assert(sizeof(FaceInfo) == 32, "FaceInfo layout");
-
 // 1-D tables of the bucket's degree, passed by value (constant bank)
 template <int N1> struct GenTab { double MinvS[N1 * N1], M[N1 * N1], mt[2][N1], mg[2][N1], g[2][N1]; };
 
@@ -171,9 +164,13 @@ __device__ __forceinline__ void generic_element_pass(const GenericParams& P, con
   // per-element shared memory: su (block), sw (accumulator), face info, stage-1 projections (der / val) of the mixed faces
   auto SU = [&](int el) { return sm_all + (size_t)el * per_elem; };
   auto SW = [&](int el) { return SU(el) + ne; };
-  auto FI = [&](int el) { return reinterpret_cast<FaceInfo*>(SW(el) + ne); };
-  auto TD = [&](int el, int f) { return SW(el) + ne + 4 * nfaces + (size_t)(2 * f) * maxtmp; };
+  const int fslots = P.fslots;
+  auto FI = [&](int el) { return reinterpret_cast<FaceInfo*>(SW(el) + ne); };   // [face][slot]
+  auto TD = [&](int el, int f) { return SW(el) + ne + 4 * nfaces * fslots + (size_t)(2 * f) * maxtmp; };
   auto TV = [&](int el, int f) { return TD(el, f) + maxtmp; };
+  // non-conforming 2-D meshes: the element's own (der, val) traces of its 4 sides, [face][node][2] (the coarse side of a hanging
+  // face mixes its face nodes); shares the place of the 3-D projection scratch
+  auto OT = [&](int el, int f) { return SW(el) + ne + 4 * nfaces * fslots + (size_t)f * 2 * N1; };
 
   // ---- phase 0: load the blocks (coalesced), face metadata -------------------------------------------------------------
   for (int t = tid; t < nel * ne; t += nthr) {
@@ -181,39 +178,10 @@ __device__ __forceinline__ void generic_element_pass(const GenericParams& P, con
     const long e = P.elist[P.ebegin + first + el];
     SU(el)[i] = __ldg(P.x + P.off[e] + i);
   }
-  for (int t = tid; t < nel * nfaces; t += nthr) {
-    const int el = t / nfaces, f = t % nfaces, d = f / 2, s = f % 2;
+  for (int t = tid; t < nel * nfaces * fslots; t += nthr) {
+    const int el = t / (nfaces * fslots), q = t % (nfaces * fslots);
     const long e = P.elist[P.ebegin + first + el];
-    long r = e; int ijk[3];
-    ijk[0] = (int)(r % P.n[0]); r /= P.n[0]; ijk[1] = (int)(r % P.n[1]); r /= P.n[1]; ijk[2] = (int)r;
-    const int c = ijk[d] + (s ? 1 : -1);
-    FaceInfo F;
-    double kappa = 1.0 / P.h[d];
-    for (int dd = 0; dd < DIM; dd++) if (dd != d) kappa *= P.h[dd];
-    F.nuk = s ? kappa : -kappa;
-    F.po = pe; F.tro = 0; F.ghost = 0; F.pad = 0;
-    if (c >= 0 && c < P.n[d]) {
-      const long stride = d == 0 ? 1 : d == 1 ? P.n[0] : (long)P.n[0] * P.n[1];
-      const long o = e + (s ? stride : -stride);
-      F.po = (short)P.deg[o];
-      F.tro = P.troff[o] + (long)(2 * d + (1 - s)) * ipow_d(F.po + 1, DIM - 1);
-      const int pm = max(P.pdeg[e], P.pdeg[o]);
-      F.cpen = P.sigma * (double)pm * pm;
-      F.mode = F.po == pe ? 2 : 3;
-    } else if (P.bnd_is_rank[f]) {
-      // face elements of a brick face are numbered with the lower tangential direction fastest
-      const int ta = d == 0 ? 1 : 0, tb = d == 2 ? 1 : 2;
-      const long fe = ijk[ta] + (long)P.n[ta] * (DIM == 3 ? ijk[tb] : 0);
-      F.ghost = 1;
-      F.po = (short)P.ghost_deg[f][fe]; F.tro = P.ghost_troff[f][fe];
-      const int pm = max(P.pdeg[e], P.ghost_pdeg[f][fe]);
-      F.cpen = P.sigma * (double)pm * pm;
-      F.mode = F.po == pe ? 2 : 3;
-    } else {
-      F.cpen = P.sigma * (double)P.pdeg[e] * P.pdeg[e];
-      F.mode = P.dirichlet ? 1 : 0;
-    }
-    FI(el)[f] = F;
+    FI(el)[q] = P.finfo[(size_t)e * nfaces * fslots + q];
   }
   __syncthreads();
 
@@ -225,7 +193,7 @@ __device__ __forceinline__ void generic_element_pass(const GenericParams& P, con
     if (lact) {
 #pragma unroll 1
       for (int f = 0; f < nfaces; f++) {
-        const FaceInfo F = FI(lel)[f];
+        const FaceInfo F = FI(lel)[f * fslots];
         if (F.mode != 3) continue;
         const int no1 = F.po + 1;
         const double* __restrict__ Pm = P.P + ((size_t)pe * (kMaxP + 1) + F.po) * kMaxN * kMaxN;
@@ -234,6 +202,7 @@ __device__ __forceinline__ void generic_element_pass(const GenericParams& P, con
         for (int q = line; q < N1 * no1; q += nf) {
           const int i = q % N1, b = q / N1;
           double a0 = 0, a1 = 0;
+#pragma unroll 4
           for (int a = 0; a < no1; a++) {
             const double pv = __ldg(Pm + i * kMaxN + a);
             const double2 rv = F.ghost ? __ldcg(raw + a + no1 * b) : __ldg(raw + a + no1 * b);
@@ -241,6 +210,23 @@ __device__ __forceinline__ void generic_element_pass(const GenericParams& P, con
           }
           td[q] = a0; tv[q] = a1;
         }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- non-conforming 2-D meshes: the own traces of the element's four sides, for the coarse side of hanging faces ------------
+  if (DIM == 2 && fslots == 2) {
+    if (lact) {
+      const double* su = SU(lel);
+#pragma unroll
+      for (int d = 0; d < DIM; d++) {
+        const int base = line_base_c<DIM, N1>(d, line), sd = line_stride_c<N1>(d);
+        double d0 = 0, d1 = 0;
+#pragma unroll
+        for (int k = 0; k < N1; k++) { const double v = su[base + k * sd]; d0 = fma(T.g[0][k], v, d0); d1 = fma(T.g[1][k], v, d1); }
+        OT(lel, 2 * d)[2 * line] = d0; OT(lel, 2 * d)[2 * line + 1] = su[base];
+        OT(lel, 2 * d + 1)[2 * line] = d1; OT(lel, 2 * d + 1)[2 * line + 1] = su[base + (N1 - 1) * sd];
       }
     }
     __syncthreads();
@@ -259,9 +245,35 @@ __device__ __forceinline__ void generic_element_pass(const GenericParams& P, con
 #pragma unroll
       for (int s = 0; s < 2; s++) {
         const int f = 2 * d + s;
-        const FaceInfo F = FI(lel)[f];
+        const FaceInfo F = FI(lel)[f * fslots];
         double a = 0, b = 0;
-        if (F.mode != 0) {
+        if (DIM == 2 && (F.kind == 1 || F.kind == 2)) {
+          // coarse side of a hanging face (sfipdg.hh:472-491): one intersection per half of this side, each with its own fine
+          // neighbour and penalty.  Face-node fields are L2 projections on the side: own terms through (M^ee)^-1 M^ee_half, the
+          // neighbour's through (M^ee)^-1 M^eo_half; |F| = h_t / 2 doubles the penalty weight, h_n^o = h_n / 2 its derivative.
+          for (int slot = 0; slot < 2; slot++) {
+            const FaceInfo G = FI(lel)[f * fslots + slot];
+            if (G.mode < 2) continue;
+            const int no1 = G.po + 1, hk = G.kind - 1;
+            const double* __restrict__ Pee = P.Pnc_ee + ((size_t)hk * (kMaxP + 1) + pe) * kMaxN * kMaxN + line * kMaxN;
+            const double* __restrict__ Peo = P.Pnc_eo + (((size_t)hk * (kMaxP + 1) + pe) * (kMaxP + 1) + G.po) * kMaxN * kMaxN + line * kMaxN;
+            const double* __restrict__ own = OT(lel, f);
+            const double2* __restrict__ raw = P.tr + G.tro;
+            double sa = 0, sb = 0;
+            for (int j = 0; j < N1; j++) {
+              const double pv = __ldg(Pee + j), De = own[2 * j], Ve = own[2 * j + 1];
+              sa = fma(pv, fma(-0.5 * G.nuk, De, 2.0 * G.cpen * Ve), sa);
+              sb = fma(pv, -0.5 * G.nuk * Ve, sb);
+            }
+            for (int a2 = 0; a2 < no1; a2++) {
+              const double pv = __ldg(Peo + a2);
+              const double2 rv = __ldg(raw + a2);
+              sa = fma(pv, fma(-0.5 * G.nuk, 2.0 * rv.x, -2.0 * G.cpen * rv.y), sa);
+              sb = fma(pv, 0.5 * G.nuk * rv.y, sb);
+            }
+            a += sa; b += sb;
+          }
+        } else if (F.mode != 0) {
           double der = 0;
 #pragma unroll
           for (int k = 0; k < N1; k++) der = fma(T.g[s][k], v[k], der);
@@ -277,17 +289,23 @@ __device__ __forceinline__ void generic_element_pass(const GenericParams& P, con
               nd = rv.x; nv = rv.y;
             } else {
               const int no1 = F.po + 1;
-              const double* __restrict__ Pm = P.P + ((size_t)pe * (kMaxP + 1) + F.po) * kMaxN * kMaxN;
+              // fine side of a hanging face (kind 3 / 4): the whole own side against half of the coarse neighbour's side
+              const double* __restrict__ Pm = (DIM == 2 && F.kind >= 3)
+                  ? P.Pnc_eo + (((size_t)(F.kind - 1) * (kMaxP + 1) + pe) * (kMaxP + 1) + F.po) * kMaxN * kMaxN
+                  : P.P + ((size_t)pe * (kMaxP + 1) + F.po) * kMaxN * kMaxN;
               nd = 0; nv = 0;
               if (DIM == 2) {
+#pragma unroll 4
                 for (int a2 = 0; a2 < no1; a2++) {
                   const double pv = __ldg(Pm + line * kMaxN + a2);
                   const double2 rv = F.ghost ? __ldcg(raw + a2) : __ldg(raw + a2);
                   nd = fma(pv, rv.x, nd); nv = fma(pv, rv.y, nv);
                 }
+                if (F.kind >= 3) nd *= 0.5;   // h_n^o = 2 h_n: the neighbour's reference derivative in this element's scaling
               } else {
                 const int i = line % N1, j = line / N1;
                 const double* __restrict__ td = TD(lel, f); const double* __restrict__ tv = TV(lel, f);
+#pragma unroll 4
                 for (int b2 = 0; b2 < no1; b2++) {
                   const double pv = __ldg(Pm + j * kMaxN + b2);
                   nd = fma(pv, td[i + N1 * b2], nd); nv = fma(pv, tv[i + N1 * b2], nv);
@@ -360,7 +378,7 @@ __device__ __forceinline__ void generic_element_pass(const GenericParams& P, con
   {
     constexpr int n2 = N1 * N1;
     double* sM = sm_all + (size_t)epc * per_elem;                                // [n2] 1-D mass (one copy per CTA)
-    auto SD = [&](int el, int d) { return SW(el) + ne + 4 * nfaces + (mixed && DIM == 3 ? 2 * nfaces * maxtmp : 0) + d * n2; };
+    auto SD = [&](int el, int d) { return SW(el) + ne + 4 * nfaces * fslots + (mixed && DIM == 3 ? 2 * nfaces * maxtmp : (fslots == 2 ? 2 * nfaces * N1 : 0)) + d * n2; };
     auto SC = [&](int el) { return SD(el, DIM); };                               // [ne] correction
     for (int t = tid; t < n2; t += nthr) sM[t] = T.M[t];
     for (int t = tid; t < nel * DIM * n2; t += nthr) {
@@ -370,7 +388,7 @@ __device__ __forceinline__ void generic_element_pass(const GenericParams& P, con
       for (int dd = 0; dd < DIM; dd++) if (dd != d) kap *= P.h[dd];
       double v = kap * DT.S[i * kMaxN + j];
       for (int s = 0; s < 2; s++) {
-        const FaceInfo F = FI(el)[2 * d + s];
+        const FaceInfo F = FI(el)[(2 * d + s) * fslots];
         if (F.mode == 0) continue;
         const double wgt = F.mode == 1 ? 1.0 : 0.5;
         v += -wgt * F.nuk * (DT.t[s][i] * DT.g[s][j] + DT.g[s][i] * DT.t[s][j]) + F.cpen * DT.t[s][i] * DT.t[s][j];
@@ -460,6 +478,7 @@ int generic_trace_setup(Ctx* ctx, Level& L) {
   std::vector<long> troff(L.nelem + 1, 0);
   for (long e = 0; e < L.nelem; e++) troff[e + 1] = troff[e] + 2 * L.dim * ipow_d(L.deg[e] + 1, L.dim - 1);
   L.tr_pairs = troff[L.nelem];
+  L.troff_h = troff;
   HPDG_CUDA(cudaMalloc(&L.d_troff, sizeof(long) * (L.nelem + 1)));
   HPDG_CUDA(cudaMemcpy(L.d_troff, troff.data(), sizeof(long) * (L.nelem + 1), cudaMemcpyHostToDevice));
   HPDG_CUDA(cudaMalloc(&L.d_tr, sizeof(double) * 2 * std::max<long>(L.tr_pairs, 1)));
@@ -471,6 +490,73 @@ int generic_trace_setup(Ctx* ctx, Level& L) {
     HPDG_CUDA(cudaMemcpyToSymbol(c_end_g, g, sizeof(g)));
     HPDG_CUDA(cudaMemcpyToSymbol(c_end_t, t, sizeof(t)));
     ctx->end_tables_set = true;
+  }
+  return 0;
+}
+
+// The level's face table: FaceInfo of every (element, side, intersection), built once on the host.  Structured meshes: one
+// intersection per side, the neighbour from the lexicographic element index; rank-boundary sides of a distributed level point
+// into the ghost layer (degrees exchanged once, hp_ghost_setup).  Non-conforming meshes: the table comes from the mesh builder
+// (api.cu: hpdg_create_refined_2d), only the trace offsets are filled in here.
+int generic_face_table(Ctx* ctx, Level& L) {
+  if (L.d_finfo) return 0;
+  if (generic_trace_setup(ctx, L)) return 1;
+  const int dim = L.dim, nfaces = 2 * dim;
+  L.fslots = L.nc ? 2 : 1;
+  std::vector<FaceInfo> tab((size_t)L.nelem * nfaces * L.fslots);
+  if (L.nc) {
+    tab = L.nc_faces;
+    for (long e = 0; e < L.nelem; e++) for (int q = 0; q < nfaces * 2; q++) {
+      FaceInfo& F = tab[(size_t)e * nfaces * 2 + q];
+      const long o = L.nc_nbr[(size_t)e * nfaces * 2 + q];
+      if (F.mode >= 2 && o >= 0) F.tro = L.troff_h[o] + (long)((q / 2) ^ 1) * ipow_d(L.deg[o] + 1, dim - 1);
+    }
+  } else {
+    for (long e = 0; e < L.nelem; e++) {
+      long r = e; int ijk[3];
+      ijk[0] = (int)(r % L.n[0]); r /= L.n[0]; ijk[1] = (int)(r % L.n[1]); r /= L.n[1]; ijk[2] = (int)r;
+      const int pe = L.deg[e];
+      for (int f = 0; f < nfaces; f++) {
+        const int d = f / 2, s = f % 2;
+        const int c = ijk[d] + (s ? 1 : -1);
+        FaceInfo F;
+        double kappa = 1.0 / L.h[d];
+        for (int dd = 0; dd < dim; dd++) if (dd != d) kappa *= L.h[dd];
+        F.nuk = s ? kappa : -kappa;
+        F.po = (short)pe; F.tro = 0; F.ghost = 0; F.kind = 0;
+        if (c >= 0 && c < L.n[d]) {
+          const long stride = d == 0 ? 1 : d == 1 ? L.n[0] : (long)L.n[0] * L.n[1];
+          const long o = e + (s ? stride : -stride);
+          F.po = (short)L.deg[o];
+          F.tro = L.troff_h[o] + (long)(2 * d + (1 - s)) * ipow_d(F.po + 1, dim - 1);
+          const int pm = std::max(L.pdeg[e], L.pdeg[o]);
+          F.cpen = ctx->sigma * (double)pm * pm;
+          F.mode = F.po == pe ? 2 : 3;
+        } else if (ctx->nranks > 1 && ctx->bnd_is_rank[f]) {
+          // face elements of a brick face are numbered with the lower tangential direction fastest
+          const int ta = d == 0 ? 1 : 0, tb = d == 2 ? 1 : 2;
+          const long fe = ijk[ta] + (long)L.n[ta] * (dim == 3 ? ijk[tb] : 0);
+          F.ghost = 1;
+          F.po = (short)L.hpg.h_deg[f][fe]; F.tro = L.hpg.h_troff[f][fe];
+          const int pm = std::max(L.pdeg[e], L.hpg.h_pdeg[f][fe]);
+          F.cpen = ctx->sigma * (double)pm * pm;
+          F.mode = F.po == pe ? 2 : 3;
+        } else {
+          F.cpen = ctx->sigma * (double)L.pdeg[e] * L.pdeg[e];
+          F.mode = ctx->dirichlet ? 1 : 0;
+        }
+        tab[(size_t)e * nfaces + f] = F;
+      }
+    }
+  }
+  HPDG_CUDA(cudaMalloc(&L.d_finfo, sizeof(FaceInfo) * tab.size()));
+  HPDG_CUDA(cudaMemcpy(L.d_finfo, tab.data(), sizeof(FaceInfo) * tab.size(), cudaMemcpyHostToDevice));
+  if (L.nc && !ctx->d_Pnc_eo) {
+    const HostTables& H = host_tables();
+    HPDG_CUDA(cudaMalloc(&ctx->d_Pnc_eo, sizeof(double) * H.Pnc_eo.size()));
+    HPDG_CUDA(cudaMemcpy(ctx->d_Pnc_eo, H.Pnc_eo.data(), sizeof(double) * H.Pnc_eo.size(), cudaMemcpyHostToDevice));
+    HPDG_CUDA(cudaMalloc(&ctx->d_Pnc_ee, sizeof(double) * H.Pnc_ee.size()));
+    HPDG_CUDA(cudaMemcpy(ctx->d_Pnc_ee, H.Pnc_ee.data(), sizeof(double) * H.Pnc_ee.size(), cudaMemcpyHostToDevice));
   }
   return 0;
 }
@@ -546,7 +632,9 @@ int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double 
     }
     maxno1 = std::max(maxno1, L.hpg.maxp + 1);
   }
-  const int mixed = (!L.uniform || ctx->nranks > 1) ? 1 : 0;
+  const int mixed = (!L.uniform || ctx->nranks > 1 || L.nc) ? 1 : 0;
+  if (generic_face_table(ctx, L)) return 1;
+  P.finfo = L.d_finfo; P.fslots = L.fslots; P.Pnc_eo = ctx->d_Pnc_eo; P.Pnc_ee = ctx->d_Pnc_ee;
   // ---- pass 2: the degree buckets write disjoint rows of y: side streams, so that small buckets overlap the large ones ----
   const size_t nb = L.bucket_p.size();
   const bool fork = nb > 1;
@@ -571,7 +659,7 @@ int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double 
     const int p = L.bucket_p[b], n1 = p + 1;
     const int ne = ipow_d(n1, L.dim), nf = ipow_d(n1, L.dim - 1);
     const int nfaces = 2 * L.dim;
-    const int per_elem = 2 * ne + 4 * nfaces + ((mixed && L.dim == 3) ? 2 * nfaces * n1 * maxno1 : 0);
+    const int per_elem = 2 * ne + 4 * nfaces * L.fslots + ((mixed && L.dim == 3) ? 2 * nfaces * n1 * maxno1 : (L.nc ? 2 * nfaces * n1 : 0));
     P.ebegin = L.bucket_begin[b];
     // elements per CTA: ~128 line threads, at most 48 KB of shared memory
     int epc = nf >= 128 ? 1 : 128 / nf;
@@ -665,6 +753,9 @@ int blockgs_mf_iterate(Ctx* ctx, Level& L, const double* b, double* x) {
   if (launch_face_traces(ctx, L, x, ctx->stream)) return 1;   // traces of the incoming iterate; the sweep keeps them current
   P.troff = L.d_troff; P.tr = reinterpret_cast<const double2*>(L.d_tr);
   for (int f = 0; f < 6; f++) { P.bnd_is_rank[f] = 0; P.ghost_deg[f] = P.ghost_pdeg[f] = nullptr; P.ghost_troff[f] = nullptr; P.ghost_tr[f] = nullptr; }
+  if (L.nc) { ctx->err = "matrix-free block Gauss-Seidel: not available on non-conforming meshes"; return 1; }
+  if (generic_face_table(ctx, L)) return 1;
+  P.finfo = L.d_finfo; P.fslots = L.fslots; P.Pnc_eo = ctx->d_Pnc_eo; P.Pnc_ee = ctx->d_Pnc_ee;
   GsParams G; G.b = b; G.x = x; G.tr = reinterpret_cast<double2*>(L.d_tr);
   const int maxno1 = L.maxp + 1;
   const int mixed = L.uniform ? 0 : 1;

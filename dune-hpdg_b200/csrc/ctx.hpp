@@ -51,7 +51,23 @@ struct HpGhost {
   long* d_send_dst[6] = {};      // [nface + 1] offsets (pairs) in d_send[f]
   long send_pairs[6] = {}, recv_pairs[6] = {};
   std::vector<int> h_deg[6], h_pdeg[6];   // host copies of the ghost degrees (block-Jacobi setup)
+  std::vector<long> h_troff[6];           // host copy of d_troff
 };
+
+// Per-face metadata of an element in the generic hp kernel (apply_generic.cu); built once per level on the host.
+struct FaceInfo {
+  double nuk;    // nu * kappa_d: outward normal sign of the face times prod_{d' != d} h_d' / h_d
+  double cpen;   // sigma * max(p-,p+)^2 (ipdgoperator.hh:129-131) or sigma p^2 on a Dirichlet face (:310)
+  long tro;      // offset (pairs) of the neighbour's traces on the shared face
+  short mode;    // -1 unused slot; 0 natural boundary: no face term (ipdgoperator.hh:97-105); 1 Dirichlet boundary (weight 1,
+                 // :357); 2 neighbour of the same degree; 3 neighbour of another degree (tangential L2 projection)
+  short po;      // neighbour degree
+  short ghost;   // neighbour lives on another rank: traces from the ghost layer of brick face f
+  short kind;    // non-conforming meshes: 0 conforming intersection; 1 / 2 this element is the coarse side and the
+                 // intersection covers the low / high half of its side; 3 / 4 it is the fine side on the low / high half of the
+                 // neighbour's side (sfipdg.hh:472-491)
+};
+static_assert(sizeof(FaceInfo) == 32, "FaceInfo layout");
 
 struct JacobiDense {
   bool ready = false;
@@ -100,6 +116,13 @@ struct Level {
   HpGhost hpg;    // distributed hp: ghost degrees / trace buffers of this level
   // hp apply: face traces (der, val) of every element, written once per apply by k_face_traces (apply_generic.cu)
   long* d_troff = nullptr;      // [nelem+1] offset (in pairs) of an element's traces; face f at troff[e] + f * N_e^(dim-1)
+  std::vector<long> troff_h;    // host copy
+  FaceInfo* d_finfo = nullptr;  // [nelem][2 dim][fslots] face metadata of the generic kernel (built on first use)
+  int fslots = 1;               // intersections per element side: 1, or 2 on a non-conforming mesh
+  // non-conforming 2-D mesh (one level of refinement, hpdg_create_refined_2d): leaf elements in base-cell order, children x-fastest
+  bool nc = false;
+  std::vector<FaceInfo> nc_faces;   // host: [nelem][4][2], tro still relative (filled in by generic_face_table)
+  std::vector<long> nc_nbr;         // host: [nelem][4][2] neighbour element of the intersection (-1: none)
   double* d_tr = nullptr;       // [2 * tr_pairs]
   long tr_pairs = 0;
   // matrix-free block Gauss-Seidel: elements sorted by (hyperplane ix+iy+iz, degree bucket); segment k = w * buckets + b
@@ -132,6 +155,7 @@ struct Ctx {
   double* d_P = nullptr;
   double* d_T = nullptr;
   double* d_Mab = nullptr;
+  double *d_Pnc_eo = nullptr, *d_Pnc_ee = nullptr;   // non-conforming face couplings (tables.hpp), uploaded on first use
   std::vector<Level> levels;  // [0] coarsest ... back() finest (reference: multigrid_impl.hh:19-20)
   std::string err;
   // distributed brick
@@ -182,6 +206,7 @@ int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double 
 int launch_face_traces(Ctx* ctx, Level& L, const double* x, cudaStream_t stream);  // every element's own face traces -> L.d_tr
 int launch_hp_pack(Ctx* ctx, Level& L, cudaStream_t stream);   // rank-boundary traces of L.d_tr -> L.hpg.d_send[f]
 int generic_trace_setup(Ctx* ctx, Level& L);                   // allocates L.d_troff / L.d_tr on first use
+int generic_face_table(Ctx* ctx, Level& L);                    // builds L.d_finfo on first use (after the ghost setup of a distributed level)
 int hp_ghost_setup(Ctx* ctx, Level& L);                        // (api.cu) one-time exchange of the neighbour degrees across rank boundaries
 int hp_halo_exchange(Ctx* ctx, Level& L);                      // (api.cu) pack + NCCL send/recv of the rank-boundary face traces
 // returns -1 if (dim, degree) has no specialised kernel

@@ -183,6 +183,44 @@ HostTables build() {
     for (int i = 0; i < nb; i++) for (int j = 0; j < na; j++)
       T[i * kMaxN + j] = (a == b) ? (double)(i == j) : (double)lag(a, nodes[a], j, nodes[b][i]);
   }
+  // non-conforming faces: sub-interval coupling of the tangential 1-D bases, exact 20-point Gauss quadrature on the sub-face
+  H.Pnc_eo.assign((size_t)4 * ND * ND * kMaxN * kMaxN, 0.0);
+  H.Pnc_ee.assign((size_t)2 * ND * kMaxN * kMaxN, 0.0);
+  for (int k = 0; k < 4; k++) for (int a = 0; a < ND; a++) for (int b = 0; b < ND; b++) {
+    const int na = a + 1, nb = b + 1;
+    ld Meo[kMaxN * kMaxN];
+    for (int i = 0; i < na; i++) for (int j = 0; j < nb; j++) {
+      ld m = 0;
+      for (int q = 0; q < kQ; q++) {
+        const ld t = qx[q];   // sub-face coordinate in [0,1]
+        ld te, to, w;         // the two sides' tangential coordinates, d tau_e / dt
+        if (k < 2) { te = (t + k) / 2; to = t; w = (ld)0.5; } else { te = t; to = (t + (k - 2)) / 2; w = 1; }
+        m += qw[q] * w * lag(a, nodes[a], i, te) * lag(b, nodes[b], j, to);
+      }
+      Meo[i * nb + j] = m;
+    }
+    double* P = &H.Pnc_eo[(((size_t)k * ND + a) * ND + b) * kMaxN * kMaxN];
+    for (int i = 0; i < na; i++) for (int j = 0; j < nb; j++) {
+      ld s = 0;
+      for (int l = 0; l < na; l++) s += Minv[a][i * na + l] * Meo[l * nb + j];
+      P[i * kMaxN + j] = (double)s;
+    }
+  }
+  for (int k = 0; k < 2; k++) for (int a = 0; a < ND; a++) {
+    const int na = a + 1;
+    ld Mee[kMaxN * kMaxN];
+    for (int i = 0; i < na; i++) for (int j = 0; j < na; j++) {
+      ld m = 0;
+      for (int q = 0; q < kQ; q++) { const ld te = (qx[q] + k) / 2; m += qw[q] * (ld)0.5 * lag(a, nodes[a], i, te) * lag(a, nodes[a], j, te); }
+      Mee[i * na + j] = m;
+    }
+    double* P = &H.Pnc_ee[((size_t)k * ND + a) * kMaxN * kMaxN];
+    for (int i = 0; i < na; i++) for (int j = 0; j < na; j++) {
+      ld s = 0;
+      for (int l = 0; l < na; l++) s += Minv[a][i * na + l] * Mee[l * na + j];
+      P[i * kMaxN + j] = (double)s;
+    }
+  }
   return H;
 }
 }  // namespace

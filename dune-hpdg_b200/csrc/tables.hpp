@@ -42,6 +42,14 @@ struct HostTables {
   std::vector<double> T;
   // rectangular mass M^{ab}
   std::vector<double> Mab;
+  // Non-conforming (hanging-node) faces, one level of refinement (reference: sfipdg.hh:472-491 evaluates both sides' 1-D bases at
+  // the sub-face's mapped quadrature points).  tau = tangential reference coordinate of element e (degree a) on its side, the
+  // sub-face covers I subset [0,1]; the neighbour o (degree b) sees it as tau_o(tau).
+  //   Pnc_eo[((k*(kMaxP+1)+a)*(kMaxP+1)+b)*kMaxN*kMaxN + i*kMaxN + j] = ((M^{aa})^-1 int_I l^a_i(tau) l^b_j(tau_o(tau)) dtau)_{ij}
+  //     k = 0 / 1: e is the COARSE side, I = [0,1/2] / [1/2,1], tau_o = 2 tau - {0,1}
+  //     k = 2 / 3: e is the FINE side on the low / high half of o's side, I = [0,1], tau_o = (tau + {0,1}) / 2
+  //   Pnc_ee[(k*(kMaxP+1)+a)*kMaxN*kMaxN + i*kMaxN + j] = ((M^{aa})^-1 int_I l^a_i l^a_j dtau)_{ij}, k = 0 / 1 (coarse side halves)
+  std::vector<double> Pnc_eo, Pnc_ee;
 };
 
 const HostTables& host_tables();
