@@ -80,6 +80,7 @@ int setup_level(Ctx* ctx, Level& L, int dim, const int* n, const double* h, cons
   L.dim = dim;
   L.nelem = 1;
   for (int d = 0; d < 3; d++) { L.n[d] = d < dim ? n[d] : 1; L.h[d] = d < dim ? h[d] : 1.0; L.nelem *= L.n[d]; }
+  if (L.nc) L.nelem = (long)deg.size();   // non-conforming mesh: the leaf elements of the refined base grid
   L.deg = deg; L.pdeg = pdeg;
   L.off.assign(L.nelem + 1, 0);
   L.maxp = 0;
@@ -90,6 +91,7 @@ int setup_level(Ctx* ctx, Level& L, int dim, const int* n, const double* h, cons
     if (deg[e] != deg[0] || pdeg[e] != pdeg[0]) uni = false;
   }
   L.ndof = L.off[L.nelem];
+  if (L.nc) uni = false;   // only the generic element pass knows hanging faces
   L.uniform = uni; L.p_uni = uni ? deg[0] : -1; L.pen_uni = uni ? pdeg[0] : -1;
   // buckets by degree (stable counting sort)
   std::vector<long> cnt(kMaxP + 2, 0);
@@ -157,6 +159,7 @@ int create_common(Ctx* ctx, int dim, const int* n, const double* Lx, const std::
   double h[3] = {1, 1, 1};
   for (int d = 0; d < dim; d++) h[d] = Lx[d] / n[d];
   ctx->levels.resize(1);
+  ctx->levels[0].nc = ctx->create_nc;
   return setup_level(ctx, ctx->levels[0], dim, n, h, deg, deg);
 }
 
@@ -491,6 +494,78 @@ int hpdg_create(hpdg_ctx** out, int dim, const int* n, const double* L, const in
   return 0;
 }
 
+// Non-conforming 2-D mesh (reference: the hanging-node branch of SumFactIPDGOperator, sfipdg.hh:213-222,472-491): the
+// base grid with the flagged cells split once into 2 x 2 children.  Builds the leaf numbering and, per (leaf, side), its one or
+// two intersections: neighbour leaf, kind (conforming / coarse side half / fine side), penalty max(p-, p+)^2, normal sign * kappa.
+int hpdg_create_refined_2d(hpdg_ctx** out, const int* n, const double* L, const unsigned char* refine, const int* degree,
+                           long nleaf, double sigma, int dirichlet, int device) {
+  *out = nullptr;
+  if (n[0] < 1 || n[1] < 1) { g_create_err = "mesh extents must be positive"; return 1; }
+  const long ncell = (long)n[0] * n[1];
+  std::vector<long> first(ncell + 1, 0);
+  for (long c = 0; c < ncell; c++) first[c + 1] = first[c] + (refine[c] ? 4 : 1);
+  if (nleaf != first[ncell]) { g_create_err = "degree array must have one entry per leaf element (unrefined cells + 4 per refined cell)"; return 1; }
+  std::vector<int> deg(nleaf);
+  for (long e = 0; e < nleaf; e++) {
+    deg[e] = degree[e];
+    if (deg[e] < 0 || deg[e] > kMaxP) { g_create_err = "polynomial degree out of range 0..13"; return 1; }
+  }
+  hpdg_ctx* ctx = new hpdg_ctx();
+  ctx->create_nc = true;
+  if (create_common(ctx, 2, n, L, deg, sigma, dirichlet, device)) { g_create_err = ctx->err; delete ctx; return 1; }
+  Level& Lv = ctx->levels[0];
+  const double h[2] = {L[0] / n[0], L[1] / n[1]};
+  Lv.nc_faces.assign((size_t)nleaf * 8, FaceInfo());
+  Lv.nc_nbr.assign((size_t)nleaf * 8, -1);
+  auto set_face = [&](long e, int f, int slot, long o, int kind) {
+    const int d = f / 2, s = f % 2;
+    FaceInfo F;
+    const double kappa = d == 0 ? h[1] / h[0] : h[0] / h[1];   // h_t / h_n: the same for a cell and its children
+    F.nuk = s ? kappa : -kappa; F.tro = 0; F.ghost = 0; F.kind = (short)kind; F.po = (short)deg[e];
+    if (o >= 0) {
+      F.po = (short)deg[o];
+      const int pm = std::max(deg[e], deg[o]);
+      F.cpen = sigma * (double)pm * pm;
+      F.mode = (kind == 0 && deg[o] == deg[e]) ? 2 : 3;
+    } else if (o == -1) {
+      F.cpen = sigma * (double)deg[e] * deg[e];
+      F.mode = dirichlet ? 1 : 0;
+    } else { F.cpen = 0; F.mode = -1; }   // o == -2: unused second slot
+    Lv.nc_faces[(size_t)e * 8 + f * 2 + slot] = F;
+    Lv.nc_nbr[(size_t)e * 8 + f * 2 + slot] = o;
+  };
+  for (int cy = 0; cy < n[1]; cy++) for (int cx = 0; cx < n[0]; cx++) {
+    const long c = cx + (long)n[0] * cy;
+    for (int f = 0; f < 4; f++) {
+      const int d = f / 2, s = f % 2;
+      const int ox = cx + (d == 0 ? (s ? 1 : -1) : 0), oy = cy + (d == 1 ? (s ? 1 : -1) : 0);
+      const bool inside = ox >= 0 && ox < n[0] && oy >= 0 && oy < n[1];
+      const long oc = inside ? ox + (long)n[0] * oy : -1;
+      // child (a, b) of a refined cell is leaf first[cell] + a + 2 b; the children of the neighbour cell that touch the shared face
+      // have normal index (s ? 0 : 1); their tangential index t selects the half of the face
+      auto nb_child = [&](int t) { return first[oc] + (d == 0 ? (s ? 0 : 1) + 2 * t : t + 2 * (s ? 0 : 1)); };
+      if (!refine[c]) {
+        const long e = first[c];
+        if (!inside) { set_face(e, f, 0, -1, 0); set_face(e, f, 1, -2, 0); }
+        else if (!refine[oc]) { set_face(e, f, 0, first[oc], 0); set_face(e, f, 1, -2, 0); }
+        else { set_face(e, f, 0, nb_child(0), 1); set_face(e, f, 1, nb_child(1), 2); }   // coarse side: low / high half
+      } else {
+        for (int b = 0; b < 2; b++) for (int a = 0; a < 2; a++) {
+          const long e = first[c] + a + 2 * b;
+          const int nrm = d == 0 ? a : b, tng = d == 0 ? b : a;   // the child's index normal / tangential to the face
+          set_face(e, f, 1, -2, 0);
+          if (nrm != s) set_face(e, f, 0, first[c] + (d == 0 ? (1 - a) + 2 * b : a + 2 * (1 - b)), 0);   // sibling
+          else if (!inside) set_face(e, f, 0, -1, 0);
+          else if (refine[oc]) set_face(e, f, 0, nb_child(tng), 0);
+          else set_face(e, f, 0, first[oc], 3 + tng);   // fine side on the low / high half of the coarse neighbour's side
+        }
+      }
+    }
+  }
+  *out = ctx;
+  return 0;
+}
+
 int hpdg_nccl_unique_id(void* out128) {
   std::string err;
   if (!load_nccl(err)) { g_create_err = err; return 1; }
@@ -660,6 +735,7 @@ int hpdg_level_degrees(const hpdg_ctx* ctx, int level, int* degree) {
 
 int hpdg_build_p_hierarchy(hpdg_ctx* ctx) {
   HPDG_ENTER(ctx);
+  if (ctx->levels.back().nc) { ctx->err = "p-hierarchy: not available on non-conforming meshes (operator apply only)"; return 1; }
   if (ctx->levels.size() != 1) { ctx->err = "hierarchy already built"; return 1; }
   Level fine = ctx->levels[0];
   const int pmax = fine.maxp;

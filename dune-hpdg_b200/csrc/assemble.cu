@@ -165,6 +165,7 @@ __global__ void k_gscore_update(const long* __restrict__ rowptr, const int* __re
 }
 
 int bcrs_build(Ctx* ctx, Level& L) {
+  if (L.nc) { ctx->err = "not available on non-conforming meshes (operator apply only)"; return 1; }
   Bcrs& A = L.bcrs;
   if (A.ready) return 0;
   const long ne = L.nelem;

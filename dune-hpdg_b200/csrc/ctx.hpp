@@ -160,6 +160,7 @@ struct Ctx {
   std::string err;
   // distributed brick
   int rank = 0, nranks = 1;
+  bool create_nc = false;        // set by hpdg_create_refined_2d before the first level is set up
   bool hp_distributed = false;   // created with a per-element degree array: every level takes the generic hp path
   int pgrid[3] = {1, 1, 1}, pcoord[3] = {0, 0, 0};
   bool bnd_is_rank[6] = {false, false, false, false, false, false};

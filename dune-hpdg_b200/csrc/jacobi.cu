@@ -159,6 +159,7 @@ static BlkParams make_blk(Ctx* ctx, Level& L) {
 }
 
 int jacobi_setup_dense(Ctx* ctx, Level& L) {
+  if (L.nc) { ctx->err = "not available on non-conforming meshes (operator apply only)"; return 1; }
   if (L.jd.ready) return 0;
   if (ctx->nranks > 1 && &L == &ctx->levels.back()) {
     // neighbour penalty degrees across ranks are uniform in the distributed path, so the blocks
@@ -225,6 +226,7 @@ int jacobi_apply_dense(Ctx* ctx, Level& L, const double* r, double* c, double da
 }
 
 int diag_block_device(Ctx* ctx, Level& L, long e, double* d_out) {
+  if (L.nc) { ctx->err = "not available on non-conforming meshes (operator apply only)"; return 1; }
   // single-element variant of k_build_blocks through a one-entry element list
   int* d_one = nullptr;
   int ei = (int)e;
@@ -309,6 +311,7 @@ __global__ void k_jacobi_fd(FDParams P) {
 static int jacobi_build_fd_generic(Ctx* ctx, Level& L);
 
 int jacobi_setup_fd(Ctx* ctx, Level& L) {
+  if (L.nc) { ctx->err = "not available on non-conforming meshes (operator apply only)"; return 1; }
   if (L.jf.ready) return 0;
   // uniform-degree 3-D levels use the tiled kernel (jacobi_uniform.cu) whose 1-D factors live in its parameter block
   if (!uniform_supported(ctx, L)) { if (jacobi_build_fd_generic(ctx, L)) return 1; }

@@ -38,6 +38,7 @@ SIGNATURES = {
                                           _ip, C.c_int, C.c_int, C.c_void_p]),
     "hpdg_create_distributed_hp": (C.c_int, [C.POINTER(_vp), C.c_int, _ip, _dp, _ip, C.c_double, C.c_int, C.c_int,
                                              _ip, C.c_int, C.c_int, C.c_void_p]),
+    "hpdg_create_refined_2d": (C.c_int, [C.POINTER(_vp), _ip, _dp, C.c_void_p, _ip, C.c_long, C.c_double, C.c_int, C.c_int]),
     "hpdg_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "hpdg_halo_ipc_handle": (C.c_int, [_vp, C.c_void_p]),
     "hpdg_halo_ipc_attach": (C.c_int, [_vp, C.c_void_p]),
@@ -169,6 +170,28 @@ class Context:
             self._h = None
             raise HpdgError(msg)
         self.n = n
+
+    @classmethod
+    def refined_2d(cls, n, refine, degree, L=None, sigma=2.0, dirichlet=True, device=0):
+        """Non-conforming 2-D mesh: the base grid `n` with the cells flagged in `refine` (x fastest) split once into 2 x 2 children
+        (hpdg_create_refined_2d); `degree` holds one entry per leaf element (base-cell order, children x fastest)."""
+        self = cls.__new__(cls)
+        self._h = _vp()
+        self.dim = 2
+        nn = np.ascontiguousarray(n, dtype=np.int32)
+        LL = np.ascontiguousarray(L if L is not None else [1.0, 1.0], dtype=np.float64)
+        rf = np.ascontiguousarray(refine, dtype=np.uint8)
+        assert rf.size == int(nn[0]) * int(nn[1])
+        nleaf = int(rf.size + 3 * np.count_nonzero(rf))
+        deg = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(degree), (nleaf,)) if np.size(degree) == 1 else degree, dtype=np.int32)
+        rc = lib().hpdg_create_refined_2d(C.byref(self._h), nn, LL, rf.ctypes.data_as(C.c_void_p), deg, deg.size, sigma,
+                                          int(dirichlet), device)
+        if rc:
+            msg = lib().hpdg_last_error(None).decode()
+            self._h = None
+            raise HpdgError(msg)
+        self.n = nn
+        return self
 
     def halo_ipc_handle(self):
         buf = C.create_string_buffer(64)

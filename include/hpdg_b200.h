@@ -51,6 +51,14 @@ int hpdg_create(hpdg_ctx** out, int dim, const int* n, const double* L, const in
 int hpdg_create_distributed(hpdg_ctx** out, int dim, const int* n, const double* L, int degree, double sigma,
                             int dirichlet, int device, const int* pgrid, int rank, int nranks,
                             const void* nccl_id);
+/* Non-conforming 2-D mesh (hanging nodes; reference: the non-conforming branch of SumFactIPDGOperator,
+ * matrix-free/localoperators/sfipdg.hh:213-222,472-491): the n[0] x n[1] base grid with the cells flagged in refine[] (x fastest,
+ * 0 / 1) split once into 2 x 2 children.  Leaf elements are numbered base cell by base cell (x fastest), the four children of a
+ * refined cell x fastest; degree[] and every vector hold one entry / block per leaf in that order.  Available on such a context:
+ * the operator apply (hpdg_op_apply*, accumulate forms, BLAS-1); smoothers, assembly and the p-hierarchy report an error. */
+int hpdg_create_refined_2d(hpdg_ctx** ctx, const int* n, const double* L, const unsigned char* refine, const int* degree,
+                           long nleaf, double sigma, int dirichlet, int device);
+
 /* The same with a per-element degree map of the LOCAL brick (x-fastest element order): the hp mesh partitioned element-wise over the
  * ranks.  The degrees of the elements across every rank-boundary face are exchanged once (parallel/updatedegrees.hh:11-46); per
  * apply the rank-boundary face traces -- variable-size blocks per element, cf. parallel/communicationhpdg.hh:309-326,387-418 --

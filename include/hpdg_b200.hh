@@ -65,6 +65,13 @@ class Context {
           int device = 0) {
     check(hpdg_create(&h_, dim, n, L, degree.data(), (long)degree.size(), sigma, dirichlet ? 1 : 0, device), nullptr);
   }
+  // non-conforming 2-D mesh: base grid n with the flagged cells split once into 2 x 2 children (hanging nodes; the grid the
+  // reference's non-conforming branch sees, sfipdg.hh:213-222); one degree per leaf element
+  struct Refined2D {};
+  Context(Refined2D, const int* n, const double* L, const std::vector<unsigned char>& refine, const std::vector<int>& degree,
+          double sigma = 2.0, bool dirichlet = false, int device = 0) {
+    check(hpdg_create_refined_2d(&h_, n, L, refine.data(), degree.data(), (long)degree.size(), sigma, dirichlet ? 1 : 0, device), nullptr);
+  }
   Context(const Context&) = delete;
   Context& operator=(const Context&) = delete;
   ~Context() { hpdg_destroy(h_); }

@@ -182,3 +182,151 @@ class SumFactIPDG2D:
                 y[self.off[o]:self.off[o + 1]] += factor * oloc.ravel()
             y[self.off[e]:self.off[e + 1]] += factor * loc.ravel()
         return y
+
+
+class RefinedSumFactIPDG2D:
+    """The same operator on a NON-CONFORMING mesh: the base grid with the flagged cells split once into 2 x 2 children, hanging
+    nodes on faces between a refined and an unrefined cell.  Follows the non-conforming branch of the reference's computeFace
+    (sfipdg.hh:213-222: `if (not is.conforming())` the 1-D values / derivatives of BOTH sides are re-evaluated at the rule points
+    mapped through geometryInInside / geometryInOutside, nonConformingMatrices :472-491; penalty sigma max(p)^2 / |intersection|
+    :227-229; each side's own inverse Jacobian :251-252,262-270).  Leaf elements: base cell by base cell (x fastest), the four
+    children of a refined cell x fastest -- the numbering of hpdg_create_refined_2d.  Intersections are found geometrically."""
+
+    def __init__(self, n, refine, degree, L=(1.0, 1.0), sigma=2.0, dirichlet=True):
+        self.n = tuple(int(v) for v in n)
+        hx, hy = L[0] / self.n[0], L[1] / self.n[1]
+        refine = np.asarray(refine).astype(bool).ravel()
+        self.leaves = []   # (x0, y0, hx, hy)
+        for c in range(self.n[0] * self.n[1]):
+            cx, cy = c % self.n[0], c // self.n[0]
+            if not refine[c]:
+                self.leaves.append((cx * hx, cy * hy, hx, hy))
+            else:
+                for b in range(2):
+                    for a in range(2):
+                        self.leaves.append((cx * hx + a * hx / 2, cy * hy + b * hy / 2, hx / 2, hy / 2))
+        ne = len(self.leaves)
+        self.deg = np.full(ne, degree, dtype=int) if np.isscalar(degree) else np.asarray(degree, dtype=int).copy()
+        assert len(self.deg) == ne
+        self.sigma, self.dirichlet, self.Ldom = sigma, dirichlet, (L[0], L[1])
+        self.off = np.concatenate(([0], np.cumsum((self.deg + 1) ** 2)))
+        self.ndof = int(self.off[-1])
+        self._sf = SumFactIPDG2D((1, 1))   # table cache and the edge helpers
+        # intersections (e, f, o, s0, s1): side f of e against the opposite side of o, overlap [s0, s1] in physical coordinates
+        self.inter, self.bnd = [], []
+        eps = 1e-12 * max(L)
+        for e, (x0, y0, ex, ey) in enumerate(self.leaves):
+            for f in range(4):
+                d, s = f // 2, f % 2
+                pos = (x0 + s * ex) if d == 0 else (y0 + s * ey)            # the side's normal coordinate
+                t0, t1 = (y0, y0 + ey) if d == 0 else (x0, x0 + ex)         # its tangential extent
+                if abs(pos - (self.Ldom[d] if s else 0.0)) < eps:
+                    self.bnd.append((e, f))
+                    continue
+                for o, (u0, v0, ox, oy) in enumerate(self.leaves):
+                    opos = (u0 + (1 - s) * ox) if d == 0 else (v0 + (1 - s) * oy)
+                    if o == e or abs(opos - pos) > eps:
+                        continue
+                    q0, q1 = (v0, v0 + oy) if d == 0 else (u0, u0 + ox)
+                    a, b = max(t0, q0), min(t1, q1)
+                    if b - a > eps:
+                        self.inter.append((e, f, o, a, b))
+
+    def _tang(self, e, f, a, b, m):
+        """1-D values / derivatives of element e's tangential basis at the m rule points of the intersection [a, b]
+        (nonConformingMatrices, sfipdg.hh:472-491: rule points mapped into the element)"""
+        x0, y0, ex, ey = self.leaves[e]
+        t0, ht = (y0, ey) if f < 2 else (x0, ex)
+        xq, wq = gauss_lobatto(m)
+        tau = (a + (b - a) * xq - t0) / ht
+        return lagrange_tables(int(self.deg[e]), tau) + (wq,)
+
+    def _grad(self, C, p, f, V, D):
+        _, _, _, Dn = self._sf._tab(p, p + 2)
+        end = 0 if f % 2 == 0 else -1
+        ec = SumFactIPDG2D._edge_coeffs(C, f)
+        if f < 2:
+            return (C @ Dn[:, end]) @ V, ec @ D
+        return ec @ D, (Dn[:, end] @ C) @ V
+
+    def _dphi(self, out, p, f, V, D, X, u):
+        _, _, Vn, Dn = self._sf._tab(p, p + 2)
+        end = 0 if f % 2 == 0 else -1
+        if f < 2:
+            out += np.outer(V @ (X[0] * u), Dn[:, end]) + np.outer(D @ (X[1] * u), Vn[:, end])
+        else:
+            out += np.outer(Dn[:, end], V @ (X[1] * u)) + np.outer(Vn[:, end], D @ (X[0] * u))
+
+    def apply(self, x, factor=1.0):
+        y = np.zeros(self.ndof)
+        blk = lambda v, e: v[self.off[e]:self.off[e + 1]].reshape(self.deg[e] + 1, self.deg[e] + 1)
+        for e, (x0, y0, hx, hy) in enumerate(self.leaves):   # computeBulk (:111-166)
+            p = int(self.deg[e])
+            C = blk(x, e)
+            xq, wq, V, D = self._sf._tab(p, p + 2)
+            dx = np.einsum('ba,aq,br->rq', C, D, V)
+            dy = np.einsum('ba,aq,br->rq', C, V, D)
+            W = np.outer(wq, wq) * hx * hy
+            loc = np.einsum('rq,aq,br->ba', dx * W / hx ** 2, D, V) + np.einsum('rq,aq,br->ba', dy * W / hy ** 2, V, D)
+            y[self.off[e]:self.off[e + 1]] += factor * loc.ravel()
+        for e, f in self.bnd:                                  # computeDirichletBoundaryEdge (:329-393)
+            if not self.dirichlet:
+                continue
+            x0, y0, hx, hy = self.leaves[e]
+            p = int(self.deg[e])
+            d, s = f // 2, f % 2
+            flen = hy if d == 0 else hx
+            nrm = np.zeros(2)
+            nrm[d] = 1.0 if s else -1.0
+            jinv = np.array([1.0 / hx, 1.0 / hy])
+            xq, wq, V, D = self._sf._tab(p, p + 2)
+            C = blk(x, e)
+            loc = np.zeros_like(C)
+            fac = wq * flen
+            u = (SumFactIPDG2D._edge_coeffs(C, f) @ V) * fac
+            d0, d1 = self._grad(C, p, f, V, D)
+            du = (d0 * jinv[0] * nrm[0] + d1 * jinv[1] * nrm[1]) * fac
+            self._dphi(loc, p, f, V, D, -np.outer(jinv * nrm, np.ones(len(wq))), u)
+            SumFactIPDG2D._add_edge(loc, -(V @ du), f)
+            SumFactIPDG2D._add_edge(loc, V @ (u * self.sigma * p ** 2 / flen), f)
+            y[self.off[e]:self.off[e + 1]] += factor * loc.ravel()
+        for e, f, o, a, b in self.inter:                       # computeFace (:168-326), once per intersection (:196)
+            if e < o:
+                continue
+            p, po, fo = int(self.deg[e]), int(self.deg[o]), f ^ 1
+            m = max(p, po) + 2
+            V, D, wq = self._tang(e, f, a, b, m)
+            Vo, Do, _ = self._tang(o, fo, a, b, m)
+            d, s = f // 2, f % 2
+            nrm = np.zeros(2)
+            nrm[d] = 1.0 if s else -1.0
+            ji = np.array([1.0 / self.leaves[e][2], 1.0 / self.leaves[e][3]])
+            jo = np.array([1.0 / self.leaves[o][2], 1.0 / self.leaves[o][3]])
+            flen = b - a
+            C, Co = blk(x, e), blk(x, o)
+            loc, oloc = np.zeros_like(C), np.zeros_like(Co)
+            fac = wq * flen
+            u = (SumFactIPDG2D._edge_coeffs(C, f) @ V - SumFactIPDG2D._edge_coeffs(Co, fo) @ Vo) * fac
+            d0i, d1i = self._grad(C, p, f, V, D)
+            d0o, d1o = self._grad(Co, po, fo, Vo, Do)
+            # the tangential derivative tables are d/dtau: the chain rule of the sub-face map is already in tau's definition
+            du = ((d0i * ji[0] + d0o * jo[0]) * nrm[0] + (d1i * ji[1] + d1o * jo[1]) * nrm[1]) * fac * 0.5
+            ones = np.ones(len(wq))
+            self._dphi(loc, p, f, V, D, -0.5 * np.outer(ji * nrm, ones), u)
+            self._dphi(oloc, po, fo, Vo, Do, -0.5 * np.outer(jo * nrm, ones), u)
+            pen = self.sigma * max(p, po) ** 2 / flen
+            SumFactIPDG2D._add_edge(loc, -(V @ du) + V @ (u * pen), f)
+            SumFactIPDG2D._add_edge(oloc, Vo @ du - Vo @ (u * pen), fo)
+            y[self.off[e]:self.off[e + 1]] += factor * loc.ravel()
+            y[self.off[o]:self.off[o + 1]] += factor * oloc.ravel()
+        return y
+
+    def interpolate(self, fn):
+        """nodal interpolation of fn(x, y) (qkgllocalinterpolation.hh:56-74: point evaluation at the GL nodes)"""
+        v = np.zeros(self.ndof)
+        for e, (x0, y0, hx, hy) in enumerate(self.leaves):
+            p = int(self.deg[e])
+            nodes = gauss_lobatto(p + 1)[0] if p > 0 else np.array([0.5])
+            X, Y = np.meshgrid(x0 + hx * nodes, y0 + hy * nodes)   # [i1][i0]
+            v[self.off[e]:self.off[e + 1]] = fn(X, Y).ravel()
+        return v

@@ -100,6 +100,38 @@ def test_2d_against_gauss_lobatto_sumfactorised_formulation(orc, hp, dirichlet):
     assert rel(y, s.apply(x)) < TOL
 
 
+@pytest.mark.parametrize("dirichlet", [True, False])
+def test_nonconforming_hanging_node_mesh(orc, hp, dirichlet):
+    # f-4: non-conforming faces (matrix-free/localoperators/sfipdg.hh:213-222,472-491).  A base grid with some cells split once
+    # (hanging nodes between refined and unrefined cells), per-leaf degree 1..5, against the oracle's restatement of the
+    # reference's non-conforming branch (oracle/sf2d.py: RefinedSumFactIPDG2D); also uniform degree, a single refined cell
+    # (testdgrestrict.cc-style one-refinement mesh), everything refined, and the entry points that must refuse such a mesh.
+    from oracle import sf2d
+    rng = np.random.default_rng(17)
+    cases = []
+    ref = np.zeros(20, dtype=np.uint8); ref[[1, 6, 7, 12, 18]] = 1
+    cases.append(((5, 4), ref, (1.0, 1.5), None))
+    one = np.zeros(9, dtype=np.uint8); one[4] = 1
+    cases.append(((3, 3), one, (1.0, 1.0), 2))
+    cases.append(((2, 3), np.ones(6, dtype=np.uint8), (2.0, 1.0), None))
+    edge = np.zeros(8, dtype=np.uint8); edge[[0, 3, 4]] = 1      # refined cells on the domain boundary and in a corner
+    cases.append(((4, 2), edge, (1.0, 1.0), 3))
+    for n, ref, L, p in cases:
+        nleaf = int(ref.size + 3 * ref.sum())
+        deg = rng.integers(1, 6, nleaf).astype(np.int32) if p is None else np.full(nleaf, p, dtype=np.int32)
+        o = sf2d.RefinedSumFactIPDG2D(n, ref, deg, L, 2.0, dirichlet)
+        ctx = hp.Context.refined_2d(n, ref, deg, L=L, sigma=2.0, dirichlet=dirichlet)
+        assert ctx.dimension() == o.ndof and np.array_equal(ctx.block_offsets(), o.off)
+        x = rng.standard_normal(o.ndof)
+        y = hp.Operator(ctx, factor=0.5).apply(x)
+        assert rel(y, o.apply(x, 0.5)) < TOL
+        with pytest.raises(hp.HpdgError):
+            hp.BlockJacobi(ctx, form=hp.JACOBI_DENSE)
+        with pytest.raises(hp.HpdgError):
+            ctx.build_p_hierarchy()
+        ctx.close()
+
+
 @pytest.mark.parametrize("dim,n", [(2, (7, 5)), (3, (4, 3, 5))])
 @pytest.mark.parametrize("dirichlet", [True, False])
 def test_hp_random_degrees(orc, hp, dim, n, dirichlet):
