@@ -59,6 +59,7 @@ struct GenericParams {
   // side (fslots = 2) and the sub-face couplings of the tangential bases (tables.hpp: Pnc_eo, Pnc_ee)
   const FaceInfo* finfo;
   int fslots;
+  int tpe;   // threads per element of this launch (>= N1^(dim-1))
   const double* Pnc_eo;
   const double* Pnc_ee;
 };
@@ -185,12 +186,16 @@ __device__ __forceinline__ void generic_element_pass(const GenericParams& P, con
   }
   __syncthreads();
 
-  const int lel = tid / nf, line = tid % nf;       // (element in CTA, DoF line / face node)
-  const bool lact = lel < nel;
+  // threads per element: nf (one per DoF line), or a full warp for the low degrees of a 3-D mixed-degree level, whose tangential
+  // projections (up to 2 x 6 x N1 x 14 x 14 FMAs per element) would otherwise be serialised over 4 or 9 threads
+  const int tpe = P.tpe;
+  const int lel = tid / tpe, line = tid % tpe;     // (element in CTA, DoF line / face node)
+  const bool pact = lel < nel;                     // the thread belongs to an element of this CTA
+  const bool lact = pact && line < nf;             // ... and owns a DoF line
 
   // ---- phase 1 (3-D, mixed-degree faces): stage 1 of the tangential projection, tmp[i + N1 b] = sum_a P[i][a] raw[a + No b] ----
   if (DIM == 3 && mixed) {
-    if (lact) {
+    if (pact) {
 #pragma unroll 1
       for (int f = 0; f < nfaces; f++) {
         const FaceInfo F = FI(lel)[f * fslots];
@@ -199,7 +204,7 @@ __device__ __forceinline__ void generic_element_pass(const GenericParams& P, con
         const double* __restrict__ Pm = P.P + ((size_t)pe * (kMaxP + 1) + F.po) * kMaxN * kMaxN;
         const double2* __restrict__ raw = (F.ghost ? P.ghost_tr[f] : P.tr) + F.tro;
         double* __restrict__ td = TD(lel, f); double* __restrict__ tv = TV(lel, f);
-        for (int q = line; q < N1 * no1; q += nf) {
+        for (int q = line; q < N1 * no1; q += tpe) {
           const int i = q % N1, b = q / N1;
           double a0 = 0, a1 = 0;
 #pragma unroll 4
@@ -661,13 +666,15 @@ int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double 
     const int nfaces = 2 * L.dim;
     const int per_elem = 2 * ne + 4 * nfaces * L.fslots + ((mixed && L.dim == 3) ? 2 * nfaces * n1 * maxno1 : (L.nc ? 2 * nfaces * n1 : 0));
     P.ebegin = L.bucket_begin[b];
-    // elements per CTA: ~128 line threads, at most 48 KB of shared memory
-    int epc = nf >= 128 ? 1 : 128 / nf;
+    // elements per CTA: ~128 threads, at most 48 KB of shared memory
+    const int tpe = (mixed && L.dim == 3 && nf < 32) ? 32 : nf;
+    P.tpe = tpe;
+    int epc = tpe >= 128 ? 1 : 128 / tpe;
     epc = (int)std::max<long>(1, std::min<long>(epc, (48 * 1024) / ((long)per_elem * 8)));
     epc = (int)std::min<long>(epc, cnt);
     const size_t smem_l = (size_t)epc * per_elem * sizeof(double);
     const unsigned grid = (unsigned)((cnt + epc - 1) / epc);
-    const int threads = std::max(32, (epc * nf + 31) / 32 * 32);
+    const int threads = std::max(32, (epc * tpe + 31) / 32 * 32);
     const DegTable& HT = host_tables().deg[p];
 #define HPDG_GEN_LAUNCH(D, NN)                                                                                            \
   do {                                                                                                                    \
@@ -769,12 +776,14 @@ int blockgs_mf_iterate(Ctx* ctx, Level& L, const double* b, double* x) {
       const int per_elem = 2 * ne + 4 * nfaces + ((mixed && L.dim == 3) ? 2 * nfaces * n1 * maxno1 : 0);
       const int per_elem_gs = per_elem + L.dim * n1 * n1 + ne;
       P.ebegin = begin;
-      int epc = nf >= 128 ? 1 : 128 / nf;
+      const int tpe = (mixed && L.dim == 3 && nf < 32) ? 32 : nf;
+      P.tpe = tpe;
+      int epc = tpe >= 128 ? 1 : 128 / tpe;
       epc = (int)std::max<long>(1, std::min<long>(epc, (48 * 1024) / ((long)per_elem_gs * 8)));
       epc = (int)std::min<long>(epc, cnt);
       const size_t smem_l = ((size_t)epc * per_elem_gs + n1 * n1) * sizeof(double);
       const unsigned grid = (unsigned)((cnt + epc - 1) / epc);
-      const int threads = std::max(32, (epc * nf + 31) / 32 * 32);
+      const int threads = std::max(32, (epc * tpe + 31) / 32 * 32);
       if (threads > 1024) { ctx->err = "matrix-free block Gauss-Seidel: degree too high for one CTA per element"; return 1; }
       const DegTable& HT = host_tables().deg[p];
 #define HPDG_GS_LAUNCH(D, NN)                                                                                             \

@@ -113,3 +113,30 @@ for tag, nn in (("cfg4small", 64), ("cfg4", 128)):
              gdofs=nd / ms / 1e6, first_call_s=ts, levels=[ctx.dimension(l) for l in range(ctx.num_levels)],
              launches_per_cycle=(ctx.launch_count - l0) // 6)
         ctx.close()
+if "blockgs" in which:
+    # the reference's default smoother without a matrix: one DynamicBlockGS sweep (hyperplane wavefronts) at cfg2 size
+    for n, p in (((64, 64, 64), 3), ((32, 32, 32), 4)):
+        ctx = hp.Context(n, degree=p)
+        nd = ctx.dimension()
+        dx, db = ctx.upload(np.zeros(nd)), ctx.upload(rng.standard_normal(nd))
+        gs = hp.MatrixFreeBlockGS(ctx)
+        l0 = ctx.launch_count
+        gs.iterate_device(dx, db)
+        nl = ctx.launch_count - l0
+        ms = timed(ctx, lambda: gs.iterate_device(dx, db), 3)
+        emit(config=f"matrix-free block-GS sweep {n[0]}^3 Q{p} (hyperplane wavefronts, generic element pass)", ndof=nd, ms=ms,
+             gdofs=nd / ms / 1e6, launches_per_sweep=nl)
+        ctx.close()
+if "nc" in which:
+    # non-conforming 2-D mesh: 256 x 256 base grid, every other cell in a checkerboard refined once, Q3
+    nb = 256
+    ref = ((np.add.outer(np.arange(nb), np.arange(nb)) % 2) == 0).astype(np.uint8).ravel()
+    nleaf = int(ref.size + 3 * ref.sum())
+    ctx = hp.Context.refined_2d((nb, nb), ref, np.full(nleaf, 3, dtype=np.int32))
+    nd = ctx.dimension()
+    dx, dy = ctx.upload(rng.standard_normal(nd)), ctx.vec_alloc()
+    op = hp.Operator(ctx)
+    ms = timed(ctx, lambda: op.apply_device(dx, dy, sync=False), a.reps)
+    emit(config="non-conforming 2D 256^2 base grid, checkerboard refined once, Q3: apply (generic kernel, hanging faces)", ndof=nd,
+         leaves=nleaf, us=ms * 1e3, gdofs=nd / ms / 1e6)
+    ctx.close()
