@@ -365,15 +365,19 @@ int mg_smooth(Ctx* ctx, int l, const VC& v, int steps, double* x, double* r) {
     return 0;
   }
   for (int i = 0; i < steps; i++) {                                   // multigrid_impl.hh:76-81
-    // smoother(tmp1, r); x += tmp1 -- fused into the Jacobi kernel (one pass instead of a kernel + an axpy)
-    ctx->fuse_xacc = x;
+    // smoother(tmp1, r); x += tmp1 -- no separate axpy: on uniform levels the update rides on the operator kernel that applies
+    // tmp1 next (those kernels are issue bound, the extra 16 B/DoF are free: measured 10.4 -> 8.1 -> ... ms per 64^3 cycle,
+    // DESIGN.md section 6a), otherwise it is fused into the Jacobi kernel
+    const bool in_apply = ctx->xacc_in_apply && uniform_supported(ctx, L);
+    if (!in_apply) ctx->fuse_xacc = x;
     int rc = jacobi_async(ctx, L, v.form, r, L.mg_t1, v.damping);
     ctx->fuse_xacc = nullptr;
     if (rc) return 1;
     // tmp2 = A tmp1; r -= tmp2 -- fused: r = r + (-1) * A tmp1 in the operator kernel's store
     ctx->fuse_accum = 1;
+    if (in_apply) ctx->fuse_xin = x;
     rc = op_apply_async(ctx, L, L.mg_t1, r, -1.0);
-    ctx->fuse_accum = 0;
+    ctx->fuse_accum = 0; ctx->fuse_xin = nullptr;
     if (rc) return 1;
   }
   return 0;
@@ -704,6 +708,7 @@ int hpdg_set_option(hpdg_ctx* ctx, const char* name, long value) {
   HPDG_ENTER(ctx);
   if (!strcmp(name, "force_generic")) { ctx->force_generic = (int)value; return 0; }
   if (!strcmp(name, "variant")) { ctx->variant = (int)value; return 0; }
+  if (!strcmp(name, "xacc_in_apply")) { ctx->xacc_in_apply = (int)value; return 0; }
   if (!strcmp(name, "q3p_grid")) { ctx->q3p_grid = (int)value; return 0; }
   if (!strcmp(name, "q3p_tune")) { ctx->q3p_tune = (int)value; return 0; }
   if (!strcmp(name, "halo_timeout_ms")) { ctx->halo_timeout_cycles = (long long)value * 2000000LL; return 0; }  // ~2 GHz SM clock

@@ -69,6 +69,13 @@ __device__ __forceinline__ void tile_body(const UniParams<N>& P, double* __restr
     const int node = zi + N * zj;
     double v[TZ][N];
     const int zbase = (zex + TX * zey) * EP + node;
+    if (P.xin_acc) {   // V-cycle: x += c fused into the apply of c (same coalesced access pattern as the loads of this pass)
+#pragma unroll
+      for (int e = 0; e < TZ; e++)
+#pragma unroll
+        for (int k = 0; k < N; k++)
+          if (FULL || e < lenz) { const long g = ecol + (long)(z0 + e) * sz + node + N2 * k; P.xin_acc[g] += __ldg(X + g); }
+    }
 #pragma unroll
     for (int e = 0; e < TZ; e++)
 #pragma unroll
@@ -329,7 +336,7 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
   P.ghost_step = (finest && ctx->ghost.p2p && part == 3) ? ctx->ghost.step : 0;
   P.ghost_err = ctx->ghost.p2p ? reinterpret_cast<int*>(ctx->ghost.arena + ctx->ghost.flag_off) + 12 : nullptr;
   P.ghost_err_host = ctx->d_ghost_err; P.ghost_timeout = ctx->halo_timeout_cycles;
-  P.x = x; P.y = y; P.part = part; P.accum = ctx->fuse_accum;
+  P.x = x; P.y = y; P.part = part; P.accum = ctx->fuse_accum; P.xin_acc = ctx->fuse_xin;
   P.tile_list = nullptr; P.tile_offset = 0; P.tile_rot = 0;
   long nlist = 0;
   if (part == 3) {

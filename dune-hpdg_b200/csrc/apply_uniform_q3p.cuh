@@ -280,6 +280,13 @@ hpdg_k_apply_q3_persist(const __grid_constant__ hpdg::UniParams<4> P, const int4
 #pragma unroll
         for (int k = 0; k < 4; k++) v[e][k] = su[zcol + 1024 * e + 16 * k + zq];
       __syncwarp();
+      if (P.xin_acc) {   // V-cycle: x += c fused into the apply of c
+        double* __restrict__ xa = P.xin_acc + (colp - X);
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) xa[(long)n01 * (N3 * e) + N2 * k] += v[e][k];
+      }
       const HaloTrace h = halo_reduce<4>(P, hr);
       q3p_pencil<2>(h.pd, h.pv, h.pm, h.nd, h.nv, h.nm,
         [&](int e, double (&l)[4]) {

@@ -182,6 +182,8 @@ struct Ctx {
   // fusion requests of the V-cycle driver, consumed by the next launch:
   int fuse_accum = 0;          // apply: y = y_old + factor * A x   (r -= A c without a separate axpy)
   double* fuse_xacc = nullptr; // block Jacobi: additionally x += c
+  double* fuse_xin = nullptr;  // uniform operator apply: additionally fuse_xin += (input vector); else an axpy in front of it
+  int xacc_in_apply = 1;       // V-cycle: fuse x += c into the apply of c (uniform levels) instead of into the Jacobi kernel (option)
   std::map<const void*, int> kattr;  // kernel_slots(): kernels whose attributes are set on this context's device -> resident CTA slots
   double* d_scalar = nullptr;        // device scratch of the BLAS-1 reductions (one context = one device)
   double* d_partial = nullptr;       // per-CTA partial sums of the two-stage dot product

@@ -365,12 +365,13 @@ static int launch_q4j(Ctx* ctx, Level& L, const double* r, double* c, double dam
 int jacobi_apply_fd_uniform(Ctx* ctx, Level& L, const double* r, double* c, double damping) {
   if (!uniform_supported(ctx, L)) return -1;
   // the bulk copies / bulk stores of the persistent kernel need 16-byte aligned vectors
-  if (uniform_persistent(ctx, L, r) && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+  const bool xacc_ok = (reinterpret_cast<uintptr_t>(ctx->fuse_xacc) & 15) == 0;   // bulk reduce-add of x += c
+  if (uniform_persistent(ctx, L, r) && (reinterpret_cast<uintptr_t>(c) & 15) == 0 && xacc_ok) {
     const int rc = launch_q3j(ctx, L, r, c, damping);
     if (rc >= 0) return rc;
   }
   if (ctx->variant != 40 && L.p_uni == 4 && L.n[0] % 4 == 0 && L.n[1] % 4 == 0 && L.n[2] % 2 == 0 && L.ndof < (1L << 31) &&
-      (reinterpret_cast<uintptr_t>(r) & 15) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+      (reinterpret_cast<uintptr_t>(r) & 15) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0 && xacc_ok) {
     const int rc = launch_q4j(ctx, L, r, c, damping);
     if (rc >= 0) return rc;
   }

@@ -270,18 +270,9 @@ hpdg_k_jacobi_fd_q3_persist(const __grid_constant__ hpdg::Q3jParams P) {
 #pragma unroll
           for (int k = 0; k < 4; k++) q3j_sweep<1, false, GY>(V, a[k]);
         }
-        if (P.xacc) {
-          // V-cycle: c and x += c straight from the registers (a store instruction fills whole 32-byte sectors)
-          const long gofs = (long)(e0 + (tid >> 6) + n0 * (row & 3) + n01 * (row >> 2)) * N3 + (tid & 3);
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              P.c[gofs + 4 * j + 16 * k] = a[k][j];
-              P.xacc[gofs + 4 * j + 16 * k] += a[k][j];
-            }
-        } else {
-          // back in place, then one bulk store per element (512 B) issued by the warp that owns the element in this stage
+        {
+          // back in place, then one bulk store per element (512 B) issued by the warp that owns the element in this stage;
+          // V-cycle: additionally x += c as a bulk reduce-add of the same element (the add runs at the L2)
 #pragma unroll
           for (int k = 0; k < 4; k++)
 #pragma unroll
@@ -290,7 +281,9 @@ hpdg_k_jacobi_fd_q3_persist(const __grid_constant__ hpdg::Q3jParams P) {
           __syncwarp();
           if ((tid & 31) < 8) {  // this warp's 8 elements: x-position tid >> 6, rows 8 ((tid >> 5) & 1) + 0..7
             const int rs = (tid & 7) + 8 * ((tid >> 5) & 1), exs = tid >> 6;
-            q3p_bulk_s2g(P.c + (long)(e0 + exs + n0 * (rs & 3) + n01 * (rs >> 2)) * N3, sw + RS * rs + 64 * exs, 512u);
+            const long go = (long)(e0 + exs + n0 * (rs & 3) + n01 * (rs >> 2)) * N3;
+            q3p_bulk_s2g(P.c + go, sw + RS * rs + 64 * exs, 512u);
+            if (P.xacc) q3p_bulk_s2g_add(P.xacc + go, sw + RS * rs + 64 * exs, 512u);
           }
         }
       }

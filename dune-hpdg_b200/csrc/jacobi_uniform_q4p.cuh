@@ -248,20 +248,15 @@ hpdg_k_jacobi_fd_q4_persist(const __grid_constant__ hpdg::Q4jParams P) {
 #pragma unroll
           for (int j = 0; j < 5; j++) sw[base + 5 * j + 25 * k] = a[k][j];
       }
-      if (!P.xacc) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       __syncthreads();  // a row holds the planes of all five warps
-      if (P.xacc) {
-        // V-cycle: c and x += c, coalesced over the tile's 8 contiguous rows
-        for (int row2 = 0; row2 < 8; row2++) {
-          const long g = row_src(e0, row2);
-          for (int q = tid; q < RS; q += 160) {
-            const double v = sw[RS * row2 + q];
-            P.c[g + q] = v;
-            P.xacc[g + q] += v;
-          }
+      if (lane == 0) {
+        // one bulk store per row; V-cycle: additionally x += c as a bulk reduce-add of the same row (the add runs at the L2:
+        // no thread waits on a load of x)
+        for (int row2 = w; row2 < 8; row2 += 5) {
+          q3p_bulk_s2g(P.c + row_src(e0, row2), sw + RS * row2, 4000u);
+          if (P.xacc) q3p_bulk_s2g_add(P.xacc + row_src(e0, row2), sw + RS * row2, 4000u);
         }
-      } else if (lane == 0) {
-        for (int row2 = w; row2 < 8; row2 += 5) q3p_bulk_s2g(P.c + row_src(e0, row2), sw + RS * row2, 4000u);
       }
     };
     switch ((fl & 3 ? 1 : 0) | (fl & 12 ? 2 : 0) | (fl & 48 ? 4 : 0)) {

@@ -31,6 +31,12 @@ __device__ __forceinline__ void q3p_bulk_s2g(void* dst, const void* src, uint32_
   asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
 }
 
+// shared -> global bulk reduction dst += src (FP64 add performed at the L2), committed as this thread's own bulk group
+__device__ __forceinline__ void q3p_bulk_s2g_add(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;\n" ::"l"(dst), "r"(q3p_smem_u32(src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+
 template <int... I, class F>
 __device__ __forceinline__ void q3p_for_impl(std::integer_sequence<int, I...>, F f) { (f(std::integral_constant<int, I>{}), ...); }
 template <int N, class F>

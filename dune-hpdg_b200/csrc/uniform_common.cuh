@@ -28,6 +28,7 @@ struct UniParams {
   const double* x;
   double* y;
   int accum; // y = y_old + factor * A x
+  double* xin_acc;  // optional: xin_acc += x (the V-cycle's x += c rides on the apply of c: its first pass holds c anyway)
   int part;  // 0 all tiles, 1 only tiles not touching a ghost face, 2 only tiles touching one
   const int* tile_list;  // part != 0: compact list of the tile ids of that part (grid = list length)
   int tile_offset;       // first tile of this launch (z-slab launches of the chunked host-pointer apply)

@@ -584,6 +584,27 @@ def test_vcycle_q3_fine_level_persistent_kernel(orc, hp):
     assert rel(x, xr) < 1e-11 and rel(bb, rr) < 1e-10
 
 
+@pytest.mark.parametrize("p,n", [(4, (4, 4, 4)), (3, (8, 4, 4))])
+def test_vcycle_xacc_fusion_placements(orc, hp, p, n):
+    # x += c of the smoothing steps is fused either into the operator kernel that applies c next (default on uniform levels) or
+    # into the block-Jacobi kernel (option xacc_in_apply = 0): both must reproduce the oracle's cycle (multigrid_impl.hh:76-81)
+    fine = orc.Mesh(n, degree=p)
+    levels = [fine.coarsen(2), fine] if p == 4 else [fine.coarsen(1), fine]
+    if p == 4:
+        levels = [levels[0].coarsen(1)] + levels
+    b = orc.fill_random(fine.ndof)
+    x0 = orc.fill_random(fine.ndof, seed=3) * 0.1
+    xr, rr = orc.vcycle(levels, None, x0, b, smoother=1, damping=0.75)
+    for in_apply in (1, 0):
+        ctx = hp.Context(n, degree=p)
+        ctx.build_p_hierarchy()
+        ctx.set_option("xacc_in_apply", in_apply)
+        x, bb = x0.copy(), b.copy()
+        hp.Multigrid(ctx, form=hp.JACOBI_FD, damping=0.75).apply(x, bb)
+        assert rel(x, xr) < 1e-11 and rel(bb, rr) < 1e-10
+        ctx.close()
+
+
 def test_vcycle_with_reference_default_smoother(orc, hp):
     # the reference's own p-MG configuration (solversetup.hh:139-145,198-215): DynamicBlockGS on the Galerkin level matrices
     n = (3, 3, 3)
