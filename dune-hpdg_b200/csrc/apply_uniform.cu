@@ -378,6 +378,7 @@ static int launch_uni(Ctx* ctx, Level& L, const double* x, double* y, double fac
         }
         PK.done = ctx->d_sched + 8;
         PK.step = ctx->ghost.step;
+        PK.npack = std::max(1, (grid + 2) / 3);
       }
       hpdg_k_apply_q3_persist<<<grid, 256, kQ3pSmemBytes, stream>>>(P, static_cast<const int4*>(L.d_tile_desc), (int)ntiles, (int)ntiles_total, ctx->d_sched + 2 * (part & 3), PK);
       ctx->launches++;

@@ -137,8 +137,8 @@ __device__ __forceinline__ HaloRaw<4> q3p_halo_issue(const UniParams<4>& P, int 
   return halo_issue<4>(pm, nm, prev, next, stride, P.ghost[2 * DIR] + gidx * 2, P.ghost[2 * DIR + 1] + gidx * 2);
 }
 
-// NVLink peer-memory halo, sender side, fused into the tile kernel (multi-GPU): before their first tile all CTAs
-// together compute the brick's boundary traces -- for brick face f = (d, s) and every boundary element and face node the
+// NVLink peer-memory halo, sender side, fused into the tile kernel (multi-GPU): before their first tile the packing
+// CTAs (a third of the grid) together compute the brick's boundary traces -- for brick face f = (d, s) and every boundary element and face node the
 // pair (der, val) of the element's DoF line normal to the face at side s -- and store them straight into the neighbours'
 // arenas; the last CTA to finish raises the neighbours' step flags.  No separate pack / flag kernels, no stream joins.
 struct Q3pPack {
@@ -146,6 +146,8 @@ struct Q3pPack {
   int* flag[6];    // that neighbour's step flag for the face
   int* done;       // local counter of CTAs that have finished packing
   int step;        // 0: no packing in this launch
+  int npack;       // CTAs 0 .. npack-1 pack (a third of the grid: in launch order one per SM, so the pack of an SM's first CTA
+                   // overlaps the first tiles of its other two)
 };
 __device__ __forceinline__ void q3p_pack(const UniParams<4>& P, const Q3pPack& K) {
   const double* __restrict__ x = P.x;
@@ -157,7 +159,7 @@ __device__ __forceinline__ void q3p_pack(const UniParams<4>& P, const Q3pPack& K
     const int d = f >> 1, sd = f & 1;
     const int na = d == 0 ? n1 : n0, nb = d == 2 ? n1 : n2;  // face element extents (low dim fastest)
     const int total = na * nb * 16;
-    for (int t = blockIdx.x * 256 + threadIdx.x; t < total; t += gridDim.x * 256) {
+    for (int t = blockIdx.x * 256 + threadIdx.x; t < total; t += K.npack * 256) {
       const int node = t & 15, fe = t >> 4;
       const int a = fe % na, b = fe / na;
       const int pp = node & 3, q = node >> 2;
@@ -173,9 +175,10 @@ __device__ __forceinline__ void q3p_pack(const UniParams<4>& P, const Q3pPack& K
       reinterpret_cast<double2*>(out)[t] = make_double2(der, sd ? u3 : u0);
     }
   }
-  __threadfence_system();
+  // release: the CTA's peer stores are ordered before thread 0's system-scope fence by the barrier (cumulativity), that fence
+  // before its count; the last packing CTA acquires every count before it raises the flags
   __syncthreads();
-  if (threadIdx.x == 0 && atomicAdd(K.done, 1) == (int)gridDim.x - 1) {
+  if (threadIdx.x == 0 && (__threadfence_system(), atomicAdd(K.done, 1)) == K.npack - 1) {
     __threadfence_system();
     for (int f = 0; f < 6; f++)
       if (K.flag[f]) *reinterpret_cast<volatile int*>(K.flag[f]) = K.step;
@@ -226,9 +229,9 @@ hpdg_k_apply_q3_persist(const __grid_constant__ hpdg::UniParams<4> P, const int4
   __syncthreads();
   int t = blockIdx.x;
   if (t >= ntiles) return;
-  if (PK.step > 0) q3p_pack(P, PK);
   int4 td = descriptor(t);
-  prefetch(threadIdx.x, td.x);
+  prefetch(threadIdx.x, td.x);   // the first tile's copies are in flight while the CTA packs
+  if (PK.step > 0 && (int)blockIdx.x < PK.npack) q3p_pack(P, PK);
   uint32_t phase = 0;
 
   for (;;) {
