@@ -82,6 +82,43 @@ def face_traces(x_local, n, p, f, g_end):
     return np.ascontiguousarray(np.stack([der, val], axis=-1).reshape(-1))
 
 
+# ---- distributed hp: the layout contract of the variable-size halo (csrc/api.cu: hp_ghost_setup / hp_halo_exchange) ----------------
+def face_elements(n, f):
+    """local indices of the brick's elements on face f = 2*dir+side, lower tangential direction fastest (the face-element numbering of
+    the ghost layer)"""
+    d, s = f // 2, f % 2
+    idx = np.arange(n[0] * n[1] * n[2]).reshape(n[2], n[1], n[0])
+    sl = [slice(None)] * 3
+    sl[2 - d] = n[d] - 1 if s else 0
+    return np.ascontiguousarray(idx[tuple(sl)].reshape(-1))
+
+
+def hp_halo_offsets(face_degrees, dim=3):
+    """offsets (in (der, val) pairs) of the variable-size trace blocks of a face's elements: block i holds (p_i + 1)^(dim-1) pairs;
+    the receiver builds them from the degrees it got in the one-time degree exchange (parallel/updatedegrees.hh:11-46)"""
+    return np.concatenate(([0], np.cumsum((np.asarray(face_degrees) + 1) ** (dim - 1))))
+
+
+def hp_face_traces(x_local, offsets, degrees, n, f, g_end_of):
+    """(der, val) traces the rank SENDS across brick face f for a per-element degree map: the face elements' blocks in
+    face-element order, each [face node (lower tangential index fastest)][2].  g_end_of(p)[s] = l_i'(s) of degree p."""
+    d, s = f // 2, f % 2
+    out = []
+    for e in face_elements(n, f):
+        p = int(degrees[e])
+        N = p + 1
+        blk = x_local[offsets[e]:offsets[e + 1]].reshape(N, N, N)          # [k][j][i]
+        g = g_end_of(p)[s]
+        if d == 0:
+            der, val = np.einsum("kji,i->kj", blk, g), blk[:, :, N - 1 if s else 0]
+        elif d == 1:
+            der, val = np.einsum("kji,j->ki", blk, g), blk[:, N - 1 if s else 0, :]
+        else:
+            der, val = np.einsum("kji,k->ji", blk, g), blk[N - 1 if s else 0]
+        out.append(np.stack([der, val], axis=-1).reshape(-1))
+    return np.ascontiguousarray(np.concatenate(out))
+
+
 def enable_p2p_halo(ctx, dist, torch, world):
     """all-gather the ranks' halo-arena IPC handles and attach (NVLink peer-memory halo).  HPDG_HALO=nccl keeps NCCL send/recv.
     If any rank cannot map its neighbours' arenas (no peer access / IPC not permitted) every rank falls back to NCCL.

@@ -79,6 +79,91 @@ def test_partition_and_halo_layout_gloo():
     assert all(r[1] for r in res) and all(r[2] == 1 for r in res), res
 
 
+def _gloo_hp_worker(rank, world, port, n, pmax, q):
+    """distributed hp on 2 ranks over gloo: one-time degree exchange, receive offsets, variable-size trace blocks"""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "dune-hpdg_b200"))
+    from hpdg_b200 import partition as part
+    from oracle import orc
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pgrid = part.pgrid_for(world)
+        Ng = [n[d] * pgrid[d] for d in range(3)]
+        degg = np.random.default_rng(7).integers(1, pmax + 1, int(np.prod(Ng))).astype(np.int64)   # same on every rank
+        offg = np.concatenate(([0], np.cumsum((degg + 1) ** 3)))
+        xg = orc.fill_random(int(offg[-1]))
+        g_end_of = lambda p: np.array([[orc.lagrange_prime(p, i, s) for i in range(p + 1)] for s in range(2)])
+        gl = part.local_to_global_elements(rank, pgrid, n)
+        degl = degg[gl]
+        offl = np.concatenate(([0], np.cumsum((degl + 1) ** 3)))
+        xl = part.scatter_global_blocks(xg, offg, gl)
+        ok, nrecv = True, 0
+        for f, peer in part.peers(rank, pgrid).items():
+            if peer is None:
+                continue
+            fel = part.face_elements(n, f)
+            # 1. degree exchange (once per level)
+            sdeg = torch.from_numpy(np.ascontiguousarray(degl[fel]))
+            rdeg = torch.empty_like(sdeg)
+            if rank < peer:
+                dist.send(sdeg, peer); dist.recv(rdeg, peer)
+            else:
+                dist.recv(rdeg, peer); dist.send(sdeg, peer)
+            roff = part.hp_halo_offsets(rdeg.numpy())
+            # 2. per apply: variable-size blocks, sizes known to both sides from the degrees
+            send = torch.from_numpy(part.hp_face_traces(xl, offl, degl, n, f, g_end_of))
+            assert send.numel() == 2 * part.hp_halo_offsets(degl[fel])[-1]
+            buf = torch.empty(2 * int(roff[-1]), dtype=torch.float64)
+            if rank < peer:
+                dist.send(send, peer); dist.recv(buf, peer)
+            else:
+                dist.recv(buf, peer); dist.send(send, peer)
+            nrecv += 1
+            # 3. the received degrees and blocks are those of the elements across the face in the GLOBAL mesh
+            d, s = f // 2, f % 2
+            stride = [1, Ng[0], Ng[0] * Ng[1]][d]
+            for i, e in enumerate(fel):
+                eg = gl[e] + (stride if s else -stride)
+                po = int(degg[eg])
+                ok &= int(rdeg[i]) == po
+                N = po + 1
+                blk = xg[offg[eg]:offg[eg + 1]].reshape(N, N, N)
+                g = g_end_of(po)[1 - s]
+                end = 0 if s else N - 1
+                if d == 0:
+                    der, val = np.einsum("kji,i->kj", blk, g), blk[:, :, end]
+                elif d == 1:
+                    der, val = np.einsum("kji,j->ki", blk, g), blk[:, end, :]
+                else:
+                    der, val = np.einsum("kji,k->ji", blk, g), blk[end]
+                got = buf.numpy()[2 * roff[i]:2 * roff[i + 1]].reshape(-1, 2)
+                ok &= np.allclose(got[:, 0], der.reshape(-1), rtol=0, atol=1e-12) and np.array_equal(got[:, 1], val.reshape(-1))
+        q.put((rank, bool(ok), nrecv))
+    except Exception as exc:
+        q.put((rank, False, repr(exc)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_hp_halo_layout_gloo():
+    # distributed hp (hpdg_create_distributed_hp): the host-side protocol of csrc/api.cu (hp_ghost_setup: degree exchange + receive
+    # offsets; hp_halo_exchange: variable-size blocks) restated in hpdg_b200.partition and run on 2 ranks over gloo
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_hp_worker, args=(r, 2, 29543, (3, 2, 4), 4, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert sorted(r[0] for r in res) == [0, 1], res
+    assert all(r[1] for r in res) and all(r[2] == 1 for r in res), res
+
+
 def test_partition_index_logic():
     sys.path.insert(0, os.path.join(ROOT, "dune-hpdg_b200"))
     from hpdg_b200 import partition as part
