@@ -1195,8 +1195,12 @@ static int pcg_device(hpdg_ctx* ctx, int precond, double damping, int smooth, in
       const int cur = (it - 1) & 1, nxt = it & 1;                         // rz of this / the next iteration
       if (op_apply_async(ctx, F, p, q, 1.0)) return 1;                    // q = A p
       if (dot_to_slot(ctx, n, p, q, PQ)) return 1;
-      if (launch_cg_update(ctx, n, cur, PQ, p, q, d_x, r)) return 1;      // x += (rz/pq) p ; r -= (rz/pq) q
-      if (dot_to_slot(ctx, n, r, r, RR)) return 1;
+      // x += (rz/pq) p ; r -= (rz/pq) q ; rr = r . r in the same pass, summed over the ranks
+      if (launch_cg_update_rr(ctx, n, cur, PQ, p, q, d_x, r, ctx->d_scalar + RR)) return 1;
+      if (ctx->nranks > 1) {
+        if (!ctx->nccl) { ctx->err = "dot product over ranks needs the NCCL communicator (context created with nccl_id = NULL)"; return 1; }
+        HPDG_NCCL(g_nccl.AllReduce(ctx->d_scalar + RR, ctx->d_scalar + RR, 1, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
+      }
       if (it % check_every == 0 || it == maxit) {
         HPDG_CUDA(cudaMemcpyAsync(&rr, ctx->d_scalar + RR, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         if (sync_check(ctx)) return 1;

@@ -35,6 +35,24 @@ __global__ void k_cg_direction(long n, const double* __restrict__ s, int num, in
 }
 
 constexpr int kDotBlocks = 592, kDotThreads = 256;
+// the same update with the new residual's r . r folded in (one pass over r instead of two): per-CTA partial sums over the fixed
+// grid of the two-stage dot product, so the result does not depend on anything but n
+__global__ void k_cg_update_rr(long n, const double* __restrict__ s, int num, int den, const double* __restrict__ p,
+                               const double* __restrict__ q, double* __restrict__ x, double* __restrict__ r, double* __restrict__ part) {
+  __shared__ double sh[kDotThreads];
+  const double alpha = s[num] / s[den];
+  double acc = 0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double rn = fma(-alpha, q[i], r[i]);
+    r[i] = rn;
+    acc = fma(rn, rn, acc);
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = kDotThreads / 2; w > 0; w >>= 1) { if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w]; __syncthreads(); }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
 __global__ void k_dot1(long n, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ part) {
   __shared__ double sh[kDotThreads];
   double s = 0;
@@ -92,6 +110,15 @@ int launch_dot(Ctx* ctx, long n, const double* x, const double* y, double* d_res
 int launch_cg_update(Ctx* ctx, long n, int num, int den, const double* p, const double* q, double* x, double* r) {
   k_cg_update<<<grid_for(n), 256, 0, ctx->stream>>>(n, ctx->d_scalar, num, den, p, q, x, r);
   ctx->launches++;
+  HPDG_CUDA(cudaGetLastError());
+  return 0;
+}
+// x += a p; r -= a q; *d_rr = r . r (this rank's part) in one pass
+int launch_cg_update_rr(Ctx* ctx, long n, int num, int den, const double* p, const double* q, double* x, double* r, double* d_rr) {
+  if (blas_scratch(ctx)) return 1;
+  k_cg_update_rr<<<kDotBlocks, kDotThreads, 0, ctx->stream>>>(n, ctx->d_scalar, num, den, p, q, x, r, ctx->d_partial);
+  k_dot2<<<1, 1024, 0, ctx->stream>>>(ctx->d_partial, d_rr);
+  ctx->launches += 2;
   HPDG_CUDA(cudaGetLastError());
   return 0;
 }

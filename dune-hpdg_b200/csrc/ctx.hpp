@@ -249,6 +249,7 @@ constexpr int kScalarSlots = 16;   // Ctx::d_scalar: device-resident scalars of 
 int blas_scratch(Ctx* ctx);        // allocates Ctx::d_scalar / d_partial on first use
 // preconditioned CG updates with device-resident scalars s = Ctx::d_scalar (no host round trip inside an iteration)
 int launch_cg_update(Ctx* ctx, long n, int num, int den, const double* p, const double* q, double* x, double* r);  // a = s[num]/s[den]; x += a p; r -= a q
+int launch_cg_update_rr(Ctx* ctx, long n, int num, int den, const double* p, const double* q, double* x, double* r, double* d_rr);  // ... and *d_rr = r . r
 int launch_cg_direction(Ctx* ctx, long n, int num, int den, const double* z, double* p);                          // b = s[num]/s[den]; p = z + b p
 
 }  // namespace hpdg
