@@ -504,6 +504,7 @@ int hpdg_create(hpdg_ctx** out, int dim, const int* n, const double* L, const in
 int hpdg_create_refined_2d(hpdg_ctx** out, const int* n, const double* L, const unsigned char* refine, const int* degree,
                            long nleaf, double sigma, int dirichlet, int device) {
   *out = nullptr;
+  if (!n || !L || !refine || !degree) { g_create_err = "null argument"; return 1; }
   if (n[0] < 1 || n[1] < 1) { g_create_err = "mesh extents must be positive"; return 1; }
   const long ncell = (long)n[0] * n[1];
   std::vector<long> first(ncell + 1, 0);
