@@ -2,6 +2,8 @@
 //   (1) matrix-free/test/testdg.cc:92-135     : SIPG apply with factor 0.5 vs an independent formulation (the CPU oracle)
 //   (2) matrix-free/test/testdgblockjacobi.cc : damped (0.75) block-Jacobi iteration drives the energy norm of the residual < 1e-2
 //   (3) test/test_solversetup.cc:25-50        : p-multigrid builds and runs (plus: residual decreases)
+//   (4) test/test_dynamicblockgs.cc:24-44     : block-GS on the assembled matrix; (5) the same sweeps matrix-free;
+//   (6) matrix-free/test/testoperator.cc:80-98 : operator tuple, on a hanging-node mesh
 // Links libhpdg_b200.so (product) and libhpdg_oracle.so (checker; tests may).
 #include <cmath>
 #include <cstdio>
@@ -89,6 +91,42 @@ int main() {
       A.mv(x, Ax); Ax -= b;
       CHECK(std::sqrt(Ax * Ax) < 1e-13, "100 DynamicBlockGS sweeps solve the small system (|b - Ax| < 1e-13)");
       CHECK(A.blockCol.size() == 12 && A.entries.size() == 12u * 81u, "DynamicBCRSMatrix pattern: 4 rows x (self + 2 neighbours), 9x9 blocks");
+    }
+    {  // (5) the same sweeps without a matrix: MatrixFreeBlockGS reproduces DynamicBlockGS on the assembled matrix sweep by sweep
+      int n[2] = {5, 4}; double L[2] = {1, 1.5};
+      std::vector<int> deg(20);
+      for (int e = 0; e < 20; e++) deg[e] = 1 + (e * 7) % 4;
+      auto ctx = std::make_shared<hpdg::Context>(2, n, L, deg, 2.0, true);
+      hpdg::AssembledMatrix A(ctx);
+      V b = ctx->makeVector(), x1 = ctx->makeVector(), x2 = ctx->makeVector();
+      for (std::size_t i = 0; i < b.dimension(); i++) b.data()[i] = std::sin(0.37 * (double)i);
+      x1 = 1.0; x2 = 1.0;
+      hpdg::DynamicBlockGS<V> gs;
+      gs.setProblem(A, x1, b);
+      hpdg::MatrixFreeBlockGS<V> mf(ctx);
+      mf.setProblem(x2, b);
+      for (int it = 0; it < 5; it++) { gs.iterate(); mf.iterate(); }
+      x2 -= x1;
+      CHECK(std::sqrt(x2 * x2) < 1e-12 * std::sqrt(x1 * x1), "MatrixFreeBlockGS == DynamicBlockGS on the assembled matrix (hp mesh, 5 sweeps)");
+    }
+    {  // (6) operator tuple (matrix-free/test/testoperator.cc:80-98: factors 1 and 2 accumulate to 3 A x) and a hanging-node mesh
+      int n[2] = {3, 3}; double L[2] = {1, 1};
+      std::vector<unsigned char> refine(9, 0);
+      refine[4] = 1;                                   // the centre cell is split once
+      std::vector<int> deg(9 + 3, 2);
+      auto ctx = std::make_shared<hpdg::Context>(hpdg::Context::Refined2D{}, n, L, refine, deg, 2.0, false);
+      V x = ctx->makeVector(), y1 = ctx->makeVector(), y3 = ctx->makeVector(), one = ctx->makeVector();
+      for (std::size_t i = 0; i < x.dimension(); i++) x.data()[i] = std::cos(0.11 * (double)i);
+      hpdg::Operator op(ctx);
+      op.apply(x, y1);
+      ctx->check(hpdg_op_apply(ctx->handle(), HPDG_FINEST, x.data(), y3.data(), 1.0));
+      ctx->check(hpdg_op_apply_accum(ctx->handle(), HPDG_FINEST, x.data(), y3.data(), 2.0));
+      y3 *= 1.0 / 3.0; y3 -= y1;
+      CHECK(std::sqrt(y3 * y3) < 1e-13 * std::sqrt(y1 * y1), "two local operators with factors 1 and 2 accumulate to 3 A x (hanging-node mesh)");
+      one = 1.0;
+      op.apply(one, y1);
+      CHECK(std::sqrt(y1 * y1) < 1e-11, "natural boundary: constants are in the kernel of the operator on the hanging-node mesh");
+      CHECK(ctx->blockOffsets().size() == 13, "leaf elements: 8 unrefined cells + 4 children");
     }
     {  // error behaviour: exceptions, not aborts
       bool threw = false;
