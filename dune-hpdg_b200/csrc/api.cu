@@ -406,10 +406,13 @@ int mg_level(Ctx* ctx, int l, const VC& v) {
   HPDG_CUDA(cudaMemsetAsync(C.mg_x, 0, sizeof(double) * C.ndof, ctx->stream));
   if (mg_level(ctx, l - 1, v)) return 1;                                // mu_ = 1
   if (launch_prolong(ctx, L, C, C.mg_x, L.mg_t1)) return 1;             // :108
-  if (launch_axpy(ctx, L.ndof, 1.0, L.mg_t1, x)) return 1;
-  ctx->fuse_accum = 1;                                                  // r -= A tmp1 (:110-112), fused
+  // x += tmp1 and r -= A tmp1 (:110-112): both ride on the operator kernel on uniform levels (no axpy pass)
+  const bool in_apply = ctx->xacc_in_apply && uniform_supported(ctx, L);
+  if (!in_apply && launch_axpy(ctx, L.ndof, 1.0, L.mg_t1, x)) return 1;
+  ctx->fuse_accum = 1;
+  if (in_apply) ctx->fuse_xin = x;
   const int rcc = op_apply_async(ctx, L, L.mg_t1, r, -1.0);
-  ctx->fuse_accum = 0;
+  ctx->fuse_accum = 0; ctx->fuse_xin = nullptr;
   if (rcc) return 1;
   return mg_smooth(ctx, l, v, v.post, x, r);                            // :116
 }
@@ -432,6 +435,21 @@ int vcycle_device(Ctx* ctx, const VC& v, double* d_x, double* d_b) {
     }
   }
   Level& F = ctx->levels[nl - 1];
+  if (nl > 1) {
+    // On the finest level of a hierarchy the cycle only ever ADDS to its iterate (smoothing steps, prolongated corrections) and
+    // subtracts A * (what it added) from its residual, so it works directly on the caller's vectors: b <- b - A x in one
+    // accumulating apply (:30-36), then x and b play state.x / state.r of the finest level.  On return x += correction and b is
+    // the residual (:60-61) without the final axpy / copy (64 B/DoF of vector traffic per cycle less).
+    ctx->fuse_accum = 1;
+    const int r0 = op_apply_async(ctx, F, d_x, d_b, -1.0);
+    ctx->fuse_accum = 0;
+    if (r0) return 1;
+    double *sx = F.mg_x, *sr = F.mg_r;
+    F.mg_x = d_x; F.mg_r = d_b;
+    const int r1 = mg_level(ctx, nl - 1, v);
+    F.mg_x = sx; F.mg_r = sr;
+    return r1;
+  }
   HPDG_CUDA(cudaMemsetAsync(F.mg_x, 0, sizeof(double) * F.ndof, ctx->stream));
   if (op_apply_async(ctx, F, d_x, F.mg_t1, 1.0)) return 1;             // r = b - A x (:30-36)
   if (launch_xpay_sub(ctx, F.ndof, d_b, F.mg_t1, F.mg_r)) return 1;

@@ -409,7 +409,7 @@ __device__ __forceinline__ void generic_element_pass(const GenericParams& P, con
       for (int k = 0; k < N1; k++) { const int j = line + nf * k; sw[j] = be[j] - sw[j]; }   // r_e = b_e - (A x)_e
     }
     const int j0 = line % N1, j1 = DIM == 3 ? line / N1 : 0;
-    const bool warp_local = tpe == 32;   // an element's threads are the lanes of one warp: no block barrier inside the substitution
+    const bool warp_local = 32 % tpe == 0;   // an element's threads are lanes of ONE warp: no block barrier inside the substitution
     if (warp_local) __syncthreads();
     for (int a = 0; a < ne; a++) {
       if (warp_local) __syncwarp(); else __syncthreads();
@@ -778,7 +778,7 @@ int blockgs_mf_iterate(Ctx* ctx, Level& L, const double* b, double* x) {
       const int per_elem = 2 * ne + 4 * nfaces + ((mixed && L.dim == 3) ? 2 * nfaces * n1 * maxno1 : 0);
       const int per_elem_gs = per_elem + L.dim * n1 * n1 + ne;
       P.ebegin = begin;
-      const int tpe = nf < 32 ? 32 : nf;   // a warp per element: the forward substitution then needs no block barriers
+      const int tpe = (mixed && L.dim == 3 && nf < 32) ? 32 : nf;
       P.tpe = tpe;
       int epc = tpe >= 128 ? 1 : 128 / tpe;
       epc = (int)std::max<long>(1, std::min<long>(epc, (48 * 1024) / ((long)per_elem_gs * 8)));
