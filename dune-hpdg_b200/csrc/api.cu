@@ -716,7 +716,7 @@ void hpdg_destroy(hpdg_ctx* ctx) {
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->stream_comm) cudaStreamDestroy(ctx->stream_comm);
-  if (ctx->bucket_stream[0]) { for (int k = 0; k < 4; k++) cudaStreamDestroy(ctx->bucket_stream[k]); for (int k = 0; k < 5; k++) cudaEventDestroy(ctx->bucket_ev[k]); }
+  if (ctx->bucket_stream[0]) { for (int k = 0; k < kBucketStreams; k++) cudaStreamDestroy(ctx->bucket_stream[k]); for (int k = 0; k <= kBucketStreams; k++) cudaEventDestroy(ctx->bucket_ev[k]); }
   if (ctx->stream_h2d) { cudaStreamDestroy(ctx->stream_h2d); cudaStreamDestroy(ctx->stream_d2h); for (int k = 0; k < 3; k++) for (int c = 0; c < 32; c++) cudaEventDestroy(ctx->ev_chunk[k][c]); }
   delete ctx;
 }

@@ -645,13 +645,15 @@ int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double 
   // ---- pass 2: the degree buckets write disjoint rows of y: side streams, so that small buckets overlap the large ones ----
   const size_t nb = L.bucket_p.size();
   const bool fork = nb > 1;
+  int nstreams = 1;
   if (fork) {
     if (!ctx->bucket_stream[0]) {
-      for (int k = 0; k < 4; k++) HPDG_CUDA(cudaStreamCreateWithFlags(&ctx->bucket_stream[k], cudaStreamNonBlocking));
-      for (int k = 0; k < 5; k++) HPDG_CUDA(cudaEventCreateWithFlags(&ctx->bucket_ev[k], cudaEventDisableTiming));
+      for (int k = 0; k < kBucketStreams; k++) HPDG_CUDA(cudaStreamCreateWithFlags(&ctx->bucket_stream[k], cudaStreamNonBlocking));
+      for (int k = 0; k <= kBucketStreams; k++) HPDG_CUDA(cudaEventCreateWithFlags(&ctx->bucket_ev[k], cudaEventDisableTiming));
     }
-    HPDG_CUDA(cudaEventRecord(ctx->bucket_ev[4], ctx->stream));
-    for (int k = 0; k < 4; k++) HPDG_CUDA(cudaStreamWaitEvent(ctx->bucket_stream[k], ctx->bucket_ev[4], 0));
+    nstreams = (int)std::min<size_t>(nb, kBucketStreams);
+    HPDG_CUDA(cudaEventRecord(ctx->bucket_ev[kBucketStreams], ctx->stream));
+    for (int k = 0; k < nstreams; k++) HPDG_CUDA(cudaStreamWaitEvent(ctx->bucket_stream[k], ctx->bucket_ev[kBucketStreams], 0));
   }
   // largest buckets first (they determine the critical path)
   std::vector<size_t> order(nb);
@@ -662,13 +664,14 @@ int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double 
     const size_t b = order[bi];
     long cnt = L.bucket_begin[b + 1] - L.bucket_begin[b];
     if (cnt == 0) continue;
-    cudaStream_t lstream = fork ? ctx->bucket_stream[bi % 4] : ctx->stream;
+    cudaStream_t lstream = fork ? ctx->bucket_stream[bi % nstreams] : ctx->stream;
     const int p = L.bucket_p[b], n1 = p + 1;
     const int ne = ipow_d(n1, L.dim), nf = ipow_d(n1, L.dim - 1);
     const int nfaces = 2 * L.dim;
     const int per_elem = 2 * ne + 4 * nfaces * L.fslots + ((mixed && L.dim == 3) ? 2 * nfaces * n1 * maxno1 : (L.nc ? 2 * nfaces * n1 : 0));
     P.ebegin = L.bucket_begin[b];
-    // elements per CTA: ~128 threads, at most 48 KB of shared memory
+    // elements per CTA: ~128 threads, at most 48 KB of shared memory (256-thread CTAs for the high degrees, i.e. fewer idle lanes in
+    // the last warp but more elements per block barrier, measured slower: cfg3 192.9 against 187.9 us)
     const int tpe = (mixed && L.dim == 3 && nf < 32) ? 32 : nf;
     P.tpe = tpe;
     int epc = tpe >= 128 ? 1 : 128 / tpe;
@@ -704,7 +707,7 @@ int launch_apply_generic(Ctx* ctx, Level& L, const double* x, double* y, double 
     HPDG_CUDA(cudaGetLastError());
   }
   if (fork) {
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < nstreams; k++) {
       HPDG_CUDA(cudaEventRecord(ctx->bucket_ev[k], ctx->bucket_stream[k]));
       HPDG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->bucket_ev[k], 0));
     }

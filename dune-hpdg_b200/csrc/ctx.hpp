@@ -144,6 +144,8 @@ struct Level {
   double *mg_x = nullptr, *mg_r = nullptr, *mg_t1 = nullptr, *mg_t2 = nullptr;
 };
 
+constexpr int kBucketStreams = 8;
+
 struct Ctx {
   int device = 0;
   int dim = 0;
@@ -176,8 +178,8 @@ struct Ctx {
   int q3p_tune = 0; // persistent Q3 kernel: tuning switches (bit 0: L2 prefetch two tiles ahead)
   int slab_z0 = 0, slab_nz = 0;  // restrict the next uniform launch to element layers [z0, z0+nz) (chunked host apply)
   cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;
-  cudaStream_t bucket_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // hp apply: degree buckets run concurrently
-  cudaEvent_t bucket_ev[5] = {};
+  cudaStream_t bucket_stream[kBucketStreams] = {};  // hp apply: degree buckets run concurrently (one side stream per bucket, up to 8)
+  cudaEvent_t bucket_ev[kBucketStreams + 1] = {};
   cudaEvent_t ev_chunk[3][32] = {};
   // fusion requests of the V-cycle driver, consumed by the next launch:
   int fuse_accum = 0;          // apply: y = y_old + factor * A x   (r -= A c without a separate axpy)
