@@ -945,6 +945,7 @@ int hpdg_diag_block(hpdg_ctx* ctx, int level, long element, double* h_out) {
 int hpdg_bcrs_sizes(hpdg_ctx* ctx, int level, long* nblocks, long* nentries) {
   HPDG_ENTER(ctx);
   Level* L = get_level(ctx, level); if (!L) return 1;
+  if (L->nc) { ctx->err = "not available on non-conforming meshes (operator apply only)"; return 1; }
   long nb = 0, ne = 0;
   const long stride[3] = {1, L->n[0], (long)L->n[0] * L->n[1]};
   for (long e = 0; e < L->nelem; e++) {
