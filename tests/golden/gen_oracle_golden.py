@@ -1,4 +1,4 @@
-"""Generates tests/golden/oracle_golden.npz from the CPU oracle (oracle/hpdg_oracle.c).
+"""Generates tests/golden/oracle_golden.npz from the CPU oracle (oracle/hpdg_oracle.c, oracle/sf2d.py).
 
 The reference itself cannot be built in this image and ships no golden vectors, so these fixtures freeze the
 ORACLE's outputs (which are pinned by the reference's differential tests, tests/test_oracle_pins.py) on small seeded cases:
@@ -51,5 +51,20 @@ bvec = orc.fill_random(fine.ndof, seed=5)
 xv, rv = orc.vcycle([l0, l1, fine], None, np.zeros(fine.ndof), bvec, smoother=1, damping=0.75)
 out["mg_vcycle_x"] = xv
 out["mg_vcycle_r"] = rv
+# the third formulation (oracle/sf2d.py: sum-factorised Gauss-Lobatto operator of sfipdg.hh) on a 2-D hp mesh, and its non-conforming
+# branch on a once-refined mesh with hanging nodes (leaf numbering of hpdg_create_refined_2d)
+from oracle import sf2d
+deg2 = np.random.default_rng(5).integers(1, 6, 42).astype(np.int32)
+s2 = sf2d.SumFactIPDG2D((7, 6), (1.0, 2.0), deg2, 2.0, True)
+x2 = orc.fill_random(s2.ndof)
+out["sf2d_deg"] = deg2
+out["sf2d_Ax"] = s2.apply(x2)
+ref = np.zeros(20, dtype=np.uint8)
+ref[[1, 6, 7, 12, 18]] = 1
+degn = np.random.default_rng(17).integers(1, 6, 20 + 3 * 5).astype(np.int32)
+nc = sf2d.RefinedSumFactIPDG2D((5, 4), ref, degn, (1.0, 1.5), 2.0, True)
+out["nc_refine"] = ref
+out["nc_deg"] = degn
+out["nc_Ax"] = nc.apply(orc.fill_random(nc.ndof))
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_golden.npz"), **out)
 print({k: v.shape for k, v in out.items()})

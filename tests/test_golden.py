@@ -20,6 +20,14 @@ def test_oracle_reproduces_golden(orc):
     assert rel(m3.apply_mf(orc.fill_random(m3.ndof)), G["q3_d_Ax"]) < 1e-14
     mh = orc.Mesh((4, 3, 5), degree=G["hp_deg"], sigma=2.0, dirichlet=True)
     assert rel(mh.apply_mf(orc.fill_random(mh.ndof)), G["hp_Ax"]) < 1e-14
+    from oracle import sf2d
+    s2 = sf2d.SumFactIPDG2D((7, 6), (1.0, 2.0), G["sf2d_deg"], 2.0, True)
+    x2 = orc.fill_random(s2.ndof)
+    assert rel(s2.apply(x2), G["sf2d_Ax"]) < 1e-14
+    # ... and the quadrature-loop formulation reproduces the sum-factorised one's fixture
+    assert rel(orc.Mesh((7, 6), L=[1.0, 2.0], degree=G["sf2d_deg"], sigma=2.0, dirichlet=True).apply_mf(x2), G["sf2d_Ax"]) < 1e-13
+    nc = sf2d.RefinedSumFactIPDG2D((5, 4), G["nc_refine"], G["nc_deg"], (1.0, 1.5), 2.0, True)
+    assert rel(nc.apply(orc.fill_random(nc.ndof)), G["nc_Ax"]) < 1e-14
 
 
 @pytest.mark.gpu
@@ -43,6 +51,10 @@ def test_cuda_matches_golden(orc, hp):
     xin = orc.fill_random(ctx.dimension())
     assert rel(hp.Operator(ctx).apply(xin), G["hp_Ax"]) < 1e-12
     assert rel(hp.BlockJacobi(ctx, form=hp.JACOBI_FD)(xin), G["hp_jac"]) < 1e-11
+    ctx = hp.Context((7, 6), L=[1.0, 2.0], degree=G["sf2d_deg"], sigma=2.0, dirichlet=True)
+    assert rel(hp.Operator(ctx).apply(orc.fill_random(ctx.dimension())), G["sf2d_Ax"]) < 1e-12
+    ctx = hp.Context.refined_2d((5, 4), G["nc_refine"], G["nc_deg"], L=[1.0, 1.5], sigma=2.0, dirichlet=True)
+    assert rel(hp.Operator(ctx).apply(orc.fill_random(ctx.dimension())), G["nc_Ax"]) < 1e-12
     ctx = hp.Context((4, 4, 4), degree=4)
     ctx.build_p_hierarchy()
     xf = orc.fill_random(ctx.dimension())
