@@ -274,9 +274,9 @@ def main():
     def aligned_start():
         """After the barrier the ranks leave it tens of microseconds apart, which a 20-step timed region of a 90 us step would book
         as step time (the ranks are coupled through the halo flags).  All ranks of the node share CLOCK_MONOTONIC: rank 0 names
-        an instant 2 ms ahead, everyone spins until then and only then records its start event and launches."""
+        an instant 0.5 ms ahead, everyone spins until then and only then records its start event and launches."""
         if world > 1:
-            t = torch.tensor([time.monotonic() + 0.002], dtype=torch.float64, device="cuda")
+            t = torch.tensor([time.monotonic() + 0.0005], dtype=torch.float64, device="cuda")
             dist.broadcast(t, 0)
             target = float(t.item())
             torch.cuda.synchronize()
@@ -284,16 +284,18 @@ def main():
                 pass
 
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
-    for i in range(args.warmup):
-        op.apply_device(dxs[i % NBUF], dys[i % NBUF], sync=False)
-    barrier()
+    # the clock sampler is started BEFORE the warm-up so that nothing but the barrier separates the warm-up steps from the timed
+    # ones: a GPU that idles for the 0.3 s of the sampler's start-up needs ~100 us to get back to speed, which a 20-step region of an
+    # 83 us step books as 4-5 us per step (measured: 87.6 against 82.9 us per step at 200 steps)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    l0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(args.warmup):
+        op.apply_device(dxs[i % NBUF], dys[i % NBUF], sync=False)
     barrier()
+    l0 = ctx.launch_count
     aligned_start()
     e0.record(stream)
     for i in range(args.steps):
