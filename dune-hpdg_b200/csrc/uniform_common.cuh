@@ -1,6 +1,8 @@
 // Shared pieces of the uniform-degree tile kernels (apply_uniform.cu, apply_uniform_q3p.cu): the parameter block, the
 // shared-memory pitches of the padded layout, the pencil sweep and the 1-D mass sweep.  See apply_uniform.cu for the formulation.
 #pragma once
+#include <cstdint>
+
 #include "ctx.hpp"
 
 namespace hpdg {
@@ -132,11 +134,17 @@ struct HaloRaw { double p[N], n[N]; int pm, nm; };  // modes: 0 interior, 1 Diri
 
 template <int N>
 __device__ __forceinline__ void halo_load_line(double (&l)[N], const double* __restrict__ line, long stride) {
-  if (N == 4 && stride == 1) {  // an x line is 32 contiguous, 32-byte aligned bytes: two 128-bit loads
-    const double2 lo = __ldg(reinterpret_cast<const double2*>(line));
-    const double2 hi = __ldg(reinterpret_cast<const double2*>(line) + 1);
-    l[0] = lo.x; l[1] = lo.y; l[2] = hi.x; l[3] = hi.y;
-    return;
+  if (N == 4 && stride == 1) {  // an x line is 32 contiguous bytes, 32-byte aligned if the vector is: one 256-bit load
+    if ((reinterpret_cast<uintptr_t>(line) & 31) == 0) {
+      asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];\n" : "=d"(l[0]), "=d"(l[1]), "=d"(l[2]), "=d"(l[3]) : "l"(line));
+      return;
+    }
+    if ((reinterpret_cast<uintptr_t>(line) & 15) == 0) {  // 16-byte aligned vector: two 128-bit loads
+      const double2 lo = __ldg(reinterpret_cast<const double2*>(line));
+      const double2 hi = __ldg(reinterpret_cast<const double2*>(line) + 1);
+      l[0] = lo.x; l[1] = lo.y; l[2] = hi.x; l[3] = hi.y;
+      return;
+    }
   }
 #pragma unroll
   for (int m = 0; m < N; m++) l[m] = __ldg(line + m * stride);
@@ -148,6 +156,8 @@ template <int N>
 __device__ __forceinline__ HaloRaw<N> halo_issue(int pm, int nm, const double* __restrict__ prev, const double* __restrict__ next,
                                                  long stride, const double* __restrict__ glo, const double* __restrict__ ghi) {
   HaloRaw<N> r;
+  // (the lines are only read in the modes that load them, but leaving them undefined costs the persistent Q3 kernel 200 bytes of
+  // spills: ptxas then keeps the undefined live ranges apart)
 #pragma unroll
   for (int m = 0; m < N; m++) r.p[m] = r.n[m] = 0.0;
   r.pm = pm; r.nm = nm;
