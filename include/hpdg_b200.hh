@@ -95,20 +95,43 @@ class Context {
   hpdg_ctx* h_ = nullptr;
 };
 
-// Operator::apply(x, Ax): Ax = factor * A x (Ax overwritten, operator.hh:42)
+// The local operator of the tuple Operator iterates over: carries its own factor (localoperator.hh:41-49: factor() / setFactor())
+class IPDGOperator {
+ public:
+  explicit IPDGOperator(double factor = 1.0) : factor_(factor) {}
+  double factor() const { return factor_; }
+  void setFactor(double f) { factor_ = f; }
+
+ private:
+  double factor_;
+};
+
+// Operator::apply(x, Ax) over a tuple of local operators (matrix-free/operator.hh:41-56): Ax is zeroed once, every local operator
+// adds factor_k * A x (matrix-free/test/testoperator.cc:80-98: factors 1 and 2 give 3 A x).  The single-operator constructor is the
+// common case: Ax = factor * A x.
 class Operator {
  public:
   explicit Operator(std::shared_ptr<Context> c, int level = HPDG_FINEST, double factor = 1.0)
-      : c_(std::move(c)), level_(level), factor_(factor) {}
-  double factor() const { return factor_; }
-  void setFactor(double f) { factor_ = f; }
+      : c_(std::move(c)), level_(level), ops_{IPDGOperator(factor)} {}
+  static Operator fromLocalOperators(std::shared_ptr<Context> c, std::vector<IPDGOperator> ops, int level = HPDG_FINEST) {
+    Operator o(std::move(c), level);
+    if (!ops.empty()) o.ops_ = std::move(ops);
+    return o;
+  }
+  double factor() const { return ops_[0].factor(); }
+  void setFactor(double f) { ops_[0].setFactor(f); }
+  std::vector<IPDGOperator>& localOperators() { return ops_; }
   template <class V>
-  void apply(const V& x, V& Ax) const { c_->check(hpdg_op_apply(c_->handle(), level_, x.data(), Ax.data(), factor_)); }
+  void apply(const V& x, V& Ax) const {
+    c_->check(hpdg_op_apply(c_->handle(), level_, x.data(), Ax.data(), ops_[0].factor()));
+    for (std::size_t k = 1; k < ops_.size(); k++)
+      c_->check(hpdg_op_apply_accum(c_->handle(), level_, x.data(), Ax.data(), ops_[k].factor()));
+  }
 
  private:
   std::shared_ptr<Context> c_;
   int level_;
-  double factor_;
+  std::vector<IPDGOperator> ops_;
 };
 
 // LinearIterationStep-shaped damped block-Jacobi step: x += damping * D^-1 (rhs - A x)

@@ -119,8 +119,8 @@ int main() {
       for (std::size_t i = 0; i < x.dimension(); i++) x.data()[i] = std::cos(0.11 * (double)i);
       hpdg::Operator op(ctx);
       op.apply(x, y1);
-      ctx->check(hpdg_op_apply(ctx->handle(), HPDG_FINEST, x.data(), y3.data(), 1.0));
-      ctx->check(hpdg_op_apply_accum(ctx->handle(), HPDG_FINEST, x.data(), y3.data(), 2.0));
+      auto tuple = hpdg::Operator::fromLocalOperators(ctx, {hpdg::IPDGOperator(1.0), hpdg::IPDGOperator(2.0)});
+      tuple.apply(x, y3);
       y3 *= 1.0 / 3.0; y3 -= y1;
       CHECK(std::sqrt(y3 * y3) < 1e-13 * std::sqrt(y1 * y1), "two local operators with factors 1 and 2 accumulate to 3 A x (hanging-node mesh)");
       one = 1.0;
