@@ -1316,6 +1316,24 @@ int hpdg_tables_1d(int degree, double* nodes, double* mass, double* stiffness, d
   return 0;
 }
 
+// host-only introspection: the tangential couplings of the mixed-degree and non-conforming faces (tables.hpp).  kind 0: conforming
+// face, (M^ee)^-1 M^eo; 1 / 2: e is the coarse side, low / high half of its side; 3 / 4: e is the fine side on the low / high half of the
+// neighbour's side.  out is (pe+1) x (po+1) row-major; own (kinds 1, 2 only, may be NULL) is the (pe+1) x (pe+1) own-side coupling.
+int hpdg_tables_face(int pe, int po, int kind, double* out, double* own) {
+  if (pe < 0 || pe > kMaxP || po < 0 || po > kMaxP || kind < 0 || kind > 4) { g_create_err = "degree or kind out of range"; return 1; }
+  const HostTables& H = host_tables();
+  const int ND = kMaxP + 1, ne = pe + 1, no = po + 1;
+  const double* P = kind == 0 ? &H.P[((size_t)pe * ND + po) * kMaxN * kMaxN]
+                              : &H.Pnc_eo[(((size_t)(kind - 1) * ND + pe) * ND + po) * kMaxN * kMaxN];
+  for (int i = 0; i < ne; i++) for (int j = 0; j < no; j++) out[i * no + j] = P[i * kMaxN + j];
+  if (own) {
+    if (kind != 1 && kind != 2) { g_create_err = "the own-side coupling exists for the coarse side (kinds 1, 2) only"; return 1; }
+    const double* Q = &H.Pnc_ee[((size_t)(kind - 1) * ND + pe) * kMaxN * kMaxN];
+    for (int i = 0; i < ne; i++) for (int j = 0; j < ne; j++) own[i * ne + j] = Q[i * kMaxN + j];
+  }
+  return 0;
+}
+
 long hpdg_launch_count(const hpdg_ctx* ctx) { return ctx->launches; }
 int hpdg_uses_uniform_kernel(const hpdg_ctx* ctx, int level) {
   Level* L = get_level(const_cast<hpdg_ctx*>(ctx), level);

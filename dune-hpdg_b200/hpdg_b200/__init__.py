@@ -100,6 +100,7 @@ SIGNATURES = {
     "hpdg_loop_solve_device": (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_double, C.c_int,
                                          C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "hpdg_tables_1d": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "hpdg_tables_face": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "hpdg_launch_count": (C.c_long, [_vp]),
     "hpdg_uses_uniform_kernel": (C.c_int, [_vp, C.c_int]),
     "hpdg_time_apply_device": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.POINTER(C.c_float)]),
@@ -114,6 +115,15 @@ def tables_1d(p):
     if lib().hpdg_tables_1d(p, nodes.ctypes.data, M.ctypes.data, S.ctypes.data, t.ctypes.data, g.ctypes.data):
         raise HpdgError(lib().hpdg_last_error(None).decode())
     return nodes, M, S, t, g
+
+
+def tables_face(pe, po, kind):
+    """(coupling (pe+1) x (po+1), own-side coupling or None) of a conforming (kind 0) / hanging (kinds 1..4) face (host only)"""
+    out = np.zeros((pe + 1, po + 1))
+    own = np.zeros((pe + 1, pe + 1)) if kind in (1, 2) else None
+    if lib().hpdg_tables_face(pe, po, kind, out.ctypes.data, own.ctypes.data if own is not None else None):
+        raise HpdgError(lib().hpdg_last_error(None).decode())
+    return out, own
 
 
 class HpdgError(RuntimeError):

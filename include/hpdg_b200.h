@@ -204,6 +204,11 @@ int hpdg_loop_solve_device(hpdg_ctx* ctx, int form, double damping, int pre, int
  * (qkgllocalbasis.hh:222-234), exact mass int l_i l_j and stiffness int l_i' l_j' (n x n row-major, n = p + 1), l_i(s) and l_i'(s)
  * at the end points s = 0, 1 ([2][n]).  Any output may be NULL. */
 int hpdg_tables_1d(int degree, double* nodes, double* mass, double* stiffness, double* end_values, double* end_derivatives);
+/* Host-only: the tangential coupling (M^ee)^-1 int_I l^e_i(tau) l^o_j(tau_o(tau)) dtau of a face between elements of degree pe and po.
+ * kind 0: conforming face (I = the whole side: the L2 projection of the neighbour's trace, variableipdg.hh:326-361); 1 / 2: e is the
+ * coarse side of a hanging face, I = low / high half of its side; 3 / 4: e is the fine side on the low / high half of the neighbour's
+ * side (sfipdg.hh:472-491).  out: (pe+1) x (po+1) row-major.  own (kinds 1, 2; may be NULL): (pe+1) x (pe+1), the same with l^e_j. */
+int hpdg_tables_face(int pe, int po, int kind, double* out, double* own);
 long hpdg_launch_count(const hpdg_ctx* ctx);      /* kernels launched so far by this context */
 int hpdg_uses_uniform_kernel(const hpdg_ctx* ctx, int level);
 /* time `reps` back-to-back operator applies with CUDA events on the context stream; ms per apply */

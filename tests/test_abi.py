@@ -3,6 +3,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -51,3 +52,31 @@ def test_product_does_not_touch_oracle():
             if f.endswith((".cu", ".cc", ".hpp", ".h", ".py", ".hh")) or f == "Makefile":
                 txt = open(os.path.join(dp, f)).read()
                 assert "hpdg_oracle" not in txt and "orc_" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_face_coupling_tables_reproduce_polynomials(hp):
+    # host-only check of the product's tangential face couplings (csrc/tables.cc), no GPU: an L2 projection onto P_pe reproduces
+    # polynomials of degree <= pe, so for q of degree <= min(pe, po) the coupling applied to the neighbour's nodal values of q must
+    # give this element's nodal values of q -- on conforming faces (variableipdg.hh:326-361) and on the fine / coarse side of a
+    # hanging face (sfipdg.hh:472-491: the neighbour sees the intersection through tau_o = (tau + {0,1}) / 2 resp. 2 tau - {0,1}).
+    rng = np.random.default_rng(2)
+    for pe in range(1, 8):
+        xe = hp.tables_1d(pe)[0]
+        for po in range(1, 8):
+            xo = hp.tables_1d(po)[0]
+            q = np.polynomial.Polynomial(rng.standard_normal(min(pe, po) + 1))
+            P, _ = hp.tables_face(pe, po, 0)
+            assert np.abs(P @ q(xo) - q(xe)).max() < 1e-12
+            for half in (0, 1):
+                # e fine on the low / high half of o's side: o's coordinate of e's point tau is (tau + half) / 2
+                P, _ = hp.tables_face(pe, po, 3 + half)
+                assert np.abs(P @ q(xo) - q((xe + half) / 2)).max() < 1e-12
+            # e coarse: its two fine neighbours hold q(tau) at tau = (x_o + half) / 2; the two half couplings together project q
+            tot = np.zeros(pe + 1)
+            own = np.zeros((pe + 1, pe + 1))
+            for half in (0, 1):
+                P, Q = hp.tables_face(pe, po, 1 + half)
+                tot += P @ q((xo + half) / 2)
+                own += Q
+            assert np.abs(tot - q(xe)).max() < 1e-12
+            assert np.abs(own - np.eye(pe + 1)).max() < 1e-12
